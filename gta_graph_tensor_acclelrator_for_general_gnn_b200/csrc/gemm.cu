@@ -1,0 +1,51 @@
+// gta_gemm_f32: COMP_MM applynode entry point.  Chooses the tcgen05 3xTF32 kernel
+// (gemm_tc.cu) when its tile rules hold, else the FFMA kernel (gemm_simt.cu).
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace gta {
+int gemm_simt_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
+                     int k, int f, cudaStream_t st);
+int attn_project_launch(const float* z, int64_t ldz, int64_t num_rows, int f, const float* al, const float* ar,
+                        int heads, float* el, float* er, cudaStream_t st);
+// returns GTA_ERR_UNSUPPORTED when the shape is outside the tensor-core kernel's rules
+int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
+                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, cudaStream_t st);
+}  // namespace gta
+
+using namespace gta;
+
+extern "C" {
+
+// 0 = auto (tensor cores when eligible), 1 = force FFMA, 2 = force tcgen05 (error if ineligible)
+static int g_gemm_mode = 0;
+int gta_gemm_set_mode(int mode) {
+  if (mode < 0 || mode > 2) return GTA_ERR_INVALID;
+  g_gemm_mode = mode;
+  return GTA_OK;
+}
+int gta_gemm_get_mode(void) { return g_gemm_mode; }
+
+int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
+                 int32_t k, int32_t f, const float* al, const float* ar, int32_t heads, float* el, float* er,
+                 void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (num_rows == 0) return GTA_OK;
+  GTA_REQUIRE(x && w && z, "gta_gemm_f32: null pointer");
+  GTA_REQUIRE(num_rows > 0 && k > 0 && f > 0, "gta_gemm_f32: non-positive shape");
+  GTA_REQUIRE(ldx >= k && ldw >= f && ldz >= f, "gta_gemm_f32: leading dimension smaller than the row");
+  const bool want_attn = (el && al) || (er && ar);
+  GTA_REQUIRE(!want_attn || heads >= 1, "gta_gemm_f32: heads must be >= 1 when el/er are requested");
+  if (g_gemm_mode != 1) {
+    int rc = gemm_tc_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, al, ar, heads, el, er, st);
+    if (rc == GTA_OK) return GTA_OK;
+    if (rc != GTA_ERR_UNSUPPORTED || g_gemm_mode == 2) return rc;
+  }
+  int rc = gemm_simt_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, st);
+  if (rc != GTA_OK) return rc;
+  if (want_attn) return attn_project_launch(z, ldz, num_rows, f, al, ar, heads, el, er, st);
+  return GTA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+"""Device-resident graph: CSR by destination, tile tables, partition, reorder, work list.
+
+Host-side mirror of the reference's graph preprocessing entry points
+(code/preprocessing.py:12-72 ``calculate_sparsity`` / ``cal_min_sparsity`` / ``gen_size``),
+re-implemented on device through the C ABI, plus the CSR / partition / reorder steps the
+north star adds.  torch owns memory and streams only; every computation is a
+``libgta_b200.so`` call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+DEFAULT_CHUNK = 1024   # edges per work item (fixed => deterministic reduction shape)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gta_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+@dataclass
+class Schedule:
+    """Work list of the aggregation kernels (gta_schedule_build)."""
+    items: torch.Tensor      # int32 [num_items, 4]
+    num_items: int
+    num_slots: int
+    chunk: int
+    row_begin: int
+    row_end: int
+
+
+@dataclass
+class DeviceGraph:
+    num_nodes: int
+    num_edges: int
+    indptr: torch.Tensor                  # int64 [rows+1]
+    indices: torch.Tensor                 # int32 [E]  (source ids, ascending inside a row)
+    perm: torch.Tensor | None = None      # int64 [E]  input position of CSR edge k
+    num_sources: int | None = None        # rows of the source-side tables (== num_nodes unless partitioned)
+    schedules: dict = field(default_factory=dict)
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.indptr.shape[0]) - 1
+
+    def schedule(self, chunk: int = DEFAULT_CHUNK) -> Schedule:
+        if chunk not in self.schedules:
+            self.schedules[chunk] = build_schedule(self.indptr, 0, self.num_rows, self.num_edges, chunk)
+        return self.schedules[chunk]
+
+
+def csr_from_coo(dst, src, num_nodes: int, want_perm: bool = False) -> DeviceGraph:
+    """COO (int32 device tensors, or numpy arrays which are uploaded) -> DeviceGraph."""
+    lib = _cabi.load()
+    if isinstance(dst, np.ndarray):
+        dst = torch.from_numpy(np.ascontiguousarray(dst, dtype=np.int32)).cuda()
+    if isinstance(src, np.ndarray):
+        src = torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)).cuda()
+    _require_cuda(dst, src)
+    if dst.dtype != torch.int32 or src.dtype != torch.int32:
+        raise TypeError("dst/src must be int32")
+    if dst.shape != src.shape or dst.dim() != 1:
+        raise ValueError("dst and src must be 1-D and of equal length")
+    dst = dst.contiguous()
+    src = src.contiguous()
+    e = int(dst.shape[0])
+    dev = dst.device
+    indptr = torch.empty(num_nodes + 1, dtype=torch.int64, device=dev)
+    indices = torch.empty(max(e, 1), dtype=torch.int32, device=dev)[:e]
+    perm = torch.empty(max(e, 1), dtype=torch.int64, device=dev)[:e] if want_perm else None
+    ws_bytes = lib.gta_csr_build_workspace(e, num_nodes)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _cabi.check(lib.gta_csr_build(_cabi.ptr(dst), _cabi.ptr(src), e, num_nodes, _cabi.ptr(indptr),
+                                  _cabi.ptr(indices), _cabi.ptr(perm), _cabi.ptr(ws), ws_bytes, _stream()),
+                "gta_csr_build")
+    return DeviceGraph(num_nodes, e, indptr, indices, perm, num_sources=num_nodes)
+
+
+def build_schedule(indptr: torch.Tensor, row_begin: int, row_end: int, num_edges: int,
+                   chunk: int = DEFAULT_CHUNK) -> Schedule:
+    lib = _cabi.load()
+    _require_cuda(indptr)
+    rows = row_end - row_begin
+    cap = int(lib.gta_schedule_max_items(rows, num_edges, chunk))
+    items = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=indptr.device)
+    ws_bytes = lib.gta_schedule_workspace(rows)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=indptr.device)
+    counts = (C.c_int64 * 2)()
+    _cabi.check(lib.gta_schedule_build(_cabi.ptr(indptr), row_begin, row_end, chunk, _cabi.ptr(items), cap, counts,
+                                       _cabi.ptr(ws), ws_bytes, _stream()), "gta_schedule_build")
+    n_items, n_slots = int(counts[0]), int(counts[1])
+    return Schedule(items[:max(n_items, 1)], n_items, n_slots, chunk, row_begin, row_end)
+
+
+# ---- tile tables: calculate_sparsity / cal_min_sparsity / gen_size -------------------------
+
+def gen_size(start: int, end: int) -> list[int]:
+    """Tile-size list ``start*k`` up to the first value >= end (code/preprocessing.py:65-72)."""
+    sizes = [start]
+    k = 1
+    while sizes[-1] < end:
+        k += 1
+        sizes.append(start * k)
+    return sizes
+
+
+def calculate_sparsity(g: DeviceGraph, row: int, col: int = 1, tile_begin: int = 0,
+                       tile_end: int | None = None) -> torch.Tensor:
+    """Device ``calculate_sparsity(row, col=1, ...)`` (code/preprocessing.py:12-40): int32
+    ``[tiles, N]`` table of per-(row tile x 1 column) non-zero counts of ``A - diag``."""
+    if col != 1:
+        raise NotImplementedError("the reference only ever calls col = 1 (code/preprocessing.py:86)")
+    if row <= 0:
+        raise ValueError("row tile size must be positive")
+    lib = _cabi.load()
+    tiles = -(-g.num_nodes // row)
+    tile_end = tiles if tile_end is None else tile_end
+    out = torch.empty((max(tile_end - tile_begin, 0), g.num_nodes), dtype=torch.int32, device=g.indptr.device)
+    _cabi.check(lib.gta_tile_nnz(_cabi.ptr(g.indptr), _cabi.ptr(g.indices), g.num_nodes, row, tile_begin, tile_end,
+                                 _cabi.ptr(out), _stream()), "gta_tile_nnz")
+    return out
+
+
+def cal_min_sparsity(g: DeviceGraph, tile_size: int, workspace_bytes: int = 256 << 20) -> int:
+    """Maximum tile nnz for one tile size (code/preprocessing.py:53-63; the reference's name
+    says min, its code takes the max), streamed in bounded batches of row tiles."""
+    lib = _cabi.load()
+    need = 256 + 4 * g.num_nodes
+    ws_bytes = max(need, min(workspace_bytes, 256 + 4 * g.num_nodes * (-(-g.num_nodes // tile_size))))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.indptr.device)
+    out = C.c_int32(0)
+    _cabi.check(lib.gta_tile_nnz_max(_cabi.ptr(g.indptr), _cabi.ptr(g.indices), g.num_nodes, tile_size, _cabi.ptr(ws),
+                                     ws_bytes, C.byref(out), _stream()), "gta_tile_nnz_max")
+    return int(out.value)
+
+
+def tile_tables(g: DeviceGraph, start: int, end: int):
+    """``sizelist`` and ``maxlist`` as the preprocessing CLI writes them (preprocessing.py:83-96)."""
+    sizes = gen_size(start, end)
+    return sizes, [cal_min_sparsity(g, s) for s in sizes]
+
+
+# ---- partition / reorder -----------------------------------------------------------------------
+
+def partition_bounds(g: DeviceGraph, parts: int) -> torch.Tensor:
+    """int64 [parts+1] destination-range bounds balanced by edge count."""
+    lib = _cabi.load()
+    bounds = torch.empty(parts + 1, dtype=torch.int64, device=g.indptr.device)
+    _cabi.check(lib.gta_partition(_cabi.ptr(g.indptr), g.num_rows, parts, _cabi.ptr(bounds), _stream()),
+                "gta_partition")
+    return bounds
+
+
+def degree_reorder(g: DeviceGraph) -> torch.Tensor:
+    """int64 [N] permutation, ``perm[new] = old``, descending in-degree, stable."""
+    lib = _cabi.load()
+    perm = torch.empty(g.num_rows, dtype=torch.int64, device=g.indptr.device)
+    ws_bytes = lib.gta_reorder_workspace(g.num_rows)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.indptr.device)
+    _cabi.check(lib.gta_reorder(_cabi.ptr(g.indptr), g.num_rows, _cabi.ptr(perm), _cabi.ptr(ws), ws_bytes, _stream()),
+                "gta_reorder")
+    return perm
+
+
+def slice_rows(g: DeviceGraph, row_begin: int, row_end: int) -> DeviceGraph:
+    """Destination rows [row_begin,row_end) as a zero-based local CSR (sources keep global ids)."""
+    e0 = int(g.indptr[row_begin].item())
+    e1 = int(g.indptr[row_end].item())
+    indptr = (g.indptr[row_begin:row_end + 1] - e0).contiguous()
+    indices = g.indices[e0:e1].contiguous()
+    return DeviceGraph(g.num_nodes, e1 - e0, indptr, indices, None, num_sources=g.num_sources)

@@ -1,0 +1,154 @@
+"""Loader / validator for the message-passing ISA programs the reference interpreter emits.
+
+Input format = the YAML ``interpret()`` writes to ``Results/Insts/<net>-<ds>-<layer>-<map>.yaml``
+(vTCAD/code/interpreter.py:809-853): a list of fused blocks, each a list of instruction
+records ``{TYPE, ID, Hardware_Unit, Tile_Times, Tile_Size, Feature_Length, [Weight_Size],
+Dependency{RAW,WAR}, Enable{RAW,WAR}}`` (gen_comp_inst :145-161, gen_load_inst :244-259,
+gen_store_inst :281-296).  ``Enable`` mirrors ``Dependency`` and no consumer reads it
+(SURVEY.md Appendix E), so it is ignored here.
+
+The program is treated as READ-ONLY (the reference's fusion pass shares dict objects
+between ``Dependency`` and ``Enable``, interpreter.py:627-632).
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+
+import yaml
+
+COMP_TYPES = ("MM", "ADD", "MUL", "SF", "NONE")
+OP_TYPES = ("applynode", "applyedge", "scatter", "gather")
+LOAD_TYPES = ("LOAD_N", "LOAD_E", "LOAD_W")
+STORE_TYPES = ("STORE_N", "STORE_E")
+
+_ID_PART = re.compile(r"(\d+)_(applynode|applyedge|scatter|gather)_(\d+)")
+
+
+class IsaError(ValueError):
+    """Malformed or unknown instruction (the executor rejects, never crashes)."""
+
+
+@dataclass(frozen=True)
+class OpRef:
+    op: int        # position in the op-graph list (the reference indexes op_info by position)
+    kind: str      # applynode | applyedge | scatter | gather
+    slot: int      # input slot for LOAD_*, 0 for COMP / STORE
+
+
+@dataclass
+class Instruction:
+    type: str
+    id: str
+    unit: str
+    tile_times: int
+    tile_size: int
+    feature_length: int
+    weight_size: int | None
+    raw: list = field(default_factory=list)   # [(TYPE, ID, [a, b])]
+    war: list = field(default_factory=list)
+    refs: tuple = ()
+
+    @property
+    def is_load(self) -> bool:
+        return self.type in LOAD_TYPES
+
+    @property
+    def is_store(self) -> bool:
+        return self.type in STORE_TYPES
+
+    @property
+    def is_comp(self) -> bool:
+        return self.type.startswith("COMP_")
+
+    @property
+    def comp_types(self) -> tuple:
+        """('MUL', 'ADD') for COMP_MUL_COMP_ADD, ('MM',) for COMP_MM."""
+        if not self.is_comp:
+            return ()
+        return tuple(p for p in self.type.split("_") if p != "COMP")
+
+
+def parse_id(inst_id: str) -> tuple:
+    refs = tuple(OpRef(int(m.group(1)), m.group(2), int(m.group(3))) for m in _ID_PART.finditer(inst_id))
+    rebuilt = "_".join(f"{r.op}_{r.kind}_{r.slot}" for r in refs)
+    if not refs or rebuilt != inst_id:
+        raise IsaError(f"unparseable instruction ID {inst_id!r}")
+    return refs
+
+
+def _parse_instruction(rec: dict) -> Instruction:
+    try:
+        typ = rec["TYPE"]
+        inst = Instruction(
+            type=typ, id=rec["ID"], unit=rec.get("Hardware_Unit", ""),
+            tile_times=int(rec["Tile_Times"]), tile_size=int(rec["Tile_Size"]),
+            feature_length=int(rec["Feature_Length"]),
+            weight_size=rec.get("Weight_Size"),
+            raw=[(d["TYPE"], d["ID"], list(d["Times"])) for d in rec["Dependency"]["RAW"]],
+            war=[(d["TYPE"], d["ID"], list(d["Times"])) for d in rec["Dependency"]["WAR"]],
+        )
+    except (KeyError, TypeError) as exc:
+        raise IsaError(f"malformed instruction record: {exc!r}") from exc
+    inst.refs = parse_id(inst.id)
+    if typ == "FETCH":
+        raise IsaError("FETCH must have been removed by fuse_fetch (interpreter.py:768-806)")
+    if inst.is_load or inst.is_store:
+        if len(inst.refs) != 1:
+            raise IsaError(f"{typ} {inst.id}: load/store names exactly one op")
+    elif inst.is_comp:
+        ct = inst.comp_types
+        if len(ct) != len(inst.refs) or any(c not in COMP_TYPES for c in ct):
+            raise IsaError(f"unknown compute instruction {typ} {inst.id}")
+    else:
+        raise IsaError(f"unknown instruction TYPE {typ!r}")
+    return inst
+
+
+@dataclass
+class Program:
+    blocks: list        # list[list[Instruction]]
+
+    @classmethod
+    def from_records(cls, records) -> "Program":
+        if not isinstance(records, list) or any(not isinstance(b, list) for b in records):
+            raise IsaError("an ISA program is a list of blocks, each a list of instructions")
+        return cls([[_parse_instruction(r) for r in block] for block in records])
+
+    @classmethod
+    def load(cls, path: str) -> "Program":
+        with open(path) as f:
+            return cls.from_records(yaml.safe_load(f))
+
+    def block_ops(self, op_info) -> list:
+        """Op positions of every block, scatters included.
+
+        Compute ops are named by their COMP instruction.  A scatter leaves no COMP after
+        fuse_fetch; it is attributed to the block that loads its input or stores its output,
+        else (producer and consumers all inside one block) to its producer's block."""
+        owner = {}
+        for b, block in enumerate(self.blocks):
+            for inst in block:
+                for r in inst.refs:
+                    if inst.is_comp or r.kind == "scatter":
+                        owner.setdefault(r.op, b)
+        for pos, op in enumerate(op_info):
+            if pos in owner or op["TYPE"] != "scatter":
+                continue
+            prods = [p for p in op["INPUT"]["input_g_list"] if p != -1]
+            if prods and prods[0] in owner:
+                owner[pos] = owner[prods[0]]
+        missing = [p for p in range(len(op_info)) if p not in owner]
+        if missing:
+            raise IsaError(f"ops {missing} of the op graph appear in no block of the program")
+        out = [[] for _ in self.blocks]
+        for pos in sorted(owner):
+            out[owner[pos]].append(pos)
+        return out
+
+    def stored_ops(self) -> list:
+        """Per block: op positions whose output a STORE_* materialises."""
+        return [[inst.refs[0].op for inst in block if inst.is_store] for block in self.blocks]
+
+    def summary(self) -> list:
+        return [[(i.type, i.id, i.tile_times, i.tile_size, i.feature_length) for i in b] for b in self.blocks]

@@ -1,0 +1,215 @@
+"""Thin Python wrappers over the compute entry points of libgta_b200.so.
+
+One function per ISA instruction kind: argument checking that needs
+tensor metadata happens here, everything else in the C library.  Tensors are fp32, CUDA,
+row-major with a row pitch that is a multiple of 4 elements (``alloc_table``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from .graph import DeviceGraph, Schedule, _require_cuda, _stream
+
+LEAKY_SLOPE = 0.2
+
+
+def pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def alloc_table(rows: int, width: int, device, zero: bool = False) -> torch.Tensor:
+    """[rows, width] fp32 view of a buffer whose row pitch is padded to 16 bytes."""
+    ld = pad4(width)
+    buf = (torch.zeros if zero else torch.empty)((max(rows, 1), ld), dtype=torch.float32, device=device)
+    return buf[:rows, :width]
+
+
+def to_table(x: torch.Tensor) -> torch.Tensor:
+    """Return ``x`` if its layout is already legal, else a padded copy (pad columns zeroed)."""
+    if x.dtype != torch.float32:
+        raise TypeError("fp32 tables only")
+    if x.dim() == 1:
+        x = x[:, None]
+    if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(0) >= x.shape[1]:
+        return x
+    t = alloc_table(x.shape[0], x.shape[1], x.device, zero=True)
+    t.copy_(x)
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a row-major 2-D table")
+    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
+
+
+def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: torch.Tensor | None = None,
+         out: torch.Tensor | None = None):
+    """COMP_MM applynode: ``Z = X.W`` and optionally the fused GAT ops 1/2 ``el = Z.Al``,
+    ``er = Z.Ar``.  Returns ``Z`` or ``(Z, el, er)``."""
+    lib = _cabi.load()
+    _require_cuda(x, w, al, ar)
+    n, k = x.shape
+    k2, f = w.shape
+    if k != k2:
+        raise ValueError(f"X is [{n},{k}] but W is [{k2},{f}]")
+    w = w.contiguous()
+    z = out if out is not None else alloc_table(n, f, x.device)
+    heads = 0
+    el = er = None
+    if al is not None or ar is not None:
+        heads = int((al if al is not None else ar).shape[1])
+        if al is not None:      # el/er are dense [N,H]
+            al = al.contiguous()
+            el = torch.empty((n, heads), dtype=torch.float32, device=x.device)
+        if ar is not None:
+            ar = ar.contiguous()
+            er = torch.empty((n, heads), dtype=torch.float32, device=x.device)
+    _cabi.check(lib.gta_gemm_f32(_cabi.ptr(x), _ld(x), _cabi.ptr(w), f, _cabi.ptr(z), _ld(z), n, k, f,
+                                 _cabi.ptr(al), _cabi.ptr(ar), heads, _cabi.ptr(el), _cabi.ptr(er), _stream()),
+                "gta_gemm_f32")
+    if al is None and ar is None:
+        return z
+    return z, el, er
+
+
+def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, rowden: torch.Tensor | None = None,
+              epilogue: int = _cabi.EPI_NONE, sched: Schedule | None = None, out: torch.Tensor | None = None):
+    """COMP_MUL_COMP_ADD / COMP_ADD gather: ``out[i] = epi(sum_k w[k] (x) x[src k])``;
+    with ``rowden`` the weight is ``w[k,h] / rowden[i,h]`` (GAT op 9)."""
+    lib = _cabi.load()
+    _require_cuda(x, w, rowden)
+    sched = sched or g.schedule()
+    f = int(x.shape[1])
+    rows = sched.row_end - sched.row_begin
+    o = out if out is not None else alloc_table(rows, f, x.device)
+    wmode, wh = _cabi.W_NONE, 0
+    if w is not None:
+        if w.dim() == 1:
+            w = w[:, None]
+        w = w.contiguous()
+        wh = int(w.shape[1])
+        wmode = _cabi.W_EDGE_DIV if rowden is not None else _cabi.W_EDGE
+        if rowden is not None:
+            rowden = rowden.contiguous()
+    partials = None
+    if sched.num_slots:
+        partials = torch.empty(sched.num_slots * f, dtype=torch.float32, device=x.device)
+    _cabi.check(lib.gta_aggregate_f32(_cabi.ptr(sched.items), sched.num_items, sched.num_slots, _cabi.ptr(g.indptr),
+                                      _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh, _cabi.ptr(rowden),
+                                      _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
+                                      _cabi.ptr(partials), _stream()), "gta_aggregate_f32")
+    return o
+
+
+class GatWorkspace:
+    """Reusable partial-slot buffer of the single-pass GAT kernel."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, n: int, device):
+        if n == 0:
+            return None
+        if self.buf is None or self.buf.numel() < n or self.buf.device != device:
+            self.buf = torch.empty(n, dtype=torch.float32, device=device)
+        return self.buf
+
+
+_gat_ws = GatWorkspace()
+
+
+def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.Tensor, slope: float = LEAKY_SLOPE,
+                  epilogue: int = _cabi.EPI_ELU, sched: Schedule | None = None, out: torch.Tensor | None = None,
+                  want_stats: bool = False):
+    """GAT ops 3-13 in one pass (online softmax): returns ``out`` or ``(out, rowmax, rowsum)``."""
+    lib = _cabi.load()
+    _require_cuda(el, er, z)
+    sched = sched or g.schedule()
+    f = int(z.shape[1])
+    heads = int(el.shape[1])
+    rows = sched.row_end - sched.row_begin
+    el = el.contiguous()
+    er = er.contiguous()
+    o = out if out is not None else alloc_table(rows, f, z.device)
+    rowmax = rowsum = None
+    if want_stats:
+        rowmax = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
+        rowsum = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
+    stride = int(lib.gta_gat_partial_stride(f, heads))
+    partials = _gat_ws.get(sched.num_slots * stride, z.device)
+    _cabi.check(lib.gta_gat_aggregate_f32(_cabi.ptr(sched.items), sched.num_items, sched.num_slots,
+                                          _cabi.ptr(g.indptr), _cabi.ptr(g.indices), _cabi.ptr(el), _cabi.ptr(er),
+                                          heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o), _ld(o), f, epilogue,
+                                          _cabi.ptr(rowmax), _cabi.ptr(rowsum), _cabi.ptr(partials), _stream()),
+                "gta_gat_aggregate_f32")
+    if want_stats:
+        return o, rowmax, rowsum
+    return o
+
+
+def gat_logits(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, slope: float = LEAKY_SLOPE,
+               stabilize: bool = True):
+    """GAT block [4,5,6,7,8]: returns ``(p [E,H], rowmax [N,H], rowsum [N,H])``."""
+    lib = _cabi.load()
+    _require_cuda(el, er)
+    heads = int(el.shape[1])
+    el = el.contiguous()
+    er = er.contiguous()
+    rows = g.num_rows
+    p = torch.empty((max(g.num_edges, 1), heads), dtype=torch.float32, device=el.device)[:g.num_edges]
+    rowmax = torch.empty((rows, heads), dtype=torch.float32, device=el.device)
+    rowsum = torch.empty((rows, heads), dtype=torch.float32, device=el.device)
+    _cabi.check(lib.gta_gat_logits_f32(_cabi.ptr(g.indptr), _cabi.ptr(g.indices), 0, rows, _cabi.ptr(el),
+                                       _cabi.ptr(er), heads, slope, int(stabilize), _cabi.ptr(p), _cabi.ptr(rowmax),
+                                       _cabi.ptr(rowsum), _stream()), "gta_gat_logits_f32")
+    return p, rowmax, rowsum
+
+
+def edge_binary(g: DeviceGraph, op: int, a: torch.Tensor, kind_a: int, b: torch.Tensor, kind_b: int):
+    lib = _cabi.load()
+    a = a if a.dim() == 2 else a[:, None]
+    b = b if b.dim() == 2 else b[:, None]
+    a, b = a.contiguous(), b.contiguous()
+    wo = max(int(a.shape[1]), int(b.shape[1]))
+    out = torch.empty((max(g.num_edges, 1), wo), dtype=torch.float32, device=a.device)[:g.num_edges]
+    _cabi.check(lib.gta_edge_binary_f32(_cabi.ptr(g.indptr), _cabi.ptr(g.indices), 0, g.num_rows, op,
+                                        _cabi.ptr(a), kind_a, int(a.shape[1]), int(a.shape[1]),
+                                        _cabi.ptr(b), kind_b, int(b.shape[1]), int(b.shape[1]),
+                                        _cabi.ptr(out), wo, wo, _stream()), "gta_edge_binary_f32")
+    return out
+
+
+def edge_unary(g: DeviceGraph, op: int, a: torch.Tensor, kind_a: int, slope: float = LEAKY_SLOPE):
+    lib = _cabi.load()
+    a = a if a.dim() == 2 else a[:, None]
+    a = a.contiguous()
+    wa = int(a.shape[1])
+    out = torch.empty((max(g.num_edges, 1), wa), dtype=torch.float32, device=a.device)[:g.num_edges]
+    _cabi.check(lib.gta_edge_unary_f32(_cabi.ptr(g.indptr), _cabi.ptr(g.indices), 0, g.num_rows, op, slope,
+                                       _cabi.ptr(a), kind_a, wa, wa, _cabi.ptr(out), wa, _stream()),
+                "gta_edge_unary_f32")
+    return out
+
+
+def node_binary(op: int, a: torch.Tensor, b: torch.Tensor):
+    lib = _cabi.load()
+    a = a if a.dim() == 2 else a[:, None]
+    b = b if b.dim() == 2 else b[:, None]
+    wo = max(int(a.shape[1]), int(b.shape[1]))
+    n = int(a.shape[0])
+    out = alloc_table(n, wo, a.device)
+    _cabi.check(lib.gta_node_binary_f32(op, _cabi.ptr(a), int(a.shape[1]), _ld(a), _cabi.ptr(b), int(b.shape[1]),
+                                        _ld(b), _cabi.ptr(out), wo, _ld(out), n, _stream()), "gta_node_binary_f32")
+    return out
+
+
+def node_unary(op: int, a: torch.Tensor, slope: float = LEAKY_SLOPE):
+    lib = _cabi.load()
+    a = a if a.dim() == 2 else a[:, None]
+    n, w = int(a.shape[0]), int(a.shape[1])
+    out = alloc_table(n, w, a.device)
+    _cabi.check(lib.gta_node_unary_f32(op, slope, _cabi.ptr(a), _ld(a), _cabi.ptr(out), _ld(out), w, n, _stream()),
+                "gta_node_unary_f32")
+    return out

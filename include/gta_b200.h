@@ -1,0 +1,193 @@
+/*
+ * gta_b200.h -- C ABI of the B200-native execution backend for the GTA message-passing ISA.
+ *
+ * The reference (Jagnate/GTA_graph_tensor_acclelrator_for_general_GNN) has NO FFI and no
+ * functional execution: its interpreter emits instruction descriptors
+ * (vTCAD/code/interpreter.py:132-163, 215-298, 313-479) that only the cycle model
+ * (vTCAD/code/simulator.py:281-355 calculate_running_cycle) consumes.  Each entry point
+ * below is therefore cited against the ISA instruction / reference function whose work it
+ * performs; the Python host (executor.py) binds them with ctypes exactly as
+ * INTEGRATION.md shows.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with h_;
+ *   - every function returns 0 (GTA_OK) or a GTA_ERR_* code and never throws;
+ *     gta_last_error() returns a thread-local message for the last failure;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and nothing
+ *     synchronises unless stated;
+ *   - the caller owns every buffer; the library allocates nothing persistent;
+ *   - feature tables are row-major with an explicit leading dimension `ld*` in ELEMENTS;
+ *     rows must be 16-byte aligned (ld % 4 == 0 for fp32) so 128-bit loads are legal;
+ *   - adjacency A[row = dst i, col = src j]; CSR rows are destinations, columns ascending
+ *     sources (template/ISA_defination.yaml:35; tile walk simulator.py:262-263,292).
+ */
+#ifndef GTA_B200_H
+#define GTA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTA_OK 0
+#define GTA_ERR_INVALID 1      /* bad argument (null pointer, misaligned ld, unsupported width) */
+#define GTA_ERR_CUDA 2         /* a CUDA call failed; see gta_last_error() */
+#define GTA_ERR_UNSUPPORTED 3  /* legal ISA but no kernel yet */
+#define GTA_ERR_WORKSPACE 4    /* workspace too small */
+
+/* epilogue applied while the aggregated row is still in registers (COMP_SF applynode,
+ * genGraphOP.py:62 GAT op 13; fused per hardware_info.yaml Inst_fused) */
+#define GTA_EPI_NONE 0
+#define GTA_EPI_ELU 1
+#define GTA_EPI_RELU 2
+
+/* how the per-edge weight of gta_aggregate_f32 is formed */
+#define GTA_W_NONE 0       /* plain sum                       (gather ADD, no applyedge)      */
+#define GTA_W_EDGE 1       /* w[k,h]                          (applyedge MUL, GCN op 1 / GAT 11) */
+#define GTA_W_EDGE_DIV 2   /* w[k,h] / rowden[i,h]            (GAT op 9 '/', encoded COMP_MUL)  */
+
+const char* gta_last_error(void);
+int gta_abi_version(void);
+/* number of kernel launches issued by this library since the last reset (for "gpu_launches") */
+int64_t gta_launch_count(void);
+void gta_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Graph preprocessing on device.  Replaces the dense-N^2 host path of
+ * code/preprocessing.py:12-72 (calculate_sparsity, cal_min_sparsity) and supplies the
+ * CSR / partition / reorder steps the north star asks for (no reference implementation;
+ * bit-exact against oracle/gta_oracle.py).
+ * ------------------------------------------------------------------------------------ */
+
+/* COO -> CSR by (dst, src) ascending, stable.  indptr[N+1] int64, indices[E] int32,
+ * perm[E] int64 (may be NULL): perm[k] = input position of CSR edge k. */
+size_t gta_csr_build_workspace(int64_t num_edges, int64_t num_nodes);
+int gta_csr_build(const int32_t* dst, const int32_t* src, int64_t num_edges, int64_t num_nodes,
+                  int64_t* indptr, int32_t* indices, int64_t* perm,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* calculate_sparsity(row = tile_rows, col = 1) (code/preprocessing.py:12-40): counts[tr*N + c]
+ * = number of edges with dst in row tile tr and src == c, self loops excluded.
+ * Only row tiles [tile_begin, tile_end) are produced (counts has (tile_end-tile_begin)*N
+ * entries), so Reddit-size tables can be streamed. */
+int gta_tile_nnz(const int64_t* indptr, const int32_t* indices, int64_t num_nodes,
+                 int64_t tile_rows, int64_t tile_begin, int64_t tile_end,
+                 int32_t* counts, void* stream);
+/* cal_min_sparsity (code/preprocessing.py:53-63): maximum entry of the whole table, computed
+ * in batches of row tiles inside `workspace` (>= num_nodes*4 bytes; more = fewer passes).
+ * *h_max is written on the HOST after an internal stream synchronise. */
+int gta_tile_nnz_max(const int64_t* indptr, const int32_t* indices, int64_t num_nodes,
+                     int64_t tile_rows, void* workspace, size_t workspace_bytes,
+                     int32_t* h_max, void* stream);
+
+/* Destination-range partition balanced by edges: bounds[k] = min r : indptr[r] >= floor(k*E/P). */
+int gta_partition(const int64_t* indptr, int64_t num_nodes, int32_t parts, int64_t* bounds,
+                  void* stream);
+
+/* Degree reorder: perm[new] = old, descending in-degree, stable. */
+size_t gta_reorder_workspace(int64_t num_nodes);
+int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Work list for the aggregation kernels: rows [row_begin,row_end) cut into items of at
+ * most `chunk` edges (deterministic, fixed shape).  items: int32[4] per item =
+ * {row, edge_begin, edge_count, partial_slot (-1 = single-item row)}.
+ * h_counts[0] = number of items, h_counts[1] = number of partial slots (host, after sync). */
+size_t gta_schedule_workspace(int64_t num_rows);
+int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chunk);
+int gta_schedule_build(const int64_t* indptr, int64_t row_begin, int64_t row_end, int32_t chunk,
+                       int32_t* items, int64_t items_capacity, int64_t* h_counts,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * COMP_MM (applynode)  --  interpreter.py:145-161 with Weight_Size; simulator.py:338-341.
+ * Z[N,F] = X[N,K] . W[K,F]  (template/ISA_defination.yaml:28-31, einsum j,ij->i).
+ * Optional fused GAT ops 1,2 (genGraphOP.py:50-51): el = Z.Al, er = Z.Ar with Al,Ar [F,H]
+ * row-major dense; pass NULL to skip.  fp32 in / fp32 out, fp32-accurate (rtol 1e-5).
+ * ------------------------------------------------------------------------------------ */
+int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw,
+                 float* z, int64_t ldz, int64_t num_rows, int32_t k, int32_t f,
+                 const float* al, const float* ar, int32_t heads, float* el, float* er,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * COMP_MUL_COMP_ADD (fused applyedge MUL + gather ADD R; hardware_info.yaml:35-38,
+ * interpreter.py:575-638) and plain COMP_ADD gather (interpreter.py:85-106):
+ *   out[i,:] = epi( sum_{k in row i, ascending src} weight(k) (x) x[src(k),:] )
+ * `w` is [E,wh] (wh = 1 scalar per edge, or wh = heads, head h covering f/wh features);
+ * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Rows are the schedule's items; `partials`
+ * holds n_slots*f floats for rows cut into several items (combined in item order).
+ * ------------------------------------------------------------------------------------ */
+int gta_aggregate_f32(const int32_t* items, int64_t num_items, int64_t num_slots,
+                      const int64_t* indptr, const int32_t* indices,
+                      int32_t wmode, const float* w, int32_t wh, const float* rowden,
+                      const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
+                      int32_t epilogue, float* partials, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GAT edge phase in ONE pass (ops 3-13 of genGraphOP.py:52-62; ISA blocks
+ * [4,5,6,7,8] + [3,9,10,11,12,13] of SURVEY Appendix B3 collapsed, online softmax):
+ *   s = el[i,h] + er[j,h]; e = leaky_relu(s, slope); alpha = softmax_row(e);
+ *   out[i,:] = epi( sum_k alpha[k,h(f)] * z[j,:] )
+ * el [rows,H] is indexed by LOCAL row, er/z by source id.
+ * partials: n_slots * gta_gat_partial_stride(f,H) floats  (= f + roundup4(2*H)).
+ * Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip).
+ * ------------------------------------------------------------------------------------ */
+int32_t gta_gat_partial_stride(int32_t f, int32_t heads);
+int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, int64_t num_slots,
+                          const int64_t* indptr, const int32_t* indices,
+                          const float* el, const float* er, int32_t heads, float slope,
+                          const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                          int32_t epilogue, float* rowmax, float* rowsum,
+                          float* partials, void* stream);
+
+/* GAT block [4,5,6,7,8] alone (COMP_ADD 6, COMP_SF 7, STORE_E 7, COMP_ADD 8 gather):
+ *   p[k,h] = exp(leaky_relu(el[i,h] + er[j,h]) - rowmax[i,h]),  rowsum[i,h] = sum_k p[k,h].
+ * One warp per row (no chunking); p is [E,H] in CSR edge order. */
+int gta_gat_logits_f32(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
+                       int64_t row_end, const float* el, const float* er, int32_t heads,
+                       float slope, int32_t stabilize, float* p, float* rowmax, float* rowsum,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Generic single-op kernels so that ANY legal plan executes.
+ * Edge operands are either materialised [E,width] tensors or VIRTUAL scatters
+ * (FETCH eliminated by fuse_fetch, interpreter.py:768-806): kind 0 = edge tensor,
+ * 1 = node tensor indexed by dst (scatter R), 2 = node tensor indexed by src (scatter C).
+ * ------------------------------------------------------------------------------------ */
+#define GTA_OPND_EDGE 0
+#define GTA_OPND_DST 1
+#define GTA_OPND_SRC 2
+#define GTA_BIN_ADD 0
+#define GTA_BIN_MUL 1
+#define GTA_BIN_DIV 2       /* a / b */
+#define GTA_UN_EXP_LEAKY_RELU 0
+#define GTA_UN_ELU 1
+#define GTA_UN_RELU 2
+#define GTA_UN_COPY 3
+
+/* out[k,:] = a[k,:] (op) b[k,:] over edges of rows [row_begin,row_end); widths wa, wb divide wo
+ * (head broadcast).  COMP_ADD / COMP_MUL applyedge. */
+int gta_edge_binary_f32(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
+                        int64_t row_end, int32_t op,
+                        const float* a, int32_t kind_a, int32_t wa, int64_t lda,
+                        const float* b, int32_t kind_b, int32_t wb, int64_t ldb,
+                        float* out, int32_t wo, int64_t ldo, void* stream);
+/* out[k,:] = f(a[k,:]); COMP_SF applyedge (exp(leaky_relu)) or a materialising scatter (COPY). */
+int gta_edge_unary_f32(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
+                       int64_t row_end, int32_t op, float slope,
+                       const float* a, int32_t kind_a, int32_t wa, int64_t lda,
+                       float* out, int64_t ldo, void* stream);
+/* node elementwise: out = a (op) b  /  out = f(a)  (COMP_ADD/MUL/SF applynode) */
+int gta_node_binary_f32(int32_t op, const float* a, int32_t wa, int64_t lda,
+                        const float* b, int32_t wb, int64_t ldb,
+                        float* out, int32_t wo, int64_t ldo, int64_t num_rows, void* stream);
+int gta_node_unary_f32(int32_t op, float slope, const float* a, int64_t lda, float* out,
+                       int64_t ldo, int32_t width, int64_t num_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTA_B200_H */

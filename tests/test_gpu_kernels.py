@@ -1,0 +1,252 @@
+"""Parity of every CUDA entry point (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import assert_close_rowscale
+from oracle import gta_oracle as O
+from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import _cabi, graph, kernels
+    _cabi.load()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.cabi, ns.graph, ns.k = torch, _cabi, graph, kernels
+    return ns
+
+
+def _dev(T, a):
+    return T.torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+GRAPHS = [
+    ("tiny", 64, 300, 1, 5.0),
+    ("cora", 2708, 10556, 0, 100.0),
+    ("skew", 3000, 90000, 2, 3.0),      # a few very long rows -> multi-item rows with chunk 32/1024
+]
+
+
+def _graph(name, n, e, seed, i0):
+    return synthetic.powerlaw_graph(n, e, seed=seed, i0=i0, name=name)
+
+
+@pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
+def test_csr_build_bit_exact(T, name, n, e, seed, i0):
+    g = _graph(name, n, e, seed, i0)
+    indptr, indices, perm = O.csr_build(g.dst, g.src, n)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n, want_perm=True)
+    assert np.array_equal(dg.indptr.cpu().numpy(), indptr)
+    assert np.array_equal(dg.indices.cpu().numpy(), indices)
+    assert np.array_equal(dg.perm.cpu().numpy(), perm)
+
+
+def test_csr_build_duplicates_and_empty(T):
+    # duplicate edges keep input order (stable); isolated nodes give empty rows
+    dst = np.array([3, 1, 3, 3, 0, 1], dtype=np.int32)
+    src = np.array([2, 0, 2, 1, 4, 0], dtype=np.int32)
+    indptr, indices, perm = O.csr_build(dst, src, 6)
+    dg = T.graph.csr_from_coo(dst, src, 6, want_perm=True)
+    assert np.array_equal(dg.indptr.cpu().numpy(), indptr)
+    assert np.array_equal(dg.indices.cpu().numpy(), indices)
+    assert np.array_equal(dg.perm.cpu().numpy(), perm)
+    empty = T.graph.csr_from_coo(np.zeros(0, np.int32), np.zeros(0, np.int32), 5)
+    assert np.array_equal(empty.indptr.cpu().numpy(), np.zeros(6, np.int64))
+
+
+def test_tile_nnz_against_reference_tables(T, golden_dir):
+    import os
+    for tag in ("g300", "g97"):
+        z = np.load(os.path.join(golden_dir, "tiles", f"{tag}.npz"))
+        n = int(z["num_nodes"])
+        dg = T.graph.csr_from_coo(z["dst"], z["src"], n)
+        for key in z.files:
+            if not key.startswith("table_"):
+                continue
+            sr = int(key.split("_")[1])
+            got = T.graph.calculate_sparsity(dg, sr).cpu().numpy()
+            assert np.array_equal(got, z[key]), f"{tag} tile {sr}"
+            assert T.graph.cal_min_sparsity(dg, sr) == int(z[key].max())
+            # streamed in tiny batches must agree too
+            assert T.graph.cal_min_sparsity(dg, sr, workspace_bytes=256 + 4 * n) == int(z[key].max())
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 8])
+def test_partition_and_reorder_bit_exact(T, parts):
+    g = _graph("skew", 3000, 90000, 2, 3.0)
+    indptr, _, _ = O.csr_build(g.dst, g.src, g.num_nodes)
+    dg = T.graph.csr_from_coo(g.dst, g.src, g.num_nodes)
+    assert np.array_equal(T.graph.partition_bounds(dg, parts).cpu().numpy(), O.partition_bounds(indptr, parts))
+    assert np.array_equal(T.graph.degree_reorder(dg).cpu().numpy(), O.degree_reorder(indptr))
+
+
+@pytest.mark.parametrize("chunk", [32, 1024])
+def test_schedule_covers_every_edge_once(T, chunk):
+    g = _graph("skew", 3000, 90000, 2, 3.0)
+    indptr, _, _ = O.csr_build(g.dst, g.src, g.num_nodes)
+    dg = T.graph.csr_from_coo(g.dst, g.src, g.num_nodes)
+    s = dg.schedule(chunk)
+    items = s.items.cpu().numpy()[:s.num_items]
+    deg = np.diff(indptr)
+    want_items = np.maximum(1, -(-deg // chunk))
+    assert s.num_items == int(want_items.sum())
+    assert s.num_slots == int(want_items[want_items > 1].sum())
+    assert np.all(items[:, 2] <= chunk)
+    cover = np.zeros(g.num_edges, np.int32)
+    for r, b, c, slot in items:
+        cover[b:b + c] += 1
+        assert indptr[r] <= b and b + c <= indptr[r + 1]
+        assert (slot >= 0) == (deg[r] > chunk)
+    assert np.all(cover == 1)
+    slots = items[items[:, 3] >= 0, 3]
+    assert np.array_equal(np.sort(slots), np.arange(s.num_slots))
+
+
+@pytest.mark.parametrize("n,k,f", [(2708, 1433, 128), (1000, 602, 128), (513, 128, 64), (300, 64, 16), (77, 500, 128),
+                                   (260, 256, 256)])
+def test_gemm_fp32(T, n, k, f):
+    rng = np.random.default_rng(n + k)
+    x = rng.standard_normal((n, k), dtype=np.float32)
+    w = synthetic.glorot(rng, k, f)
+    xd = T.k.to_table(_dev(T, x))
+    z = T.k.gemm(xd, _dev(T, w)).cpu().numpy()
+    z64 = O.gemm(x, w)
+    scale = np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64)
+    assert_close_rowscale(z, z64, scale, what=f"gemm {n}x{k}x{f}")
+
+
+@pytest.mark.parametrize("heads", [1, 4, 8, 16])
+def test_gemm_attention_projections(T, heads):
+    n, k, f = 700, 602, 128
+    x, w, al, ar = synthetic.gat_tensors(n, k, f, heads, seed=3, dense_attention=(heads == 4))
+    z, el, er = T.k.gemm(T.k.to_table(_dev(T, x)), _dev(T, w), _dev(T, al), _dev(T, ar))
+    z64 = O.gemm(x, w)
+    zs = np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64)
+    assert_close_rowscale(z.cpu().numpy(), z64, zs, what="Z")
+    assert_close_rowscale(el.cpu().numpy(), z64 @ al.astype(np.float64), zs @ np.abs(al).astype(np.float64), what="el")
+    assert_close_rowscale(er.cpu().numpy(), z64 @ ar.astype(np.float64), zs @ np.abs(ar).astype(np.float64), what="er")
+
+
+@pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
+@pytest.mark.parametrize("f", [16, 64, 128, 256, 500])
+@pytest.mark.parametrize("chunk", [32, 1024])
+def test_aggregate_scalar_weight(T, name, n, e, seed, i0, f, chunk):
+    g = _graph(name, n, e, seed, i0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    rng = np.random.default_rng(f)
+    x = rng.standard_normal((n, f), dtype=np.float32)
+    w = synthetic.gcn_edge_norm(indptr, indices)
+    xd = T.k.to_table(_dev(T, x))
+    got = T.k.aggregate(dg, xd, _dev(T, w), sched=dg.schedule(chunk)).cpu().numpy()
+    want = O.spmm(indptr, indices, w, x)
+    scale = O.spmm(indptr, indices, np.abs(w), np.abs(x))
+    assert_close_rowscale(got, want, scale, what=f"aggregate f={f} chunk={chunk}")
+    # plain gather ADD (no weights) and run-to-run bitwise reproducibility
+    plain = T.k.aggregate(dg, xd, None, sched=dg.schedule(chunk))
+    again = T.k.aggregate(dg, xd, None, sched=dg.schedule(chunk))
+    assert T.torch.equal(plain, again)
+    assert_close_rowscale(plain.cpu().numpy(), O.spmm(indptr, indices, None, x),
+                          O.spmm(indptr, indices, None, np.abs(x)), what="plain gather")
+
+
+@pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
+@pytest.mark.parametrize("f,heads", [(128, 4), (128, 8), (128, 16), (128, 1), (64, 4), (64, 16), (16, 4), (16, 2), (256, 8)])
+@pytest.mark.parametrize("chunk", [32, 1024])
+def test_gat_single_pass(T, name, n, e, seed, i0, f, heads, chunk):
+    g = _graph(name, n, e, seed, i0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    x, w, al, ar = synthetic.gat_tensors(n, 96, f, heads, seed=seed)
+    ref = O.gat_layer(indptr, indices, x, w, al, ar)
+    z32 = ref["Z"].astype(np.float32)
+    el32 = ref["el"].astype(np.float32)
+    er32 = ref["er"].astype(np.float32)
+    # oracle on the SAME fp32 inputs the kernel sees
+    r2 = _gat_from_z(indptr, indices, z32, el32, er32)
+    out, rowmax, rowsum = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)),
+                                            sched=dg.schedule(chunk), want_stats=True)
+    out2 = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)), sched=dg.schedule(chunk))
+    assert T.torch.equal(out, out2), "not bitwise reproducible"
+    scale = O.gat_rowscale(indptr, indices, z32.astype(np.float64), r2["alpha"])
+    assert_close_rowscale(out.cpu().numpy(), r2["Y"], scale, what=f"GAT f={f} H={heads} chunk={chunk}")
+    np.testing.assert_allclose(rowmax.cpu().numpy(), r2["rowmax"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(rowsum.cpu().numpy(), r2["S"], rtol=2e-5)
+
+
+def _gat_from_z(indptr, indices, z, el, er):
+    """Oracle edge phase on given (fp32-rounded) Z, el, er, evaluated in fp64."""
+    rows = O.row_ids(indptr)
+    z, el, er = z.astype(np.float64), el.astype(np.float64), er.astype(np.float64)
+    lr = O.leaky_relu(el[rows] + er[indices])
+    mx = O.segment_max(lr, indptr)
+    mx = np.where(np.isfinite(mx), mx, 0)
+    p = np.exp(lr - mx[rows])
+    s = O.segment_sum(p, indptr)
+    alpha = p / s[rows]
+    o = O.segment_sum(O.head_broadcast(alpha, z.shape[1]) * z[indices], indptr)
+    return {"p": p, "S": s, "rowmax": mx, "alpha": alpha, "O": o, "Y": O.elu(o)}
+
+
+@pytest.mark.parametrize("heads,f", [(4, 128), (16, 128), (4, 64)])
+def test_gat_two_block_path(T, heads, f):
+    """ISA blocks [4,5,6,7,8] then [3,9,10,11,12,13] as separate kernels (STORE_E p honoured)."""
+    g = _graph("skew", 3000, 90000, 2, 3.0)
+    n = g.num_nodes
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((n, f), dtype=np.float32)
+    el = rng.standard_normal((n, heads), dtype=np.float32)
+    er = rng.standard_normal((n, heads), dtype=np.float32)
+    r = _gat_from_z(indptr, indices, z, el, er)
+    p, rowmax, rowsum = T.k.gat_logits(dg, _dev(T, el), _dev(T, er))
+    np.testing.assert_allclose(p.cpu().numpy(), r["p"], rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(rowsum.cpu().numpy(), r["S"], rtol=2e-5)
+    out = T.k.aggregate(dg, T.k.to_table(_dev(T, z)), p, rowden=rowsum, epilogue=T.cabi.EPI_ELU)
+    scale = O.gat_rowscale(indptr, indices, z.astype(np.float64), r["alpha"])
+    assert_close_rowscale(out.cpu().numpy(), r["Y"], scale, rtol=2e-5, what="two-block GAT")
+
+
+def test_generic_edge_and_node_ops(T):
+    g = _graph("tiny", 64, 300, 1, 5.0)
+    n = g.num_nodes
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    rows = O.row_ids(indptr)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((n, 4), dtype=np.float32)
+    b = rng.standard_normal((n, 4), dtype=np.float32)
+    zt = rng.standard_normal((n, 32), dtype=np.float32)
+    C = T.cabi
+    s = T.k.edge_binary(dg, C.BIN_ADD, _dev(T, a), C.OPND_DST, _dev(T, b), C.OPND_SRC)
+    np.testing.assert_array_equal(s.cpu().numpy(), a[rows] + b[indices])
+    p = T.k.edge_unary(dg, C.UN_EXP_LEAKY_RELU, s, C.OPND_EDGE)
+    np.testing.assert_allclose(p.cpu().numpy(), np.exp(O.leaky_relu(a[rows] + b[indices])), rtol=1e-6)
+    m = T.k.edge_binary(dg, C.BIN_MUL, p, C.OPND_EDGE, _dev(T, zt), C.OPND_SRC)
+    np.testing.assert_allclose(m.cpu().numpy(), np.repeat(p.cpu().numpy(), 8, axis=1) * zt[indices], rtol=1e-6)
+    zs = T.k.edge_unary(dg, C.UN_COPY, _dev(T, zt), C.OPND_SRC)
+    np.testing.assert_array_equal(zs.cpu().numpy(), zt[indices])
+    q = T.k.node_binary(C.BIN_DIV, _dev(T, zt), _dev(T, np.abs(a) + 1))
+    np.testing.assert_allclose(q.cpu().numpy(), zt / np.repeat(np.abs(a) + 1, 8, axis=1), rtol=1e-6)
+    e = T.k.node_unary(C.UN_ELU, _dev(T, zt))
+    np.testing.assert_allclose(e.cpu().numpy(), O.elu(zt), rtol=1e-6, atol=1e-7)
+
+
+def test_errors_are_loud(T):
+    g = _graph("tiny", 64, 300, 1, 5.0)
+    dg = T.graph.csr_from_coo(g.dst, g.src, g.num_nodes)
+    x = T.torch.zeros((64, 6), device="cuda")           # width not a multiple of 4
+    with pytest.raises(T.cabi.GtaError):
+        T.k.aggregate(dg, x)
+    with pytest.raises(T.cabi.GtaUnsupported):            # per-head width 2 has no kernel yet
+        T.k.gat_aggregate(dg, T.torch.zeros((64, 8), device="cuda"), T.torch.zeros((64, 8), device="cuda"),
+                          T.torch.zeros((64, 16), device="cuda"))
+    with pytest.raises(RuntimeError):
+        T.k.aggregate(dg, T.torch.zeros((64, 8)))          # CPU tensor: no CPU fallback
