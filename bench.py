@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Headline benchmark: GTEPS of one GAT layer on a Reddit-shape synthetic graph, executed from
+the ISA program the reference's compiler.py -> interpreter.py emit (tests/golden/isa), on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+N > 1 is launched by torchrun (one rank per GPU); the graph is partitioned by destination range
+(balanced by edges), each layer all-gathers Z and er over NCCL.  Prints ONE JSON line (rank 0).
+
+A step = one full GAT layer (ops 0-13 of genGraphOP.py:49-62): GEMM X.W with the el/er
+projections, single-pass edge softmax + aggregation + ELU.  ``value`` = E / step time with the
+inputs resident in HBM; ``e2e`` = the same through ``execute()`` with HOST (pinned) features
+copied in and the result copied out inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (shape, network, layer, reorder, opgraph yaml, isa yaml, heads)
+    "reddit-gat": ("reddit", "GAT", 1, False, "opgraph/GAT-reddit-restamped-h4.yaml",
+                   "isa/GAT-reddit-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml", 4),
+    "flickr-gat": ("flickr", "GAT", 1, False, "opgraph/GAT-flickr-layer1-original.yaml",
+                   "isa/GAT-flickr-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml", 16),
+    "cora-gat": ("cora", "GAT", 1, False, "opgraph/GAT-cora-restamped-h4.yaml",
+                 "isa/GAT-cora-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml", 4),
+    "flickr-gcn": ("flickr", "GCN", 1, True, "opgraph/GCN-flickr-layer1-trans.yaml",
+                   "isa/GCN-flickr-layer1-trans__0_1-2-3.yaml", 0),
+    "reddit-gcn": ("reddit", "GCN", 1, True, "opgraph/GCN-reddit-layer1-trans.yaml",
+                   "isa/GCN-reddit-layer1-trans__0_1-2-3.yaml", 0),
+}
+F_OUT = 128
+METRIC = "GTEPS per GAT/GCN layer (Reddit shape)"
+
+
+def load_yaml(rel):
+    import yaml
+    with open(os.path.join(REPO, "tests", "golden", rel)) as f:
+        return yaml.safe_load(f)
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(network, n, e, fin, f, h, s=4):
+    """SURVEY.md section 8d, no-reuse gather model.  Returns (layer bytes, dominant-kernel bytes)."""
+    gemm = n * fin * s + fin * f * s + n * f * s
+    if network == "GAT":
+        gemm += 2 * f * h * s + 2 * n * h * s
+        edge = (n + 1) * 4 + e * 4 + e * h * s + n * h * s + e * f * s + n * f * s
+    else:
+        edge = (n + 1) * 4 + e * (4 + s) + e * f * s + n * f * s
+    return gemm + edge, edge
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.uuid, self.proc, self.lines = uuid, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.uuid, f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement on the host cores (the reference has no functional path)
+# ------------------------------------------------------------------------------------------
+
+def cpu_layer_sample(network, indptr_s, indices_s, row0, x, w, al, ar, edge_w_s):
+    """One layer on the host: full GEMM (numpy BLAS, all threads) + the edge phase of the sample
+    rows (C oracle, OpenMP).  Returns (t_gemm, t_edge) in seconds."""
+    from oracle import c_oracle
+    t0 = time.perf_counter()
+    z = x @ w
+    if network == "GAT":
+        el = z @ al
+        er = z @ ar
+    t1 = time.perf_counter()
+    rows = indptr_s.shape[0] - 1
+    if network == "GAT":
+        c_oracle.gat_edge_phase(indptr_s, indices_s, el[row0:row0 + rows], er, z, dtype=np.float32)
+    else:
+        c_oracle.spmm(indptr_s, indices_s, edge_w_s, z, dtype=np.float32)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def host_sample_csr(coo, n, sample_rows):
+    """CSR of destination rows [0, sample_rows) of a host edge list (numpy)."""
+    from oracle import gta_oracle as O
+    keep = coo.dst < sample_rows
+    d, s = coo.dst[keep], coo.src[keep]
+    indptr, indices, _ = O.csr_build(d, s, sample_rows)
+    return indptr, indices
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the CPU restatement of the path on this box's host cores, bounded sample."""
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
+    from oracle import c_oracle
+    shape, network, layer, reorder, _, _, heads = wl
+    n, e, fin = synthetic.SHAPES[shape]
+    coo = synthetic.shape_graph(shape)
+    x, w, al, ar = synthetic.gat_tensors(n, fin, F_OUT, max(heads, 1), seed=0)
+    # sample = first rows holding about sample_edges edges
+    deg = np.bincount(coo.dst, minlength=n)
+    cum = np.cumsum(deg)
+    sample_rows = int(min(n, max(64, np.searchsorted(cum, args.cpu_sample_edges) + 1)))
+    indptr_s, indices_s = host_sample_csr(coo, n, sample_rows)
+    e_s = int(indptr_s[-1])
+    ew = None
+    if network == "GCN":
+        d = np.maximum(deg, 1).astype(np.float64)
+        rows = np.repeat(np.arange(sample_rows), np.diff(indptr_s))
+        ew = (1.0 / np.sqrt(d[rows] * d[indices_s])).astype(np.float32)
+    c_oracle.load()
+    times = []
+    for it in range(args.warmup + args.steps):
+        tg, te = cpu_layer_sample(network, indptr_s, indices_s, 0, x, w, al, ar, ew)
+        if it >= args.warmup:
+            times.append((tg, te))
+    tg = float(np.mean([t[0] for t in times]))
+    te = float(np.mean([t[1] for t in times]))
+    full = tg + te * e / max(e_s, 1)
+    value = e / full / 1e9
+    cores = os.cpu_count()
+    sample = (f"full GEMM {n}x{fin}x{F_OUT} (numpy BLAS) + edge phase of dst rows [0,{sample_rows}) = {e_s} of {e} "
+              f"edges (C oracle, OpenMP {c_oracle.threads()} threads); layer time extrapolated as "
+              f"t_gemm + t_edge*E/E_sample")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tg + te) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(args, wl)},
+            "cpu_baseline": {"value": value, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(args, wl):
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
+    shape, network, layer, reorder, _, isa_rel, heads = wl
+    n, e, fin = synthetic.SHAPES[shape]
+    h = f" H={args.heads or heads}" if network == "GAT" else ""
+    return (f"{network} layer{layer} ({'trans' if reorder else 'original'}) on {shape}-shape synthetic graph "
+            f"N={n} E={e} Fin={fin} F={F_OUT}{h} fp32, program {os.path.basename(isa_rel)}")
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit-gat", choices=sorted(WORKLOADS))
+    ap.add_argument("--heads", type=int, default=0, help="override the attention width H")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample-edges", type=int, default=4_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="honour every STORE_* of the program")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import _cabi, executor, graph, isa, kernels, synthetic
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import dist as gdist
+
+    lib = _cabi.load()      # no CUDA extension => fail here, loudly
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    shape, network, layer, reorder, op_rel, isa_rel, heads = wl
+    heads = args.heads or heads
+    n, e, fin = synthetic.SHAPES[shape]
+    op_info = load_yaml(op_rel)
+    program = isa.Program.from_records(load_yaml(isa_rel))
+
+    # ---- inputs (synthetic, deterministic) ---------------------------------------------------
+    t_setup = time.perf_counter()
+    coo = synthetic.shape_graph(shape)
+    x_h, w_h, al_h, ar_h = synthetic.gat_tensors(n, fin, F_OUT, max(heads, 1), seed=0)
+    full = graph.csr_from_coo(coo.dst, coo.src, n)
+    torch.cuda.synchronize()
+    if world > 1:
+        part = gdist.make_partition(full, rank, world)
+        g, r0, r1 = part.local, part.row_begin, part.row_end
+        exchange = gdist.SourceExchange(part)
+    else:
+        g, r0, r1, exchange = full, 0, n, None
+    edge_w = None
+    if network == "GCN":
+        deg = (full.indptr[1:] - full.indptr[:-1]).clamp(min=1).to(torch.float64)
+        rows = torch.repeat_interleave(torch.arange(r0, r1, device=dev), (full.indptr[r0 + 1:r1 + 1] - full.indptr[r0:r1]))
+        src_glob = full.indices[int(full.indptr[r0]):int(full.indptr[r1])].long()
+        edge_w = (1.0 / torch.sqrt(deg[rows] * deg[src_glob])).to(torch.float32)[:, None].contiguous()
+        del rows, src_glob
+    host_csr = None
+    if rank == 0 and not args.no_cpu_baseline:
+        host_csr = (full.indptr.cpu().numpy(), None)
+        deg_h = np.diff(host_csr[0])
+        sample_rows = int(min(n, max(64, np.searchsorted(np.cumsum(deg_h), args.cpu_sample_edges) + 1)))
+        e_s = int(host_csr[0][sample_rows])
+        host_csr = (host_csr[0][:sample_rows + 1].copy(), full.indices[:e_s].cpu().numpy(), sample_rows, deg_h)
+    if world > 1:
+        del full
+        torch.cuda.empty_cache()
+    g.schedule()
+    x_pin = torch.from_numpy(x_h[r0:r1]).pin_memory()
+    x_d = kernels.to_table(x_pin.to(dev))
+    w_d, al_d, ar_d = (torch.from_numpy(a).to(dev) for a in (w_h, al_h, ar_h))
+    weights = {0: w_d, 1: al_d, 2: ar_d} if network == "GAT" else {0: w_d}
+    final_op = len(op_info) - 1
+    edge_inputs = {2: edge_w} if network == "GCN" else None
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    def step(x_dev):
+        return executor.execute(program, op_info, g, {0: x_dev}, weights, edge_inputs, network=network,
+                                is_reorder=reorder, fuse_across_blocks=not args.no_fuse, source_table=exchange,
+                                check_shapes=(world == 1))[final_op]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        y = step(x_d)
+    barrier()
+
+    # ---- timed region: K steps, resident inputs ---------------------------------------------
+    props = torch.cuda.get_device_properties(dev)
+    sampler = ClockSampler("GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local_rank))
+    if rank == 0:
+        sampler.start()
+    kernels.EVENT_LOG = []
+    lib.gta_launch_count_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        y = step(x_d)
+    ev1.record()
+    barrier()
+    launches = int(lib.gta_launch_count())
+    elapsed_ms = ev0.elapsed_time(ev1)
+    log, kernels.EVENT_LOG = kernels.EVENT_LOG, None
+    clocks = sampler.stop() if rank == 0 else None
+    per_kernel = {}
+    for name, a, b in log:
+        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = e / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host features in, result out, through execute() -------------------------------
+    y_pin = torch.empty((r1 - r0, F_OUT), dtype=torch.float32).pin_memory()
+    x_stage = kernels.alloc_table(r1 - r0, fin, dev, zero=True)
+
+    def e2e_step():
+        x_stage.copy_(x_pin, non_blocking=True)
+        out = step(x_stage)
+        y_pin.copy_(out, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    ev0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.e2e_steps
+    h2d = int(x_pin.numel() * 4)
+    d2h = int(y_pin.numel() * 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    dom = "gta_gat_aggregate_f32" if network == "GAT" else "gta_aggregate_f32"
+    dom_ms = float(np.mean(per_kernel[dom])) if dom in per_kernel else None
+    e_local = g.num_edges
+    _, dom_bytes = algorithmic_bytes(network, r1 - r0, e_local, fin, F_OUT, max(heads, 1))
+    layer_bytes, _ = algorithmic_bytes(network, n, e, fin, F_OUT, max(heads, 1))
+    peak, peak_src = measured_peak()
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(f"{args.workload}:{dom}")
+    roofline = None
+    if dom_ms:
+        ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                    "kernel_ms": dom_ms,
+                    "layer_frac": layer_bytes / (ms_per_step * 1e-3) / 1e9 / peak / max(world, 1),
+                    "kernel_ms_by_name": {k: float(np.mean(v)) for k, v in per_kernel.items()}}
+
+    cpu_baseline = None
+    if host_csr is not None:
+        indptr_s, indices_s, sample_rows, deg_h = host_csr
+        ew_s = None
+        if network == "GCN":
+            d = np.maximum(deg_h, 1).astype(np.float64)
+            rows = np.repeat(np.arange(sample_rows), np.diff(indptr_s))
+            ew_s = (1.0 / np.sqrt(d[rows] * d[indices_s])).astype(np.float32)
+        from oracle import c_oracle
+        c_oracle.load()
+        cpu_layer_sample(network, indptr_s[:65], indices_s[:int(indptr_s[64])], 0, x_h, w_h, al_h, ar_h, ew_s)  # warm
+        tg, te = cpu_layer_sample(network, indptr_s, indices_s, 0, x_h, w_h, al_h, ar_h, ew_s)
+        e_s = int(indptr_s[-1])
+        full_t = tg + te * e / max(e_s, 1)
+        cpu_baseline = {"value": e / full_t / 1e9, "unit": "GTEPS", "cores": os.cpu_count(), "kind": "port",
+                        "threads": c_oracle.threads(),
+                        "sample": (f"full GEMM (numpy BLAS, {tg:.2f} s) + edge phase of dst rows [0,{sample_rows}) = "
+                                   f"{e_s} of {e} edges (C oracle fp32, {te:.2f} s); layer time extrapolated as "
+                                   f"t_gemm + t_edge*E/E_sample")}
+
+    line = {"metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, wl),
+                       "parallelism": f"dst-range partition x{world}" + (", NCCL all-gather of Z and er per layer" if world > 1 else ""),
+                       "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
+                           e * 4 / 1e6, n * fin * 4 / 1e6, n * F_OUT * 4 / 1e6),
+                       "fuse_across_blocks": not args.no_fuse, "graph_checksum": coo.checksum(),
+                       "setup_s": round(t_setup, 1)},
+            "clocks": clocks,
+            "e2e": {"value": e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "per rank: features X (pinned host) -> device, execute(), result -> pinned host; "
+                            "the CSR (static graph structure) and the weights stay resident"},
+            "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

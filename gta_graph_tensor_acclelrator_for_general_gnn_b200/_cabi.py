@@ -36,6 +36,7 @@ SIGNATURES = {
     "gta_tile_nnz": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "gta_tile_nnz_max": (C.c_int, [_p, _p, _i64, _i64, _p, _sz, C.POINTER(_i32), _p]),
     "gta_partition": (C.c_int, [_p, _i64, _i32, _p, _p]),
+    "gta_remap_sources": (C.c_int, [_p, _i64, _p, _i32, _i64, _p, _p]),
     "gta_reorder_workspace": (_sz, [_i64]),
     "gta_reorder": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "gta_schedule_workspace": (_sz, [_i64]),

@@ -19,7 +19,7 @@ __device__ __forceinline__ float fetch_operand(const float* __restrict__ a, int 
 __device__ __forceinline__ float binary_op(int op, float a, float b) {
   if (op == GTA_BIN_ADD) return a + b;
   if (op == GTA_BIN_MUL) return a * b;
-  return a / b;
+  return b != 0.f ? a / b : 0.f;   // rows without edges: sum 0 / sum 0 is pinned to 0 (oracle gat_layer)
 }
 
 __device__ __forceinline__ float unary_op(int op, float slope, float a) {

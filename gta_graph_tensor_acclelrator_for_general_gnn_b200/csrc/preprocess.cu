@@ -179,6 +179,25 @@ __global__ void item_fill_kernel(const int64_t* __restrict__ indptr, int64_t row
   }
 }
 
+// ---- source-id remap for destination-partitioned execution ---------------------------------
+// The all-gathered source table is [parts, stride, F] (every rank's rows padded to `stride`),
+// so global source id j owned by rank p becomes p*stride + (j - bounds[p]).  Monotonic in j:
+// the ascending-source reduction order of every row is preserved.
+__global__ void remap_sources_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ bounds,
+                                     int parts, int64_t stride, int32_t* __restrict__ out) {
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  int64_t step = int64_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += step) {
+    int64_t j = in[i];
+    int lo = 0, hi = parts;            // largest p with bounds[p] <= j
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (bounds[mid] <= j) lo = mid; else hi = mid;
+    }
+    out[i] = int32_t(int64_t(lo) * stride + (j - bounds[lo]));
+  }
+}
+
 static int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   int64_t cap = int64_t(kNumSMs) * 16;
@@ -304,6 +323,18 @@ int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm, void* w
   count_launch(4);
   low_word_kernel<<<grid_for(num_nodes, 256), 256, 0, stream>>>(keys_out, num_nodes, perm);
   GTA_CHECK_LAUNCH("low_word_kernel");
+  return GTA_OK;
+}
+
+int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* bounds, int32_t parts,
+                      int64_t stride, int32_t* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (num_edges == 0) return GTA_OK;
+  GTA_REQUIRE(indices && bounds && out, "gta_remap_sources: null pointer");
+  GTA_REQUIRE(parts >= 1 && stride >= 1 && int64_t(parts) * stride < (int64_t(1) << 31),
+              "gta_remap_sources: parts*stride must fit int32");
+  remap_sources_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(indices, num_edges, bounds, parts, stride, out);
+  GTA_CHECK_LAUNCH("remap_sources_kernel");
   return GTA_OK;
 }
 

@@ -1,0 +1,481 @@
+"""``execute()``: functional execution of a GTA ISA program on B200.
+
+This is the entry point that sits next to the reference's ``simulate()`` in the
+``compile -> interpret -> simulate`` flow (vTCAD/code/test.py:10-15): it consumes exactly what
+``simulate`` consumes -- the op graph (``Network/...yaml``) and the instruction program
+(``Results/Insts/...yaml``, interpreter.py:809-853) -- and, where the simulator only counts
+cycles (simulator.py:281-355), it computes the tensors.
+
+How a program becomes kernels
+-----------------------------
+The op graph gives the dataflow, the ISA program gives the fused blocks and the points
+where a tensor is materialised (``STORE_*`` / ``LOAD_*``).  Blocks are run in dependency
+order (the reference sorts them by size, compiler.py:60, which is not an execution order).
+Inside a block every op first becomes a *lazy value*; scatters stay virtual exactly as
+``fuse_fetch`` removed their FETCH (interpreter.py:768-806).  Values are forced at the
+block's ``STORE_*`` instructions, and forcing pattern-matches onto the fused kernels:
+
+=============================================  ==========================================
+lazy expression                                  kernel (include/gta_b200.h)
+=============================================  ==========================================
+MM(x, W) [+ MM(., Al), MM(., Ar) same block]     gta_gemm_f32 (el/er fused)
+gather(MUL(scatterC(x), w))  COMP_MUL_COMP_ADD   gta_aggregate_f32 (W_EDGE)
+gather(MUL(scatterC(x), p / scatterR(S)))        gta_aggregate_f32 (W_EDGE_DIV)
+SF(ADD(scatterR(el), scatterC(er))) + its sum    gta_gat_logits_f32
+whole GAT edge phase (ops 3..13 / trans 3..12)   gta_gat_aggregate_f32 (single pass)
+applynode SF after a gather                      epilogue of the aggregate kernel
+anything else                                    gta_edge_* / gta_node_* generic kernels
+=============================================  ==========================================
+
+``fuse_across_blocks=True`` (default) treats a ``STORE_E``/``LOAD_E`` pair whose tensor has
+no consumer outside the program as a dead store, which lets the two GAT edge blocks
+collapse into the single-pass kernel; ``False`` honours every ``STORE_*`` of the program.
+Plans that would materialise an ``E x F`` tensor larger than ``max_edge_bytes`` are refused
+(Reddit would need 58.7 GB per tensor).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import torch
+import yaml
+
+from . import _cabi, kernels
+from .graph import DeviceGraph
+from .isa import IsaError, Program
+
+#: COMP_TYPE -> arithmetic where the YAML alone is ambiguous (the reference only names ops)
+DEFAULT_SEMANTICS = {
+    ("applyedge", "SF"): "exp_leaky_relu",   # GAT op 7: template/GAT_op.png 'f' then 'exp'
+    ("applynode", "SF"): "elu",              # GAT op 13; activation unspecified upstream, pinned
+    ("applyedge", "MUL"): "mul", ("applynode", "MUL"): "mul",
+    ("applyedge", "ADD"): "add", ("applynode", "ADD"): "add",
+}
+#: MULs that are DIVIDES in GAT (template/GAT_op.png '/'), keyed (network, isReorder) -> {op: kind}
+NETWORK_SEMANTICS = {
+    ("GAT", False): {9: "div"},      # alpha = p / S[dst]        inputs [7, 10]
+    ("GAT", True): {11: "rdiv"},     # O = O' / S                inputs [9 (S), 10 (O')]
+}
+
+
+class ExecutionError(RuntimeError):
+    pass
+
+
+def read_yaml(path: str):
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+def repair_op_graph(op_info, network: str | None, is_reorder: bool):
+    """Return producer lists per op position with the one wiring quirk repaired:
+    genGraphOP's GAT-original op 10 lists op 7 as input but consumes op 8's row sums
+    (genGraphOP.py:59 vs V2/GAT_Cora.yaml:250-252)."""
+    prods = [list(op["INPUT"]["input_g_list"]) for op in op_info]
+    if (network == "GAT" and not is_reorder and len(op_info) == 14 and prods[10] == [7]
+            and op_info[8]["TYPE"] == "gather" and op_info[10]["TYPE"] == "scatter"):
+        prods[10] = [8]
+    return prods
+
+
+# ---- lazy values -----------------------------------------------------------------------------
+
+@dataclass(eq=False)
+class Value:
+    kind: str                    # node | edge | scatter | edge_expr | gather | node_expr | mm
+    op: str = ""                 # arithmetic: add mul div rdiv exp_leaky_relu elu relu
+    args: tuple = ()
+    side: str = ""               # scatter: 'R' (dst) or 'C' (src)
+    width: int = 0
+    tensor: torch.Tensor | None = None
+    weight: torch.Tensor | None = None
+    pos: int = -1
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def forced(self) -> bool:
+        return self.tensor is not None
+
+    @property
+    def on_edges(self) -> bool:
+        return self.kind in ("edge", "scatter", "edge_expr")
+
+
+class _Run:
+    def __init__(self, graph: DeviceGraph, opts):
+        self.g = graph
+        self.o = opts
+        self.kernel_log = []
+
+    # -- helpers
+    def _guard(self, width: int, what: str):
+        need = self.g.num_edges * width * 4
+        if need > self.o["max_edge_bytes"]:
+            raise ExecutionError(
+                f"plan materialises {what} as an E x {width} edge tensor ({need / 2**30:.1f} GiB > "
+                f"max_edge_bytes); fuse it (COMP_MUL_COMP_ADD) or raise the budget")
+
+    def _operand(self, v: Value):
+        """(tensor, operand kind) for the generic edge kernels, scatters stay virtual."""
+        if v.kind == "scatter":
+            t = self.force(v.args[0])
+            if v.side == "C":
+                t = self.o["source_table"](t)
+            return t, (_cabi.OPND_DST if v.side == "R" else _cabi.OPND_SRC)
+        return self.force(v), _cabi.OPND_EDGE
+
+    def _is_softmax_numerator(self, v: Value):
+        """p = SF(ADD(scatterR(el), scatterC(er))) -> (el_value, er_value) or None."""
+        if v.kind != "edge_expr" or v.op != "exp_leaky_relu":
+            return None
+        s = v.args[0]
+        if s.kind != "edge_expr" or s.op != "add" or s.forced:
+            return None
+        a, b = s.args
+        if a.kind == "scatter" and b.kind == "scatter" and {a.side, b.side} == {"R", "C"}:
+            return (a.args[0], b.args[0]) if a.side == "R" else (b.args[0], a.args[0])
+        return None
+
+    @staticmethod
+    def _split_mul(v: Value):
+        """MUL(scatterC(x), w) in either order -> (x_value, w_value) or None."""
+        if v.kind != "edge_expr" or v.op != "mul" or v.forced:
+            return None
+        a, b = v.args
+        for wide, other in ((a, b), (b, a)):
+            if wide.kind == "scatter" and wide.side == "C" and not wide.forced and other.width <= wide.width:
+                return wide.args[0], other
+        return None
+
+    # -- forcing
+    def force(self, v: Value, epilogue: int = _cabi.EPI_NONE) -> torch.Tensor:
+        if v.forced:
+            if epilogue != _cabi.EPI_NONE:
+                raise ExecutionError("internal: epilogue requested on a forced value")
+            return v.tensor
+        k = kernels
+        if v.kind == "mm":
+            x = k.to_table(self.force(v.args[0]))
+            v.tensor = k.gemm(x, v.weight)
+            self.kernel_log.append(("gta_gemm_f32", v.pos))
+        elif v.kind == "scatter":
+            self._guard(v.width, f"scatter op {v.pos}")
+            t, kind = self._operand(v)
+            v.tensor = k.edge_unary(self.g, _cabi.UN_COPY, t, kind)
+            self.kernel_log.append(("gta_edge_unary_f32:copy", v.pos))
+        elif v.kind == "edge_expr":
+            v.tensor = self._force_edge_expr(v)
+        elif v.kind == "gather":
+            v.tensor = self._force_gather(v, epilogue)
+            return v.tensor
+        elif v.kind == "node_expr":
+            v.tensor = self._force_node_expr(v)
+        else:
+            raise ExecutionError(f"cannot force value kind {v.kind}")
+        if epilogue != _cabi.EPI_NONE:
+            raise ExecutionError("internal: epilogue requested on a non-gather value")
+        return v.tensor
+
+    def _force_edge_expr(self, v: Value) -> torch.Tensor:
+        k = kernels
+        sm = self._is_softmax_numerator(v)
+        if sm is not None:
+            el, er = self.force(sm[0]), self.o["source_table"](self.force(sm[1]))
+            p, rowmax, rowsum = k.gat_logits(self.g, el, er, self.o["slope"], self.o["stabilize"])
+            v.extra["rowsum"], v.extra["rowmax"] = rowsum, rowmax
+            self.kernel_log.append(("gta_gat_logits_f32", v.pos))
+            return p
+        self._guard(v.width, f"applyedge op {v.pos}")
+        if v.op in ("exp_leaky_relu", "elu", "relu"):
+            t, kind = self._operand(v.args[0])
+            code = {"exp_leaky_relu": _cabi.UN_EXP_LEAKY_RELU, "elu": _cabi.UN_ELU, "relu": _cabi.UN_RELU}[v.op]
+            self.kernel_log.append(("gta_edge_unary_f32", v.pos))
+            return k.edge_unary(self.g, code, t, kind, self.o["slope"])
+        a, b = v.args
+        if v.op == "rdiv":
+            a, b = b, a
+        ta, ka = self._operand(a)
+        tb, kb = self._operand(b)
+        code = {"add": _cabi.BIN_ADD, "mul": _cabi.BIN_MUL, "div": _cabi.BIN_DIV, "rdiv": _cabi.BIN_DIV}[v.op]
+        self.kernel_log.append(("gta_edge_binary_f32", v.pos))
+        return k.edge_binary(self.g, code, ta, ka, tb, kb)
+
+    def _gat_single_pass(self, numer: Value, z_value: Value, epilogue: int, pos: int):
+        sm = self._is_softmax_numerator(numer)
+        el, er = self.force(sm[0]), self.o["source_table"](self.force(sm[1]))
+        z = self.o["source_table"](kernels.to_table(self.force(z_value)))
+        self.kernel_log.append(("gta_gat_aggregate_f32", pos))
+        return kernels.gat_aggregate(self.g, el, er, z, self.o["slope"], epilogue)
+
+    def _force_gather(self, v: Value, epilogue: int) -> torch.Tensor:
+        k = kernels
+        src = v.args[0]
+        # S = gather(p) where p came out of the logits kernel: the row sums are already there
+        if src.forced and "rowsum" in src.extra and epilogue == _cabi.EPI_NONE:
+            return src.extra["rowsum"]
+        if src.kind == "scatter" and src.side == "C" and not src.forced:
+            x = self.o["source_table"](k.to_table(self.force(src.args[0])))
+            self.kernel_log.append(("gta_aggregate_f32:sum", v.pos))
+            return k.aggregate(self.g, x, None, None, epilogue)
+        sp = self._split_mul(src)
+        if sp is not None:
+            xv, wv = sp
+            # w = p / scatterR(gather(p)) with p still lazy  ->  the whole GAT edge phase, one pass
+            if (wv.kind == "edge_expr" and wv.op == "div" and not wv.forced):
+                p, den = wv.args
+                if (den.kind == "scatter" and den.side == "R" and den.args[0].kind == "gather"
+                        and den.args[0].args[0] is p and not p.forced and not den.args[0].forced
+                        and self._is_softmax_numerator(p) is not None and xv.width % p.width == 0
+                        and (xv.width // p.width) % 4 == 0):
+                    return self._gat_single_pass(p, xv, epilogue, v.pos)
+                if den.kind == "scatter" and den.side == "R" and p.width == den.width:
+                    x = self.o["source_table"](k.to_table(self.force(xv)))
+                    pt = self.force(p)
+                    dt = self.force(den.args[0])
+                    if pt.shape[1] == 1 or (x.shape[1] // pt.shape[1]) % 4 == 0:
+                        self.kernel_log.append(("gta_aggregate_f32:w/rowden", v.pos))
+                        return k.aggregate(self.g, x, pt, dt, epilogue)
+            x = self.o["source_table"](k.to_table(self.force(xv)))
+            wt = self.force(wv)
+            if wt.dim() == 1 or wt.shape[1] == 1 or (x.shape[1] // wt.shape[1]) % 4 == 0:
+                self.kernel_log.append(("gta_aggregate_f32:w", v.pos))
+                return k.aggregate(self.g, x, wt, None, epilogue)
+        # generic: materialise the edge tensor and segment-sum it (identity gather)
+        et = k.to_table(self.force(src))
+        if "arange" not in self.g.schedules:
+            self.g.schedules["arange"] = torch.arange(max(self.g.num_edges, 1), dtype=torch.int32, device=et.device)
+        ident = DeviceGraph(self.g.num_nodes, self.g.num_edges, self.g.indptr, self.g.schedules["arange"],
+                            schedules=self.g.schedules)
+        self.kernel_log.append(("gta_aggregate_f32:segment_sum", v.pos))
+        return k.aggregate(ident, et, None, None, epilogue, sched=self.g.schedule())
+
+    def _force_node_expr(self, v: Value) -> torch.Tensor:
+        k = kernels
+        if v.op in ("elu", "relu", "exp_leaky_relu"):
+            a = v.args[0]
+            if (a.kind == "gather" and not a.forced and v.op in ("elu", "relu") and a.extra.get("consumers", 1) == 1
+                    and a.pos not in self.o["wanted"]):
+                a.extra["absorbed"] = True
+                return self.force(a, _cabi.EPI_ELU if v.op == "elu" else _cabi.EPI_RELU)
+            if (a.kind == "node_expr" and not a.forced and v.op in ("elu", "relu") and a.extra.get("consumers", 1) == 1
+                    and a.pos not in self.o["wanted"]):
+                fused = self._try_gat_trans(a, _cabi.EPI_ELU if v.op == "elu" else _cabi.EPI_RELU)
+                if fused is not None:
+                    return fused
+            code = {"elu": _cabi.UN_ELU, "relu": _cabi.UN_RELU, "exp_leaky_relu": _cabi.UN_EXP_LEAKY_RELU}[v.op]
+            self.kernel_log.append(("gta_node_unary_f32", v.pos))
+            return k.node_unary(code, k.to_table(self.force(a)), self.o["slope"])
+        fused = self._try_gat_trans(v, _cabi.EPI_NONE)
+        if fused is not None:
+            return fused
+        a, b = v.args
+        if v.op == "rdiv":
+            a, b = b, a
+        code = {"add": _cabi.BIN_ADD, "mul": _cabi.BIN_MUL, "div": _cabi.BIN_DIV, "rdiv": _cabi.BIN_DIV}[v.op]
+        ta, tb = k.to_table(self.force(a)), k.to_table(self.force(b))
+        self.kernel_log.append(("gta_node_binary_f32", v.pos))
+        return k.node_binary(code, ta, tb)
+
+    def _try_gat_trans(self, v: Value, epilogue: int):
+        """GAT-trans op 11: O = gather(p (x) Z[src]) / gather(p) with p still lazy."""
+        if v.kind != "node_expr" or v.op not in ("div", "rdiv") or v.forced:
+            return None
+        num, den = v.args if v.op == "div" else (v.args[1], v.args[0])
+        if num.kind != "gather" or den.kind != "gather" or num.forced or den.forced:
+            return None
+        sp = self._split_mul(num.args[0])
+        if sp is None:
+            return None
+        xv, wv = sp
+        if wv is not den.args[0] or wv.forced or self._is_softmax_numerator(wv) is None:
+            return None
+        if xv.width % wv.width or (xv.width // wv.width) % 4:
+            return None
+        return self._gat_single_pass(wv, xv, epilogue, v.pos)
+
+
+def _width(nbytes: int) -> int:
+    if nbytes % 4:
+        raise IsaError(f"size_per_feature {nbytes} is not a whole number of fp32 elements")
+    return nbytes // 4
+
+
+def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: dict, edge_inputs: dict | None = None,
+            network: str | None = None, is_reorder: bool = False, semantics: dict | None = None,
+            fuse_across_blocks: bool = True, stabilize: bool = True, slope: float = kernels.LEAKY_SLOPE,
+            max_edge_bytes: int = 8 << 30, outputs=None, source_table=None, return_log: bool = False,
+            check_shapes: bool = True):
+    """Run an ISA program functionally.
+
+    program      : isa.Program, a path to ``Results/Insts/*.yaml`` or the raw list interpret() built
+    op_info      : the op-graph list (``Network/.../*.yaml``) or a path to it
+    graph        : DeviceGraph (CSR by destination)
+    node_inputs  : {op position: [N, F] tensor} for ops with an external graph input
+    weights      : {op position: [Fin, Fout] tensor} for COMP_MM ops
+    edge_inputs  : {op position: [E] or [E, w] tensor} for '-1' entries of input_g_list
+    outputs      : op positions to return (default: ops with an empty output_list)
+    Returns {op position: tensor} (and the kernel log with ``return_log``).
+    """
+    if isinstance(op_info, (str, os.PathLike)):
+        op_info = read_yaml(op_info)
+    if isinstance(program, (str, os.PathLike)):
+        program = Program.load(program)
+    elif isinstance(program, list):
+        program = Program.from_records(program)
+    edge_inputs = edge_inputs or {}
+    sem = dict(NETWORK_SEMANTICS.get((network, bool(is_reorder)), {}))
+    sem.update(semantics or {})
+    for pos, op in enumerate(op_info):
+        if "COMP_TYPE" not in op:
+            raise IsaError(f"op {pos} has no COMP_TYPE (V1/V2-era YAML; re-stamp it, changeyaml.py:18-114)")
+        if op["TYPE"] not in ("applynode", "applyedge", "scatter", "gather"):
+            raise IsaError(f"op {pos}: unknown TYPE {op['TYPE']!r}")
+        if check_shapes:
+            want = graph.num_edges if op["TYPE"] in ("applyedge", "gather") else graph.num_nodes
+            for cnt in op["INPUT"]["feature_number"]:
+                if cnt != want:
+                    raise ExecutionError(f"op {pos} was generated for {cnt} {'edges' if want == graph.num_edges else 'nodes'}"
+                                         f" but the graph has {want} (pass check_shapes=False to run it anyway)")
+    prods = repair_op_graph(op_info, network, is_reorder)
+    block_ops = program.block_ops(op_info)
+    stored = program.stored_ops()
+    n_ops = len(op_info)
+    finals = [p for p in range(n_ops) if not op_info[p]["OUTPUT"]["output_list"]]
+    wanted = list(outputs) if outputs is not None else finals
+
+    # block order: dependency order, ties by program order
+    owner = {p: b for b, ops in enumerate(block_ops) for p in ops}
+    deps = [set() for _ in block_ops]
+    for p in range(n_ops):
+        for q in prods[p]:
+            if q != -1 and owner[q] != owner[p]:
+                deps[owner[p]].add(owner[q])
+    order, done = [], set()
+    while len(order) < len(block_ops):
+        ready = [b for b in range(len(block_ops)) if b not in done and deps[b] <= done]
+        if not ready:
+            raise ExecutionError("the blocks of the program depend on each other cyclically")
+        order.append(ready[0])
+        done.add(ready[0])
+
+    consumers = {p: 0 for p in range(n_ops)}
+    for p in range(n_ops):
+        for q in prods[p]:
+            if q != -1:
+                consumers[q] += 1
+
+    opts = {"slope": float(slope), "stabilize": bool(stabilize), "max_edge_bytes": int(max_edge_bytes),
+            "source_table": source_table or (lambda t: t), "wanted": set(wanted)}
+    run = _Run(graph, opts)
+    env: dict[int, Value] = {}
+
+    def make_value(pos: int) -> Value:
+        op = op_info[pos]
+        typ, comp, order_ = op["TYPE"], op["COMP_TYPE"], op["ORDER"]
+        wout = _width(op["OUTPUT"]["size_per_feature"])
+        args = []
+        for slot, q in enumerate(prods[pos]):
+            if q == -1:
+                if typ in ("applyedge", "gather"):
+                    if pos not in edge_inputs:
+                        raise ExecutionError(f"op {pos} needs an external edge input (edge_inputs[{pos}])")
+                    t = edge_inputs[pos]
+                    t = t if t.dim() == 2 else t[:, None]
+                    args.append(Value("edge", tensor=t.contiguous(), width=int(t.shape[1]), pos=pos))
+                else:
+                    if pos not in node_inputs:
+                        raise ExecutionError(f"op {pos} needs an external node input (node_inputs[{pos}])")
+                    t = node_inputs[pos]
+                    args.append(Value("node", tensor=t, width=int(t.shape[1]), pos=pos))
+            else:
+                args.append(env[q])
+        if not prods[pos]:
+            if pos not in node_inputs:
+                raise ExecutionError(f"op {pos} has no producer: pass node_inputs[{pos}]")
+            t = node_inputs[pos]
+            args.append(Value("node", tensor=t, width=int(t.shape[1]), pos=pos))
+        if typ == "scatter":
+            if order_ not in ("R", "C"):
+                raise IsaError(f"op {pos}: ORDER {order_!r}")
+            return Value("scatter", args=(args[0],), side=order_, width=args[0].width, pos=pos)
+        if typ == "gather":
+            if order_ != "R":
+                raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute",
+                                           f"op {pos}: ORDER C gather needs a CSC walk (not built yet)")
+            return Value("gather", args=(args[0],), width=args[0].width, pos=pos,
+                         extra={"consumers": consumers[pos]})
+        if comp == "MM":
+            if typ == "applyedge":
+                raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute",
+                                           f"op {pos}: COMP_MM on edges (DGN/PNA) is not built yet")
+            if pos not in weights:
+                raise ExecutionError(f"op {pos} is COMP_MM: pass weights[{pos}]")
+            w = weights[pos]
+            if int(w.shape[0]) != args[0].width:
+                raise ExecutionError(f"op {pos}: weight is {tuple(w.shape)} but the input is {args[0].width} wide")
+            return Value("mm", args=(args[0],), weight=w, width=int(w.shape[1]), pos=pos)
+        kind = sem.get(pos, DEFAULT_SEMANTICS.get((typ, comp)))
+        if kind is None:
+            raise IsaError(f"op {pos}: no semantics for {typ} COMP_{comp}")
+        if kind in ("add", "mul", "div", "rdiv") and len(args) != 2:
+            raise IsaError(f"op {pos}: COMP_{comp} needs two inputs, has {len(args)}")
+        width = max(a.width for a in args)
+        return Value("edge_expr" if typ == "applyedge" else "node_expr", op=kind, args=tuple(args), width=width,
+                     pos=pos, extra={"consumers": consumers[pos]})
+
+    def fuse_mm_chain(ops):
+        """MM(x,W) feeding MM(.,Al) and MM(.,Ar) inside one block -> one gta_gemm_f32 call."""
+        for p in ops:
+            v = env[p]
+            if v.kind != "mm" or v.forced:
+                continue
+            kids = [q for q in ops if env[q].kind == "mm" and env[q].args[0] is v and not env[q].forced]
+            if len(kids) == 2 and env[kids[0]].width == env[kids[1]].width and env[kids[0]].width <= 16:
+                x = kernels.to_table(run.force(v.args[0]))
+                z, el, er = kernels.gemm(x, v.weight, env[kids[0]].weight, env[kids[1]].weight)
+                v.tensor, env[kids[0]].tensor, env[kids[1]].tensor = z, el, er
+                run.kernel_log.append(("gta_gemm_f32+el/er", p))
+
+    for b in order:
+        ops = block_ops[b]
+        pending = list(ops)
+        guard = 0
+        while pending:
+            guard += 1
+            if guard > len(ops) * len(ops) + 8:
+                raise ExecutionError(f"block {b} has a dependency cycle")
+            p = pending.pop(0)
+            if any(q != -1 and q not in env for q in prods[p]):
+                pending.append(p)
+                continue
+            env[p] = make_value(p)
+        fuse_mm_chain(ops)
+        for p in stored[b]:
+            v = env[p]
+            needed_outside = p in wanted
+            if fuse_across_blocks and not needed_outside and v.kind != "mm":
+                continue           # dead store unless somebody forces it later
+            if v.extra.get("absorbed"):
+                continue
+            run.force(v)
+    result = {}
+    for p in wanted:
+        result[p] = run.force(env[p])
+    if return_log:
+        return result, run.kernel_log
+    return result
+
+
+def execute_files(tile_size_list, dataset, network, layer, isReorder, graph: DeviceGraph, node_inputs, weights,
+                  edge_inputs=None, root: str = ".", **kw):
+    """Same positional arguments and CWD-relative files as the reference's
+    ``simulate(tile_size_list, dataset, network, layer, isReorder, ...)`` (simulator.py:423-482):
+    reads ``Network/<net>/<net>-<ds>/<net>-<map>/<net>-<layer>-<map>.yaml`` and
+    ``Results/Insts/<net>-<ds>-<layer>-<map>.yaml`` below ``root``."""
+    del tile_size_list   # tiling is an ASIC buffer decision; B200 kernels tile by work item
+    m = "trans" if isReorder else "original"
+    op_path = os.path.join(root, "Network", network, f"{network}-{dataset}", f"{network}-{m}", f"{network}-{layer}-{m}.yaml")
+    isa_path = os.path.join(root, "Results", "Insts", f"{network}-{dataset}-{layer}-{m}.yaml")
+    return execute(isa_path, op_path, graph, node_inputs, weights, edge_inputs, network=network,
+                   is_reorder=isReorder, **kw)

@@ -86,6 +86,12 @@ int gta_tile_nnz_max(const int64_t* indptr, const int32_t* indices, int64_t num_
 int gta_partition(const int64_t* indptr, int64_t num_nodes, int32_t parts, int64_t* bounds,
                   void* stream);
 
+/* Destination-partitioned execution: the all-gathered source table is [parts, stride, F]
+ * (each rank's rows padded to `stride`); out[k] = p*stride + (indices[k] - bounds[p]) with p the
+ * owner of indices[k].  Monotonic, so every row keeps its ascending-source order. */
+int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* bounds,
+                      int32_t parts, int64_t stride, int32_t* out, void* stream);
+
 /* Degree reorder: perm[new] = old, descending in-degree, stable. */
 size_t gta_reorder_workspace(int64_t num_nodes);
 int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm,
@@ -111,6 +117,10 @@ int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw,
                  float* z, int64_t ldz, int64_t num_rows, int32_t k, int32_t f,
                  const float* al, const float* ar, int32_t heads, float* el, float* er,
                  void* stream);
+/* kernel choice of gta_gemm_f32: 0 = auto (tcgen05 3xTF32 when the shape is eligible, else
+ * FFMA), 1 = force the FFMA kernel, 2 = force tcgen05 (GTA_ERR_UNSUPPORTED if ineligible). */
+int gta_gemm_set_mode(int mode);
+int gta_gemm_get_mode(void);
 
 /* ---------------------------------------------------------------------------------------
  * COMP_MUL_COMP_ADD (fused applyedge MUL + gather ADD R; hardware_info.yaml:35-38,
@@ -162,7 +172,7 @@ int gta_gat_logits_f32(const int64_t* indptr, const int32_t* indices, int64_t ro
 #define GTA_OPND_SRC 2
 #define GTA_BIN_ADD 0
 #define GTA_BIN_MUL 1
-#define GTA_BIN_DIV 2       /* a / b */
+#define GTA_BIN_DIV 2       /* a / b, and 0 where b == 0 (rows without edges) */
 #define GTA_UN_EXP_LEAKY_RELU 0
 #define GTA_UN_ELU 1
 #define GTA_UN_RELU 2

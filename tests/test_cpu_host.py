@@ -1,0 +1,95 @@
+"""Host logic that needs no GPU: ISA loader on every golden program, block/op attribution,
+the C-ABI library's exported symbols, and failure modes."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import yaml
+
+from gta_graph_tensor_acclelrator_for_general_gnn_b200 import _cabi, isa
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+with open(os.path.join(GOLDEN, "manifest.json")) as _f:
+    MANIFEST = json.load(_f)
+
+
+def _load(rel):
+    with open(os.path.join(GOLDEN, rel)) as f:
+        return yaml.safe_load(f)
+
+
+@pytest.mark.parametrize("prog", MANIFEST["programs"], ids=[p["file"].split("/")[-1][:-5] for p in MANIFEST["programs"]])
+def test_program_loads_and_blocks_match_the_plan(prog):
+    program = isa.Program.from_records(_load(prog["file"]))
+    op_info = _load(prog["opgraph"])
+    assert len(program.blocks) == len(prog["op_array"])
+    # the op sets recovered from the instruction stream alone equal the plan interpret() was given
+    assert [sorted(b) for b in program.block_ops(op_info)] == [sorted(b) for b in prog["op_array"]]
+    for block in program.blocks:
+        for inst in block:
+            assert inst.type != "FETCH"
+            assert inst.tile_times > 0 and inst.tile_size > 0 and inst.feature_length > 0
+            for _, dep_id, times in inst.raw + inst.war:
+                isa.parse_id(dep_id)
+                assert len(times) == 2
+
+
+def test_fused_instruction_is_recognised():
+    prog = next(p for p in MANIFEST["programs"] if p["file"].endswith("GCN-flickr-layer1-trans__0_1-2-3.yaml"))
+    program = isa.Program.from_records(_load(prog["file"]))
+    fused = [i for i in program.blocks[1] if i.type == "COMP_MUL_COMP_ADD"]
+    assert len(fused) == 1
+    assert fused[0].comp_types == ("MUL", "ADD")
+    assert [(r.op, r.kind) for r in fused[0].refs] == [(2, "applyedge"), (3, "gather")]
+    assert fused[0].tile_times == 175 * 89250           # TR*TC, SURVEY Appendix B1
+    assert program.stored_ops() == [[0], [3]]
+
+
+def test_loader_rejects_garbage():
+    with pytest.raises(isa.IsaError):
+        isa.Program.from_records({"not": "a list"})
+    with pytest.raises(isa.IsaError):
+        isa.Program.from_records([[{"TYPE": "COMP_MM"}]])
+    good = _load(MANIFEST["programs"][0]["file"])
+    with pytest.raises(isa.IsaError):
+        isa.Program.from_records([[dict(good[0][0], TYPE="FETCH")]])
+    with pytest.raises(isa.IsaError):
+        isa.Program.from_records([[dict(good[0][0], ID="0_bogus_0")]])
+
+
+def test_library_exports_every_declared_symbol():
+    """include/gta_b200.h <-> _cabi.SIGNATURES <-> libgta_b200.so agree (no compute calls)."""
+    header = open(os.path.join(REPO, "include", "gta_b200.h")).read()
+    declared = set(re.findall(r"\b(gta_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    if not os.path.exists(_cabi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = _cabi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gta_abi_version() == 1
+    assert lib.gta_schedule_max_items(10, 100, 32) == 14
+    assert lib.gta_gat_partial_stride(128, 4) == 136 and lib.gta_gat_partial_stride(16, 1) == 20
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _cabi.load()
+
+
+def test_cpu_tensors_are_refused():
+    import numpy as np
+    import torch
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import graph
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        graph.csr_from_coo(torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int32), 4)
+    with pytest.raises((RuntimeError, AssertionError)):
+        graph.csr_from_coo(np.zeros(4, np.int32), np.zeros(4, np.int32), 4)   # upload needs a GPU

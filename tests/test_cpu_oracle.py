@@ -1,0 +1,147 @@
+"""The CPU oracle against the reference's own outputs (tests/golden, made by
+oracle/gen_golden.py from the unmodified reference) and against itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+from oracle import gta_oracle as O
+from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(GOLDEN, "manifest.json")) as _f:
+    MANIFEST = json.load(_f)
+
+
+@pytest.mark.parametrize("tag", ["g300", "g97"])
+def test_tile_nnz_matches_reference_calculate_sparsity(tag):
+    z = np.load(os.path.join(GOLDEN, "tiles", f"{tag}.npz"))
+    n = int(z["num_nodes"])
+    indptr, indices, _ = O.csr_build(z["dst"], z["src"], n)
+    entry = next(t for t in MANIFEST["tiles"] if t["file"].endswith(f"{tag}.npz"))
+    for sr, mx in zip(entry["sizes"], entry["maxlist"]):
+        table = O.tile_nnz(indptr, indices, n, sr)
+        assert np.array_equal(table, z[f"table_{sr}"]), f"tile {sr}"
+        assert O.tile_nnz_max(table) == mx        # cal_min_sparsity through the reference's YAML round trip
+    assert O.tile_size_list(16, 100) == entry["gen_size_16_100"]
+
+
+def test_compile_anchor_constants_recorded():
+    """Known-answer anchors of the reference: GAT/Cora layer-1 without
+    fusion moves 58 978 768 bytes (code/genetic_algorithm.py:68)."""
+    gat = next(c for c in MANIFEST["compile"] if c["network"] == "GAT" and not c["reorder"])
+    nofuse = next(p for p in gat["plans"] if set(p["pattern"]) == {"0"})
+    assert nofuse["rw"] == 58978768
+    assert gat["num_plans"] == 3072
+
+
+def test_csr_build_properties():
+    g = synthetic.powerlaw_graph(500, 4000, seed=4, i0=10.0)
+    indptr, indices, perm = O.csr_build(g.dst, g.src, 500)
+    assert indptr[0] == 0 and indptr[-1] == g.num_edges
+    rows = O.row_ids(indptr)
+    assert np.array_equal(g.dst[perm], rows) and np.array_equal(g.src[perm], indices)
+    key = rows * 500 + indices
+    assert np.all(np.diff(key) > 0)           # strictly ascending (dst, src): sorted, duplicate free
+    # symmetric graph: CSC of the same edges equals CSR
+    cptr, cidx, _ = O.csc_build(g.dst, g.src, 500)
+    assert np.array_equal(cptr, indptr) and np.array_equal(cidx, indices)
+
+
+@pytest.mark.parametrize("parts", [1, 2, 5, 8])
+def test_partition_bounds_balanced(parts):
+    g = synthetic.powerlaw_graph(3000, 90000, seed=2, i0=3.0)
+    indptr, _, _ = O.csr_build(g.dst, g.src, 3000)
+    b = O.partition_bounds(indptr, parts)
+    assert b[0] == 0 and b[-1] == 3000 and np.all(np.diff(b) >= 0)
+    loads = np.diff(indptr[b])
+    assert loads.sum() == g.num_edges
+    assert loads.max() - g.num_edges / parts <= np.diff(indptr).max()
+
+
+def test_degree_reorder_is_stable_descending():
+    g = synthetic.powerlaw_graph(400, 3000, seed=9, i0=5.0)
+    indptr, _, _ = O.csr_build(g.dst, g.src, 400)
+    perm = O.degree_reorder(indptr)
+    deg = np.diff(indptr)[perm]
+    assert np.all(np.diff(deg) <= 0)
+    same = np.flatnonzero(np.diff(deg) == 0)
+    assert np.all(perm[same] < perm[same + 1])
+    d2, s2 = O.relabel_graph(g.dst, g.src, perm)
+    ip2, _, _ = O.csr_build(d2, s2, 400)
+    assert np.array_equal(np.diff(ip2), deg)
+
+
+@pytest.mark.parametrize("variant", ["original", "trans"])
+@pytest.mark.parametrize("heads", [4, 16])
+def test_opgraph_executor_equals_closed_form_gat(variant, heads):
+    """run_opgraph on the reference's op-graph YAML == the closed-form GAT layer."""
+    reorder = variant == "trans"
+    name = f"opgraph/GAT-cora-layer1-{variant}.yaml" if heads == 16 else "opgraph/GAT-cora-restamped-h4.yaml"
+    if heads == 4 and reorder:
+        pytest.skip("the re-stamped V2 YAML exists in the original op order only")
+    with open(os.path.join(GOLDEN, name)) as f:
+        op_info = yaml.safe_load(f)
+    n, e, fin = 300, 2400, 1433
+    g = synthetic.powerlaw_graph(n, e, seed=1, i0=10.0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    x, w, al, ar = synthetic.gat_tensors(n, fin, 128, heads, seed=0)
+    out = O.run_opgraph(op_info, indptr, indices, {0: x}, {0: w, 1: al, 2: ar},
+                        semantics=O.NETWORK_SEMANTICS[("GAT", reorder)])
+    ref = O.gat_layer(indptr, indices, x, w, al, ar, variant=variant, stabilize=False)
+    final = len(op_info) - 1
+    np.testing.assert_allclose(out[final], ref["Y"], rtol=1e-12, atol=1e-14)
+    stab = O.gat_layer(indptr, indices, x, w, al, ar, variant=variant, stabilize=True)
+    np.testing.assert_allclose(stab["Y"], ref["Y"], rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("variant", ["original", "trans"])
+def test_opgraph_executor_equals_closed_form_gcn(variant):
+    with open(os.path.join(GOLDEN, f"opgraph/GCN-cora-layer1-{variant}.yaml")) as f:
+        op_info = yaml.safe_load(f)
+    n, e, fin = 300, 2400, 1433
+    g = synthetic.powerlaw_graph(n, e, seed=1, i0=10.0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, fin), dtype=np.float32)
+    w = synthetic.glorot(rng, fin, 128)
+    ew = synthetic.gcn_edge_norm(indptr, indices)
+    if variant == "trans":
+        out = O.run_opgraph(op_info, indptr, indices, {0: x}, {0: w}, {2: ew})
+    else:
+        out = O.run_opgraph(op_info, indptr, indices, {0: x}, {3: w}, {1: ew})
+    ref = O.gcn_layer(indptr, indices, ew, x, w, variant=variant)
+    np.testing.assert_allclose(out[3], ref["Y"], rtol=1e-12, atol=1e-13)
+    # (A X) W == A (X W): the two op orders agree to rounding
+    other = O.gcn_layer(indptr, indices, ew, x, w, variant="original" if variant == "trans" else "trans")
+    np.testing.assert_allclose(other["Y"], ref["Y"], rtol=1e-9, atol=1e-11)
+
+
+def test_empty_rows_and_single_edges():
+    indptr = np.array([0, 0, 1, 1, 3], dtype=np.int64)
+    indices = np.array([0, 1, 2], dtype=np.int32)
+    x = np.arange(16, dtype=np.float64).reshape(4, 4)
+    out = O.spmm(indptr, indices, np.array([2.0, 1.0, 1.0]), x)
+    assert np.array_equal(out[0], np.zeros(4)) and np.array_equal(out[2], np.zeros(4))
+    assert np.array_equal(out[1], 2 * x[0]) and np.array_equal(out[3], x[1] + x[2])
+    r = O.gat_layer(indptr, indices, x, np.eye(4), np.ones((4, 2)) * 0.1, np.ones((4, 2)) * 0.1)
+    assert np.array_equal(r["Y"][0], np.zeros(4)) and np.all(np.isfinite(r["Y"]))
+    np.testing.assert_allclose(r["S"][[1, 3]].sum(axis=1) > 0, True)
+
+
+def test_synthetic_graphs_are_deterministic_simple_and_symmetric():
+    a = synthetic.shape_graph("cora")
+    b = synthetic.shape_graph("cora")
+    assert a.checksum() == b.checksum()
+    n, e, _ = synthetic.SHAPES["cora"]
+    assert a.num_nodes == n and a.num_edges == e
+    assert np.all(a.dst != a.src)
+    key = a.dst.astype(np.int64) * n + a.src
+    assert np.unique(key).shape[0] == e
+    rev = a.src.astype(np.int64) * n + a.dst
+    assert np.array_equal(np.sort(key), np.sort(rev))
+    r = synthetic.rmat_graph(10, seed=1)
+    assert r.num_edges == 16 * 1024 and np.all(r.dst != r.src)
+    assert np.unique(r.dst.astype(np.int64) * 1024 + r.src).shape[0] == r.num_edges
