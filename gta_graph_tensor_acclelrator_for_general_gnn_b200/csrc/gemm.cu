@@ -11,7 +11,9 @@ int attn_project_launch(const float* z, int64_t ldz, int64_t num_rows, int f, co
                         int heads, float* el, float* er, cudaStream_t st);
 // returns GTA_ERR_UNSUPPORTED when the shape is outside the tensor-core kernel's rules
 int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
-                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, cudaStream_t st);
+                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st);
+size_t gemm_tc_workspace(int k, int f);
 }  // namespace gta
 
 using namespace gta;
@@ -27,9 +29,11 @@ int gta_gemm_set_mode(int mode) {
 }
 int gta_gemm_get_mode(void) { return g_gemm_mode; }
 
+size_t gta_gemm_workspace(int32_t k, int32_t f) { return (k > 0 && f > 0) ? gemm_tc_workspace(k, f) : 0; }
+
 int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
                  int32_t k, int32_t f, const float* al, const float* ar, int32_t heads, float* el, float* er,
-                 void* stream_) {
+                 void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (num_rows == 0) return GTA_OK;
   GTA_REQUIRE(x && w && z, "gta_gemm_f32: null pointer");
@@ -38,9 +42,14 @@ int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float
   const bool want_attn = (el && al) || (er && ar);
   GTA_REQUIRE(!want_attn || heads >= 1, "gta_gemm_f32: heads must be >= 1 when el/er are requested");
   if (g_gemm_mode != 1) {
-    int rc = gemm_tc_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, al, ar, heads, el, er, st);
+    int rc = gemm_tc_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, al, ar, heads, el, er, workspace, workspace_bytes, st);
     if (rc == GTA_OK) return GTA_OK;
-    if (rc != GTA_ERR_UNSUPPORTED || g_gemm_mode == 2) return rc;
+    if (rc != GTA_ERR_UNSUPPORTED) return rc;
+    if (g_gemm_mode == 2) {
+      set_error("gta_gemm_f32: shape k=%d f=%d ldx=%lld (or a missing workspace) is outside the tcgen05 kernel's rules",
+                k, f, (long long)ldx);
+      return rc;
+    }
   }
   int rc = gemm_simt_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, st);
   if (rc != GTA_OK) return rc;

@@ -67,6 +67,29 @@ def _ld(t: torch.Tensor) -> int:
     return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
 
 
+class _Workspace:
+    """Grow-only scratch buffer (fp32 elements) reused across calls on one device."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, n: int, device):
+        if n == 0:
+            return None
+        device = torch.device(device)
+        if self.buf is None or self.buf.numel() < n or self.buf.device != device:
+            self.buf = torch.empty(n, dtype=torch.float32, device=device)
+        return self.buf
+
+
+_gemm_ws = _Workspace()
+
+
+def set_gemm_mode(mode: str) -> None:
+    """'auto' (tcgen05 3xTF32 when eligible), 'simt' (FFMA) or 'tc' (tcgen05 or error)."""
+    _cabi.check(_cabi.load().gta_gemm_set_mode({"auto": 0, "simt": 1, "tc": 2}[mode]), "gta_gemm_set_mode")
+
+
 @_timed("gta_gemm_f32")
 def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: torch.Tensor | None = None,
          out: torch.Tensor | None = None):
@@ -90,8 +113,11 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
         if ar is not None:
             ar = ar.contiguous()
             er = torch.empty((n, heads), dtype=torch.float32, device=x.device)
+    ws_bytes = int(lib.gta_gemm_workspace(k, f))
+    ws = _gemm_ws.get((ws_bytes + 3) // 4, x.device)
     _cabi.check(lib.gta_gemm_f32(_cabi.ptr(x), _ld(x), _cabi.ptr(w), f, _cabi.ptr(z), _ld(z), n, k, f,
-                                 _cabi.ptr(al), _cabi.ptr(ar), heads, _cabi.ptr(el), _cabi.ptr(er), _stream()),
+                                 _cabi.ptr(al), _cabi.ptr(ar), heads, _cabi.ptr(el), _cabi.ptr(er),
+                                 _cabi.ptr(ws), ws_bytes, _stream()),
                 "gta_gemm_f32")
     if al is None and ar is None:
         return z

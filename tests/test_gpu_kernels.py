@@ -108,9 +108,17 @@ def test_schedule_covers_every_edge_once(T, chunk):
     assert np.array_equal(np.sort(slots), np.arange(s.num_slots))
 
 
+@pytest.fixture(params=["simt", "tc"])
+def gemm_mode(T, request):
+    """Both realisations of COMP_MM: the FFMA kernel and the tcgen05 3xTF32 kernel."""
+    T.k.set_gemm_mode(request.param)
+    yield request.param
+    T.k.set_gemm_mode("auto")
+
+
 @pytest.mark.parametrize("n,k,f", [(2708, 1433, 128), (1000, 602, 128), (513, 128, 64), (300, 64, 16), (77, 500, 128),
-                                   (260, 256, 256)])
-def test_gemm_fp32(T, n, k, f):
+                                   (260, 256, 256), (40000, 602, 128), (129, 7, 32), (1, 33, 48)])
+def test_gemm_fp32(T, gemm_mode, n, k, f):
     rng = np.random.default_rng(n + k)
     x = rng.standard_normal((n, k), dtype=np.float32)
     w = synthetic.glorot(rng, k, f)
@@ -118,11 +126,25 @@ def test_gemm_fp32(T, n, k, f):
     z = T.k.gemm(xd, _dev(T, w)).cpu().numpy()
     z64 = O.gemm(x, w)
     scale = np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64)
-    assert_close_rowscale(z, z64, scale, what=f"gemm {n}x{k}x{f}")
+    assert_close_rowscale(z, z64, scale, what=f"gemm[{gemm_mode}] {n}x{k}x{f}")
+    again = T.k.gemm(xd, _dev(T, w)).cpu().numpy()
+    assert np.array_equal(z, again), "GEMM is not bitwise reproducible"
+
+
+def test_gemm_tc_refuses_ineligible_shapes(T):
+    T.k.set_gemm_mode("tc")
+    try:
+        x = T.k.to_table(_dev(T, np.ones((64, 40), np.float32)))
+        with pytest.raises(T.cabi.GtaUnsupported):
+            T.k.gemm(x, _dev(T, np.ones((40, 24), np.float32)))      # F not a multiple of 16
+    finally:
+        T.k.set_gemm_mode("auto")
+    z = T.k.gemm(x, _dev(T, np.ones((40, 24), np.float32)))          # auto: falls back to FFMA
+    assert float(z.min()) == 40.0 and float(z.max()) == 40.0
 
 
 @pytest.mark.parametrize("heads", [1, 4, 8, 16])
-def test_gemm_attention_projections(T, heads):
+def test_gemm_attention_projections(T, gemm_mode, heads):
     n, k, f = 700, 602, 128
     x, w, al, ar = synthetic.gat_tensors(n, k, f, heads, seed=3, dense_attention=(heads == 4))
     z, el, er = T.k.gemm(T.k.to_table(_dev(T, x)), _dev(T, w), _dev(T, al), _dev(T, ar))
