@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgta_b200.so")
+_TAG = os.environ.get("GTA_LIB_TAG", "")          # experiment builds, see build.py
+LIB_PATH = os.path.join(_HERE, "libgta_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 EPI_NONE, EPI_ELU, EPI_RELU = 0, 1, 2
@@ -39,17 +40,18 @@ SIGNATURES = {
     "gta_remap_sources": (C.c_int, [_p, _i64, _p, _i32, _i64, _p, _p]),
     "gta_reorder_workspace": (_sz, [_i64]),
     "gta_reorder": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
-    "gta_schedule_workspace": (_sz, [_i64]),
-    "gta_schedule_max_items": (_i64, [_i64, _i64, _i32]),
-    "gta_schedule_build": (C.c_int, [_p, _i64, _i64, _i32, _p, _i64, C.POINTER(_i64), _p, _sz, _p]),
+    "gta_schedule_workspace": (_sz, [_i64, _i64, _i64]),
+    "gta_schedule_max_items": (_i64, [_i64, _i64, _i32, _i64, _i64]),
+    "gta_schedule_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i64, _p, C.POINTER(_i64), _p, _sz, _p]),
     "gta_gemm_workspace": (_sz, [_i32, _i32]),
     "gta_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "gta_gemm_set_mode": (C.c_int, [C.c_int]),
     "gta_gemm_get_mode": (C.c_int, []),
-    "gta_aggregate_f32": (C.c_int, [_p, _i64, _i64, _p, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32, _p, _p]),
+    "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
+                                    _p, _p]),
     "gta_gat_partial_stride": (_i32, [_i32, _i32]),
-    "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _p, _i32, _f32, _p, _i64, _p, _i64, _i32, _i32,
-                                        _p, _p, _p, _p]),
+    "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _f32, _p, _i64, _p, _i64, _i32,
+                                        _i32, _p, _p, _p, _p]),
     "gta_gat_logits_f32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "gta_edge_binary_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _i32, _i32, _i64, _p, _i32,
                                       _i64, _p]),

@@ -15,10 +15,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
-LIB = os.path.join(HERE, "libgta_b200.so")
-SOURCES = ["api.cu", "preprocess.cu", "aggregate.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu"]
+# experiment builds: GTA_LIB_TAG=u4 GTA_NVCC_DEFS="-DGTA_AGG_UNROLL=4" -> libgta_b200_u4.so (load with GTA_LIB_TAG=u4)
+TAG = os.environ.get("GTA_LIB_TAG", "")
+OBJ = os.path.join(CSRC, "_build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libgta_b200" + ("_" + TAG if TAG else "") + ".so")
+SOURCES = ["api.cu", "preprocess.cu", "schedule.cu", "aggregate.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("GTA_NVCC_DEFS", "").split()
 
 
 def _nvcc() -> str:

@@ -4,24 +4,36 @@
 //   gat_aggregate_kernel  GAT ops 3-13 in one pass, online softmax (genGraphOP.py:52-62)
 //   gat_logits_kernel     GAT block [4,5,6,7,8] alone (STORE_E p, STORE_N S)
 //
-// Mapping.  A work item (<= chunk edges of one destination row, see gta_schedule_build) is
-// owned by a GROUP of LANES = min(F,128)/4 lanes; each lane owns 4 consecutive features, so
-// one gathered source row is ONE 128-bit load per lane and a full 512 B row per 32 lanes.
-// Wider rows (F > 128) are covered by blockIdx.y feature windows of 128.  Source ids (and
-// scalar edge weights) are read once per group, coalesced and streaming (L2 evict_first),
-// and handed round the group by shuffle / shared memory; gathered rows use the read-only
-// path with L2 evict_last so the feature table stays resident in the 126 MB L2.
-// UNROLL independent row loads are in flight per lane.
+// Mapping.  A work item (<= chunk edges of one destination row inside one column block, see
+// schedule.cu) is owned by a GROUP of LANES = min(F,128)/4 lanes; each lane owns 4 consecutive
+// features, so one gathered source row is ONE 128-bit load per lane and a full 512 B row per 32
+// lanes.  Wider rows (F > 128) are covered by blockIdx.y feature windows of 128.  Source ids (and
+// scalar edge weights) are read once per group, coalesced and streaming (L1 no-allocate, L2
+// evict_first), then handed round the group by shuffle / shared memory.  Gathered rows use the
+// read-only path without L1 allocation (no reuse inside an SM); L2 residency comes from the
+// column-block order of the work list.  kUnroll independent row loads are in flight per lane and a
+// full batch runs without a single predicate.
 //
-// Determinism.  Every destination row is reduced by exactly one group in ascending source
-// order inside an item, and items of a long row are combined in item order by
-// *_combine_kernel: a fixed-shape reduction, bitwise reproducible run to run, no atomics.
+// Determinism.  Every item is reduced by exactly one group in ascending source order, and the
+// items of a row are combined in slot order by *_combine_kernel: a fixed-shape reduction, bitwise
+// reproducible run to run, no atomics.
 #include "common.cuh"
 
 namespace gta {
 
-constexpr int kAggThreads = 256;
-constexpr int kUnroll = 8;
+#ifndef GTA_AGG_THREADS
+#define GTA_AGG_THREADS 128
+#endif
+#ifndef GTA_AGG_UNROLL
+#define GTA_AGG_UNROLL 8
+#endif
+#ifndef GTA_AGG_MINBLOCKS
+#define GTA_AGG_MINBLOCKS 6       // 128 threads x 6 blocks = 24 warps/SM => at most 80 registers (measured best)
+#endif
+constexpr int kAggThreads = GTA_AGG_THREADS;
+constexpr int kAggWarps = kAggThreads / 32;
+constexpr int kUnroll = GTA_AGG_UNROLL;
+constexpr int kAggMinBlocks = GTA_AGG_MINBLOCKS;
 
 // floats per partial slot of the GAT kernel: acc[f] | max[H] | sum[H], padded to 16 bytes
 __host__ __device__ inline int gat_partial_stride(int f, int heads) { return f + ((2 * heads + 3) & ~3); }
@@ -43,6 +55,41 @@ __device__ __forceinline__ int warp_max_i32(int v) {
   for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// gathered feature row, 128 bits per lane.  GTA_AGG_GATHER picks the cache policy (measured on B200,
+// see DESIGN.md): 0 = L1 no-allocate, 1 = default, 2 = L1 no-allocate + L2 evict_last, 3 = L2 evict_last
+#ifndef GTA_AGG_GATHER
+#define GTA_AGG_GATHER 2
+#endif
+__device__ __forceinline__ float4 ld_row_f32x4(const float* p, uint64_t pol_keep) {
+  float4 v;
+#if GTA_AGG_GATHER == 0
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#elif GTA_AGG_GATHER == 1
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+#elif GTA_AGG_GATHER == 2
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_keep));
+#else
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_keep));
+#endif
+  return v;
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x);
+  acc.y = fmaf(w, v.y, acc.y);
+  acc.z = fmaf(w, v.z, acc.z);
+  acc.w = fmaf(w, v.w, acc.w);
+}
+__device__ __forceinline__ float4 epilogue4(float4 a, float scale, int epi) {
+  a.x = apply_epilogue(a.x * scale, epi);
+  a.y = apply_epilogue(a.y * scale, epi);
+  a.z = apply_epilogue(a.z * scale, epi);
+  a.w = apply_epilogue(a.w * scale, epi);
+  return a;
+}
 
 // ----------------------------------------------------------------------------------------
 // weighted aggregate
@@ -50,7 +97,7 @@ __device__ __forceinline__ int warp_max_i32(int v) {
 //   (f / wh) % 4 == 0 so a lane's 4 features share a head)
 // ----------------------------------------------------------------------------------------
 template <int LANES, int WKIND, bool DIV>
-__global__ void __launch_bounds__(kAggThreads)
+__global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
 aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
                  const float* __restrict__ w, int wh, const float* __restrict__ rowden,
                  const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo,
@@ -68,89 +115,108 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
   const int max_count = (LANES == 32) ? count : warp_max_i32(count);
   const int32_t* idx_base = indices + it.y;
   const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
+  const float* xf = x + (active ? fo : 0);
   int head = 0;
   float den = 1.f;
   if (WKIND == 2) head = active ? fo / (f / wh) : 0;
   if (DIV && have) den = rowden[int64_t(it.x) * wh + head];
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // software pipeline: ids (and scalar weights) of batch b+1 are in flight under the gathers of batch b
+  int idx_nxt = 0;
+  float w_nxt = 0.f;
+  if (l < count) {
+    idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+    if (WKIND == 1) w_nxt = ld_stream_f32(w_base + l, pol_stream);
+  }
   for (int base = 0; base < max_count; base += LANES) {
     int n = count - base;
     n = n < 0 ? 0 : (n > LANES ? LANES : n);
-    int my_idx = 0;
-    float my_w = 0.f;
-    if (l < n) {
-      my_idx = ld_stream_i32(idx_base + base + l, pol_stream);
-      if (WKIND == 1) {
-        my_w = ld_stream_f32(w_base + base + l, pol_stream);
-        if (DIV) my_w = my_w / den;
-      }
+    const int my_idx = idx_nxt;
+    float my_w = w_nxt;
+    if (WKIND == 1 && DIV) my_w = my_w / den;
+    if (base + LANES + l < count) {
+      idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
+      if (WKIND == 1) w_nxt = ld_stream_f32(w_base + base + LANES + l, pol_stream);
     }
-    for (int j = 0; j < LANES; j += kUnroll) {
-      if (LANES == 32 && j >= n) break;   // warp-uniform when a group is a whole warp
-      float4 v[kUnroll];
-      float wv[kUnroll];
+    const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
+    if (full) {
+      // whole batch, no predicates: kUnroll loads in flight, then their FMAs (the outer loop stays
+      // rolled: unrolled, ptxas hoists every load of the batch and spills)
+#pragma unroll 1
+      for (int j = 0; j < LANES; j += kUnroll) {
+        float4 v[kUnroll];
+        float wv[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (j + u < LANES) {
-          int src = __shfl_sync(0xffffffffu, my_idx, j + u, LANES);
-          float ws = 1.f;
-          if (WKIND == 1) ws = __shfl_sync(0xffffffffu, my_w, j + u, LANES);
-          const bool ok = active && (j + u) < n;
-          v[u] = ok ? ld_gather_f32x4(x + int64_t(src) * ldx + fo, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (WKIND == 2) {
-            ws = ok ? __ldg(w_base + int64_t(base + j + u) * wh + head) : 0.f;
-            if (DIV) ws = ws / den;
+        for (int u = 0; u < kUnroll; ++u) {
+          if (j + u < LANES) {
+            const int src = __shfl_sync(0xffffffffu, my_idx, j + u, LANES);
+            wv[u] = 1.f;
+            if (WKIND == 1) wv[u] = __shfl_sync(0xffffffffu, my_w, j + u, LANES);
+            if (LANES < 32 || active) v[u] = ld_row_f32x4(xf + int64_t(src) * ldx, pol_keep);
+            if (WKIND == 2) {
+              wv[u] = __ldg(w_base + int64_t(base + j + u) * wh + head);
+              if (DIV) wv[u] = wv[u] / den;
+            }
           }
-          wv[u] = ws;
+        }
+        if (LANES < 32 || active) {
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) fma4(acc, wv[u], v[u]);
         }
       }
+    } else {
+      const int nmax = (LANES == 32) ? n : LANES;
+      for (int j = 0; j < nmax; j += kUnroll) {
+        float4 v[kUnroll];
+        float wv[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (j + u < LANES) {
-          acc.x = fmaf(wv[u], v[u].x, acc.x);
-          acc.y = fmaf(wv[u], v[u].y, acc.y);
-          acc.z = fmaf(wv[u], v[u].z, acc.z);
-          acc.w = fmaf(wv[u], v[u].w, acc.w);
+        for (int u = 0; u < kUnroll; ++u) {
+          if (j + u < LANES) {
+            const int src = __shfl_sync(0xffffffffu, my_idx, j + u, LANES);
+            float ws = 1.f;
+            if (WKIND == 1) ws = __shfl_sync(0xffffffffu, my_w, j + u, LANES);
+            const bool ok = active && (j + u) < n;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v[u] = ld_row_f32x4(xf + int64_t(src) * ldx, pol_keep);
+            if (WKIND == 2) {
+              ws = ok ? __ldg(w_base + int64_t(base + j + u) * wh + head) : 0.f;
+              if (DIV) ws = ws / den;
+            }
+            wv[u] = ws;
+          }
         }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (j + u < LANES) fma4(acc, wv[u], v[u]);
       }
     }
   }
   if (!active) return;
   if (it.w < 0) {
-    acc.x = apply_epilogue(acc.x, epilogue);
-    acc.y = apply_epilogue(acc.y, epilogue);
-    acc.z = apply_epilogue(acc.z, epilogue);
-    acc.w = apply_epilogue(acc.w, epilogue);
-    st_stream_f32x4(out + int64_t(it.x) * ldo + fo, acc);
+    st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
   } else {
     *reinterpret_cast<float4*>(partials + int64_t(it.w) * f + fo) = acc;
   }
 }
 
-// rows cut into several items: sum the partial rows in item order
+// rows that own several items: sum their partial rows in slot order
 __global__ void __launch_bounds__(kAggThreads)
-aggregate_combine_kernel(const int4* __restrict__ items, int64_t num_items, const float* __restrict__ partials,
+aggregate_combine_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, const float* __restrict__ partials,
                          float* __restrict__ out, int64_t ldo, int f, int epilogue) {
   const int lane = threadIdx.x & 31;
-  const int64_t idx = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
-  if (idx >= num_items) return;
-  int4 it = items[idx];
-  if (it.w < 0) return;
-  if (idx > 0 && items[idx - 1].x == it.x) return;   // not the first item of its row
+  const int64_t r = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
+  if (r >= num_rows) return;
+  const int s0 = row_slots[r], s1 = row_slots[r + 1];
+  if (s1 == s0) return;
   for (int fo = 4 * lane; fo < f; fo += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = idx; c < num_items; ++c) {
-      int4 ic = items[c];
-      if (ic.x != it.x) break;
-      float4 p = *reinterpret_cast<const float4*>(partials + int64_t(ic.w) * f + fo);
+    for (int s = s0; s < s1; ++s) {
+      float4 p = *reinterpret_cast<const float4*>(partials + int64_t(s) * f + fo);
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
-    acc.x = apply_epilogue(acc.x, epilogue);
-    acc.y = apply_epilogue(acc.y, epilogue);
-    acc.z = apply_epilogue(acc.z, epilogue);
-    acc.w = apply_epilogue(acc.w, epilogue);
-    *reinterpret_cast<float4*>(out + int64_t(it.x) * ldo + fo) = acc;
+    *reinterpret_cast<float4*>(out + r * ldo + fo) = epilogue4(acc, 1.f, epilogue);
   }
 }
 
@@ -186,18 +252,16 @@ __device__ __forceinline__ float pick(const float (&v)[H], int h) {
 }
 
 template <int LANES, int H>
-__global__ void __launch_bounds__(kAggThreads)
+__global__ void __launch_bounds__(kAggThreads, (H <= 4) ? kAggMinBlocks : (kAggMinBlocks + 1) / 2)
 gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
                      const float* __restrict__ el, const float* __restrict__ er, float slope,
                      const float* __restrict__ z, int64_t ldz, float* __restrict__ out, int64_t ldo,
                      int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
                      float* __restrict__ partials) {
-  // per warp: 32 staged edges = source id + H softmax numerators
-  __shared__ int s_idx[kAggThreads / 32][32];
-  __shared__ float s_p[kAggThreads / 32][32][H];
+  // per warp: 32 staged edges x H heads, each entry = {source id, softmax numerator}
+  __shared__ uint2 s_e[kAggWarps][32 * H];
   const uint64_t pol_stream = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();
-  const int warp_in_cta = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int gbase = lane & ~(LANES - 1);          // first lane of my group inside the warp
@@ -210,80 +274,99 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   const int max_count = (LANES == 32) ? count : warp_max_i32(count);
   const int32_t* idx_base = indices + it.y;
   const int head = active ? fo / (f / H) : 0;
+  const float* zf = z + (active ? fo : 0);
+  uint2* se = s_e[threadIdx.x >> 5];
+  const uint2* mine = se + gbase * H + head;
 
-  float elr[H], m[H], s[H];
+  float elr[H], m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
   if (have) load_heads<H>(el + int64_t(it.x) * H, elr);
 #pragma unroll
   for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; if (!have) elr[h] = 0.f; }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // software pipeline: source ids are loaded two batches ahead and the er rows one batch ahead, so
+  // the id -> er -> softmax dependency chain of batch b+1 hides under the row gathers of batch b
+  int idx_cur = 0, idx_nxt = 0;
+  float er_cur[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
+  if (l < count) {
+    idx_cur = ld_stream_i32(idx_base + l, pol_stream);
+    load_heads<H>(er + int64_t(idx_cur) * H, er_cur);
+  }
+  if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
+
   for (int base = 0; base < max_count; base += LANES) {
     int n = count - base;
     n = n < 0 ? 0 : (n > LANES ? LANES : n);
     float e[H];
-    int my_idx = 0;
-    if (l < n) {
-      my_idx = ld_stream_i32(idx_base + base + l, pol_stream);
-      float erv[H];
-      load_heads<H>(er + int64_t(my_idx) * H, erv);
+    const int my_idx = idx_cur;
 #pragma unroll
-      for (int h = 0; h < H; ++h) e[h] = leaky(elr[h] + erv[h], slope);
-    } else {
-#pragma unroll
-      for (int h = 0; h < H; ++h) e[h] = -INFINITY;
-    }
+    for (int h = 0; h < H; ++h) e[h] = (l < n) ? leaky(elr[h] + er_cur[h], slope) : -INFINITY;
+    // prefetch: er of the next batch (its ids arrived during the previous iteration), ids of the one after
+    idx_cur = idx_nxt;
+    if (base + LANES + l < count) load_heads<H>(er + int64_t(idx_cur) * H, er_cur);
+    if (base + 2 * LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + 2 * LANES + l, pol_stream);
     float my_scale = 1.f;
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-      float bm = group_max<LANES>(e[h]);
-      float mn = fmaxf(m[h], bm);
-      // n == 0 for this group (another group in the warp is still running): mn may be -inf
-      float sc = (mn == -INFINITY) ? 1.f : expf(m[h] - mn);
-      float p = (l < n) ? expf(e[h] - mn) : 0.f;
-      float bs = group_sum<LANES>(p);
-      s[h] = s[h] * sc + bs;
+      const float mn = fmaxf(m[h], group_max<LANES>(e[h]));
+      // mn stays -inf only while this group has seen no edge (another group in the warp is running)
+      const float sc = (mn == -INFINITY) ? 1.f : expf(m[h] - mn);
+      const float p = (l < n) ? expf(e[h] - mn) : 0.f;
+      s[h] = fmaf(s[h], sc, p);
       m[h] = mn;
       my_scale = (h == head) ? sc : my_scale;
-      s_p[warp_in_cta][lane][h] = p;
+      se[lane * H + h] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
     }
-    s_idx[warp_in_cta][lane] = my_idx;
     acc.x *= my_scale; acc.y *= my_scale; acc.z *= my_scale; acc.w *= my_scale;
     __syncwarp();
-    for (int j = 0; j < LANES; j += kUnroll) {
-      if (LANES == 32 && j >= n) break;
-      float4 v[kUnroll];
-      float pv[kUnroll];
+    const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
+    if (full) {
+      if (LANES < 32 || active) {
+#pragma unroll 1
+        for (int j = 0; j < LANES; j += kUnroll) {
+          uint2 ed[kUnroll];
+          float4 v[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (j + u < LANES) {
-          const bool ok = active && (j + u) < n;
-          int src = s_idx[warp_in_cta][gbase + j + u];
-          pv[u] = s_p[warp_in_cta][gbase + j + u][head];
-          v[u] = ok ? ld_gather_f32x4(z + int64_t(src) * ldz + fo, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) ed[u] = mine[(j + u) * H];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) v[u] = ld_row_f32x4(zf + int64_t(ed[u].x) * ldz, pol_keep);
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) fma4(acc, __uint_as_float(ed[u].y), v[u]);
         }
       }
+    } else {
+      const int nmax = (LANES == 32) ? n : LANES;
+      for (int j = 0; j < nmax; j += kUnroll) {
+        float4 v[kUnroll];
+        float pv[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (j + u < LANES) {
-          acc.x = fmaf(pv[u], v[u].x, acc.x);
-          acc.y = fmaf(pv[u], v[u].y, acc.y);
-          acc.z = fmaf(pv[u], v[u].z, acc.z);
-          acc.w = fmaf(pv[u], v[u].w, acc.w);
+        for (int u = 0; u < kUnroll; ++u) {
+          if (j + u < LANES) {
+            const uint2 ed = mine[(j + u) * H];
+            pv[u] = __uint_as_float(ed.y);
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active && (j + u) < n) v[u] = ld_row_f32x4(zf + int64_t(ed.x) * ldz, pol_keep);
+          }
         }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+          if (j + u < LANES) fma4(acc, pv[u], v[u]);
       }
     }
     __syncwarp();
   }
+#pragma unroll
+  for (int h = 0; h < H; ++h) s[h] = group_sum<LANES>(s[h]);
   if (!have) return;
   if (it.w < 0) {
     if (active) {
-      float sh = pick<H>(s, head);
-      float inv = sh > 0.f ? 1.f / sh : 0.f;
-      acc.x = apply_epilogue(acc.x * inv, epilogue);
-      acc.y = apply_epilogue(acc.y * inv, epilogue);
-      acc.z = apply_epilogue(acc.z * inv, epilogue);
-      acc.w = apply_epilogue(acc.w * inv, epilogue);
-      st_stream_f32x4(out + int64_t(it.x) * ldo + fo, acc);
+      const float sh = pick<H>(s, head);
+      st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue));
     }
     if (blockIdx.y == 0 && l < H) {
       if (rowmax) rowmax[int64_t(it.x) * H + l] = (count > 0) ? pick<H>(m, l) : 0.f;
@@ -299,62 +382,53 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   }
 }
 
-// merge the (max, sum, acc) triples of a long row in item order
+// merge the (max, sum, acc) triples of a row in slot order
 template <int H>
 __global__ void __launch_bounds__(kAggThreads)
-gat_combine_kernel(const int4* __restrict__ items, int64_t num_items, const float* __restrict__ partials,
+gat_combine_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, const float* __restrict__ partials,
                    float* __restrict__ out, int64_t ldo, int f, int epilogue,
                    float* __restrict__ rowmax, float* __restrict__ rowsum) {
   const int lane = threadIdx.x & 31;
-  const int64_t idx = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
-  if (idx >= num_items) return;
-  int4 it = items[idx];
-  if (it.w < 0) return;
-  if (idx > 0 && items[idx - 1].x == it.x) return;
+  const int64_t r = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
+  if (r >= num_rows) return;
+  const int s0 = row_slots[r], s1 = row_slots[r + 1];
+  if (s1 == s0) return;
   const int stride = gat_partial_stride(f, H);
   const int d = f / H;
   // pass 1: global max and rescaled sum per head (every lane redundantly, H is small)
   float gm[H], gs[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) { gm[h] = -INFINITY; gs[h] = 0.f; }
-  for (int64_t c = idx; c < num_items; ++c) {
-    int4 ic = items[c];
-    if (ic.x != it.x) break;
-    const float* part = partials + int64_t(ic.w) * stride;
+  for (int c = s0; c < s1; ++c) {
+    const float* part = partials + int64_t(c) * stride;
 #pragma unroll
     for (int h = 0; h < H; ++h) gm[h] = fmaxf(gm[h], part[f + h]);
   }
-  for (int64_t c = idx; c < num_items; ++c) {
-    int4 ic = items[c];
-    if (ic.x != it.x) break;
-    const float* part = partials + int64_t(ic.w) * stride;
+  for (int c = s0; c < s1; ++c) {
+    const float* part = partials + int64_t(c) * stride;
 #pragma unroll
-    for (int h = 0; h < H; ++h) gs[h] += part[f + H + h] * expf(part[f + h] - gm[h]);
+    for (int h = 0; h < H; ++h) {
+      const float mc = part[f + h];
+      gs[h] += (mc == -INFINITY) ? 0.f : part[f + H + h] * expf(mc - gm[h]);
+    }
   }
   for (int fo = 4 * lane; fo < f; fo += 128) {
     const int head = fo / d;
     const float mh = pick<H>(gm, head);
     const float sh = pick<H>(gs, head);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c = idx; c < num_items; ++c) {
-      int4 ic = items[c];
-      if (ic.x != it.x) break;
-      const float* part = partials + int64_t(ic.w) * stride;
-      float sc = expf(part[f + head] - mh);
-      float4 p = *reinterpret_cast<const float4*>(part + fo);
-      acc.x = fmaf(sc, p.x, acc.x); acc.y = fmaf(sc, p.y, acc.y);
-      acc.z = fmaf(sc, p.z, acc.z); acc.w = fmaf(sc, p.w, acc.w);
+    for (int c = s0; c < s1; ++c) {
+      const float* part = partials + int64_t(c) * stride;
+      const float mc = part[f + head];
+      if (mc == -INFINITY) continue;          // an item without edges contributes nothing
+      fma4(acc, expf(mc - mh), *reinterpret_cast<const float4*>(part + fo));
     }
-    float inv = sh > 0.f ? 1.f / sh : 0.f;
-    acc.x = apply_epilogue(acc.x * inv, epilogue);
-    acc.y = apply_epilogue(acc.y * inv, epilogue);
-    acc.z = apply_epilogue(acc.z * inv, epilogue);
-    acc.w = apply_epilogue(acc.w * inv, epilogue);
-    *reinterpret_cast<float4*>(out + int64_t(it.x) * ldo + fo) = acc;
+    *reinterpret_cast<float4*>(out + r * ldo + fo) = epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue);
   }
   if (lane < H) {
-    if (rowmax) rowmax[int64_t(it.x) * H + lane] = pick<H>(gm, lane);
-    if (rowsum) rowsum[int64_t(it.x) * H + lane] = pick<H>(gs, lane);
+    const float mh = pick<H>(gm, lane);
+    if (rowmax) rowmax[r * H + lane] = (mh == -INFINITY) ? 0.f : mh;
+    if (rowsum) rowsum[r * H + lane] = pick<H>(gs, lane);
   }
 }
 
@@ -402,34 +476,18 @@ static int lanes_for(int f) {
   return l < 4 ? 4 : l;
 }
 
-template <int LANES, int WKIND, bool DIV>
-static void launch_aggregate(dim3 grid, cudaStream_t st, const int4* items, int64_t num_items, const int32_t* indices,
-                             const float* w, int wh, const float* rowden, const float* x, int64_t ldx, float* out,
-                             int64_t ldo, int f, int epi, float* partials) {
-  aggregate_kernel<LANES, WKIND, DIV><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, w, wh, rowden, x, ldx,
-                                                                    out, ldo, f, epi, partials);
-}
-
 template <int LANES>
-static int dispatch_aggregate(int wkind, bool div, dim3 grid, cudaStream_t st, const int4* items, int64_t num_items,
-                              const int32_t* indices, const float* w, int wh, const float* rowden, const float* x,
-                              int64_t ldx, float* out, int64_t ldo, int f, int epi, float* partials) {
-#define GTA_AGG(K, D) launch_aggregate<LANES, K, D>(grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epi, partials)
+static void dispatch_aggregate(int wkind, bool div, dim3 grid, cudaStream_t st, const int4* items, int64_t num_items,
+                               const int32_t* indices, const float* w, int wh, const float* rowden, const float* x,
+                               int64_t ldx, float* out, int64_t ldo, int f, int epi, float* partials) {
+#define GTA_AGG(K, D) \
+  aggregate_kernel<LANES, K, D><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epi, partials)
   if (wkind == 0) GTA_AGG(0, false);
   else if (wkind == 1 && !div) GTA_AGG(1, false);
   else if (wkind == 1 && div) GTA_AGG(1, true);
   else if (wkind == 2 && !div) GTA_AGG(2, false);
   else GTA_AGG(2, true);
 #undef GTA_AGG
-  return GTA_OK;
-}
-
-template <int LANES, int H>
-static void launch_gat(dim3 grid, cudaStream_t st, const int4* items, int64_t num_items, const int32_t* indices,
-                       const float* el, const float* er, float slope, const float* z, int64_t ldz, float* out,
-                       int64_t ldo, int f, int epi, float* rowmax, float* rowsum, float* partials) {
-  gat_aggregate_kernel<LANES, H><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, slope, z, ldz, out,
-                                                               ldo, f, epi, rowmax, rowsum, partials);
 }
 
 template <int H>
@@ -437,7 +495,8 @@ static int dispatch_gat(int lanes, dim3 grid, cudaStream_t st, const int4* items
                         const int32_t* indices, const float* el, const float* er, float slope, const float* z,
                         int64_t ldz, float* out, int64_t ldo, int f, int epi, float* rowmax, float* rowsum,
                         float* partials) {
-#define GTA_GAT(L) launch_gat<L, H>(grid, st, items, num_items, indices, el, er, slope, z, ldz, out, ldo, f, epi, rowmax, rowsum, partials)
+#define GTA_GAT(L) \
+  gat_aggregate_kernel<L, H><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, slope, z, ldz, out, ldo, f, epi, rowmax, rowsum, partials)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
     case 8: if (H <= 8) { GTA_GAT(8); return GTA_OK; } break;
@@ -456,11 +515,10 @@ extern "C" {
 
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads) { return gat_partial_stride(f, heads); }
 
-int gta_aggregate_f32(const int32_t* items_, int64_t num_items, int64_t num_slots, const int64_t* indptr,
-                      const int32_t* indices, int32_t wmode, const float* w, int32_t wh, const float* rowden,
-                      const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f, int32_t epilogue,
-                      float* partials, void* stream_) {
-  (void)indptr;
+int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_rows,
+                      int64_t num_slots, const int32_t* indices, int32_t wmode, const float* w, int32_t wh,
+                      const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
+                      int32_t epilogue, float* partials, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (num_items == 0) return GTA_OK;
   GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
@@ -468,7 +526,7 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, int64_t num_slot
   GTA_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f, "gta_aggregate_f32: leading dimensions must be multiples of 4 and >= f");
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gta_aggregate_f32: tables must be 16-byte aligned");
   GTA_REQUIRE(wmode >= GTA_W_NONE && wmode <= GTA_W_EDGE_DIV, "gta_aggregate_f32: bad wmode %d", wmode);
-  GTA_REQUIRE(num_slots == 0 || partials, "gta_aggregate_f32: partials required for %lld slots", (long long)num_slots);
+  GTA_REQUIRE(num_slots == 0 || (partials && row_slots), "gta_aggregate_f32: partials and row_slots required for %lld slots", (long long)num_slots);
   int wkind = 0;
   bool div = wmode == GTA_W_EDGE_DIV;
   if (wmode != GTA_W_NONE) {
@@ -492,19 +550,18 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, int64_t num_slot
   }
   GTA_CHECK_LAUNCH("aggregate_kernel");
   if (num_slots > 0) {
-    int64_t cthreads = num_items * 32;
+    int64_t cthreads = num_rows * 32;
     aggregate_combine_kernel<<<(unsigned)((cthreads + kAggThreads - 1) / kAggThreads), kAggThreads, 0, st>>>(
-        items, num_items, partials, out, ldo, f, epilogue);
+        row_slots, num_rows, partials, out, ldo, f, epilogue);
     GTA_CHECK_LAUNCH("aggregate_combine_kernel");
   }
   return GTA_OK;
 }
 
-int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, int64_t num_slots, const int64_t* indptr,
-                          const int32_t* indices, const float* el, const float* er, int32_t heads, float slope,
-                          const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f, int32_t epilogue,
-                          float* rowmax, float* rowsum, float* partials, void* stream_) {
-  (void)indptr;
+int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_rows,
+                          int64_t num_slots, const int32_t* indices, const float* el, const float* er, int32_t heads,
+                          float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (num_items == 0) return GTA_OK;
   GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
@@ -514,7 +571,7 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, int64_t num_
               (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
               "gta_gat_aggregate_f32: tables must be 16-byte aligned");
   GTA_REQUIRE(heads >= 1 && f % heads == 0, "gta_gat_aggregate_f32: heads=%d must divide f=%d", heads, f);
-  GTA_REQUIRE(num_slots == 0 || partials, "gta_gat_aggregate_f32: partials required for %lld slots", (long long)num_slots);
+  GTA_REQUIRE(num_slots == 0 || (partials && row_slots), "gta_gat_aggregate_f32: partials and row_slots required for %lld slots", (long long)num_slots);
   if ((f / heads) % 4 != 0) {
     set_error("gta_gat_aggregate_f32: per-head width f/heads=%d is not a multiple of 4", f / heads);
     return GTA_ERR_UNSUPPORTED;
@@ -540,15 +597,17 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, int64_t num_
   }
   GTA_CHECK_LAUNCH("gat_aggregate_kernel");
   if (num_slots > 0) {
-    int64_t cthreads = num_items * 32;
+    int64_t cthreads = num_rows * 32;
     unsigned cgrid = (unsigned)((cthreads + kAggThreads - 1) / kAggThreads);
+#define GTA_COMB(HH) gat_combine_kernel<HH><<<cgrid, kAggThreads, 0, st>>>(row_slots, num_rows, partials, out, ldo, f, epilogue, rowmax, rowsum)
     switch (heads) {
-      case 1: gat_combine_kernel<1><<<cgrid, kAggThreads, 0, st>>>(items, num_items, partials, out, ldo, f, epilogue, rowmax, rowsum); break;
-      case 2: gat_combine_kernel<2><<<cgrid, kAggThreads, 0, st>>>(items, num_items, partials, out, ldo, f, epilogue, rowmax, rowsum); break;
-      case 4: gat_combine_kernel<4><<<cgrid, kAggThreads, 0, st>>>(items, num_items, partials, out, ldo, f, epilogue, rowmax, rowsum); break;
-      case 8: gat_combine_kernel<8><<<cgrid, kAggThreads, 0, st>>>(items, num_items, partials, out, ldo, f, epilogue, rowmax, rowsum); break;
-      default: gat_combine_kernel<16><<<cgrid, kAggThreads, 0, st>>>(items, num_items, partials, out, ldo, f, epilogue, rowmax, rowsum); break;
+      case 1: GTA_COMB(1); break;
+      case 2: GTA_COMB(2); break;
+      case 4: GTA_COMB(4); break;
+      case 8: GTA_COMB(8); break;
+      default: GTA_COMB(16); break;
     }
+#undef GTA_COMB
     GTA_CHECK_LAUNCH("gat_combine_kernel");
   }
   return GTA_OK;

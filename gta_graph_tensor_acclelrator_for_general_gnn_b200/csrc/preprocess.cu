@@ -1,5 +1,5 @@
 // Device-side graph preprocessing: COO -> CSR, tile-nnz tables, partition bounds, degree
-// reorder and the aggregation work list.  Integer work, bit-exact against
+// reorder (the aggregation work list lives in schedule.cu).  Integer work, bit-exact against
 // oracle/gta_oracle.py (csr_build / tile_nnz / partition_bounds / degree_reorder).
 //
 // The global radix sort and prefix sums call CUB (library code shipped with the CUDA
@@ -140,43 +140,6 @@ __global__ void low_word_kernel(const uint64_t* __restrict__ keys, int64_t n, in
   int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) out[i] = int64_t(uint32_t(keys[i]));
-}
-
-// ---- aggregation work list -----------------------------------------------------------------
-
-__global__ void item_counts_kernel(const int64_t* __restrict__ indptr, int64_t row_begin, int64_t rows,
-                                   int32_t chunk, int32_t* __restrict__ nitems, int32_t* __restrict__ nslots) {
-  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (; i < rows; i += stride) {
-    int64_t deg = indptr[row_begin + i + 1] - indptr[row_begin + i];
-    int32_t n = deg <= chunk ? 1 : int32_t((deg + chunk - 1) / chunk);
-    nitems[i] = n;
-    nslots[i] = n > 1 ? n : 0;
-  }
-}
-
-__global__ void item_fill_kernel(const int64_t* __restrict__ indptr, int64_t row_begin, int64_t rows,
-                                 int32_t chunk, const int32_t* __restrict__ item_off,
-                                 const int32_t* __restrict__ slot_off, int4* __restrict__ items) {
-  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (; i < rows; i += stride) {
-    int64_t b = indptr[row_begin + i], e = indptr[row_begin + i + 1];
-    int64_t deg = e - b;
-    int32_t o = item_off[i];
-    if (deg <= chunk) {
-      items[o] = make_int4(int32_t(i), int32_t(b), int32_t(deg), -1);
-    } else {
-      int32_t s = slot_off[i];
-      int32_t n = int32_t((deg + chunk - 1) / chunk);
-      for (int32_t c = 0; c < n; ++c) {
-        int64_t cb = b + int64_t(c) * chunk;
-        int64_t ce = cb + chunk < e ? cb + chunk : e;
-        items[o + c] = make_int4(int32_t(i), int32_t(cb), int32_t(ce - cb), s + c);
-      }
-    }
-  }
 }
 
 // ---- source-id remap for destination-partitioned execution ---------------------------------
@@ -338,62 +301,5 @@ int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* 
   return GTA_OK;
 }
 
-size_t gta_schedule_workspace(int64_t num_rows) {
-  size_t cub_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t*)nullptr, (int32_t*)nullptr, num_rows + 1);
-  return 4 * align_up(size_t(num_rows + 1) * 4, 256) + align_up(cub_bytes, 256);
-}
-
-int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chunk) {
-  if (chunk <= 0) return -1;
-  return num_rows + num_edges / chunk + 1;
-}
-
-int gta_schedule_build(const int64_t* indptr, int64_t row_begin, int64_t row_end, int32_t chunk,
-                       int32_t* items, int64_t items_capacity, int64_t* h_counts, void* workspace,
-                       size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(indptr && items && h_counts && workspace, "gta_schedule_build: null pointer");
-  GTA_REQUIRE(chunk >= 32, "gta_schedule_build: chunk must be >= 32");
-  GTA_REQUIRE(row_end >= row_begin, "gta_schedule_build: empty or negative row range");
-  int64_t rows = row_end - row_begin;
-  h_counts[0] = h_counts[1] = 0;
-  if (rows == 0) return GTA_OK;
-  size_t need = gta_schedule_workspace(rows);
-  if (workspace_bytes < need) {
-    set_error("gta_schedule_build: workspace %zu < required %zu", workspace_bytes, need);
-    return GTA_ERR_WORKSPACE;
-  }
-  size_t nb = align_up(size_t(rows + 1) * 4, 256);
-  char* base = static_cast<char*>(workspace);
-  int32_t* nitems = reinterpret_cast<int32_t*>(base);
-  int32_t* nslots = reinterpret_cast<int32_t*>(base + nb);
-  int32_t* item_off = reinterpret_cast<int32_t*>(base + 2 * nb);
-  int32_t* slot_off = reinterpret_cast<int32_t*>(base + 3 * nb);
-  void* cub_temp = base + 4 * nb;
-  size_t cub_bytes = workspace_bytes - 4 * nb;
-  // the scan runs over rows+1 entries so the last output is the total
-  GTA_CUDA(cudaMemsetAsync(nitems + rows, 0, 4, stream));
-  GTA_CUDA(cudaMemsetAsync(nslots + rows, 0, 4, stream));
-  item_counts_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(indptr, row_begin, rows, chunk, nitems, nslots);
-  GTA_CHECK_LAUNCH("item_counts_kernel");
-  GTA_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, nitems, item_off, rows + 1, stream));
-  GTA_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, nslots, slot_off, rows + 1, stream));
-  count_launch(4);
-  int32_t totals[2];
-  GTA_CUDA(cudaMemcpyAsync(&totals[0], item_off + rows, 4, cudaMemcpyDeviceToHost, stream));
-  GTA_CUDA(cudaMemcpyAsync(&totals[1], slot_off + rows, 4, cudaMemcpyDeviceToHost, stream));
-  GTA_CUDA(cudaStreamSynchronize(stream));
-  if (int64_t(totals[0]) > items_capacity) {
-    set_error("gta_schedule_build: %d items exceed capacity %lld", totals[0], (long long)items_capacity);
-    return GTA_ERR_WORKSPACE;
-  }
-  item_fill_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(indptr, row_begin, rows, chunk, item_off, slot_off,
-                                                           reinterpret_cast<int4*>(items));
-  GTA_CHECK_LAUNCH("item_fill_kernel");
-  h_counts[0] = totals[0];
-  h_counts[1] = totals[1];
-  return GTA_OK;
-}
 
 }  // extern "C"

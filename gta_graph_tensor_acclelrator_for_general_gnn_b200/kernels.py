@@ -83,6 +83,7 @@ class _Workspace:
 
 
 _gemm_ws = _Workspace()
+_agg_ws = _Workspace()      # partial slots of gta_aggregate_f32
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -131,7 +132,7 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
     with ``rowden`` the weight is ``w[k,h] / rowden[i,h]`` (GAT op 9)."""
     lib = _cabi.load()
     _require_cuda(x, w, rowden)
-    sched = sched or g.schedule()
+    sched = sched or g.schedule_for(_ld(x) * 4)
     f = int(x.shape[1])
     rows = sched.row_end - sched.row_begin
     o = out if out is not None else alloc_table(rows, f, x.device)
@@ -146,31 +147,15 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
         wmode = _cabi.W_EDGE_DIV if rowden is not None else _cabi.W_EDGE
         if rowden is not None:
             rowden = rowden.contiguous()
-    partials = None
-    if sched.num_slots:
-        partials = torch.empty(sched.num_slots * f, dtype=torch.float32, device=x.device)
-    _cabi.check(lib.gta_aggregate_f32(_cabi.ptr(sched.items), sched.num_items, sched.num_slots, _cabi.ptr(g.indptr),
-                                      _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh, _cabi.ptr(rowden),
+    partials = _agg_ws.get(sched.num_slots * f, x.device)
+    _cabi.check(lib.gta_aggregate_f32(_cabi.ptr(sched.items), sched.num_items, _cabi.ptr(sched.row_slots), rows,
+                                      sched.num_slots, _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh, _cabi.ptr(rowden),
                                       _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
                                       _cabi.ptr(partials), _stream()), "gta_aggregate_f32")
     return o
 
 
-class GatWorkspace:
-    """Reusable partial-slot buffer of the single-pass GAT kernel."""
-
-    def __init__(self):
-        self.buf = None
-
-    def get(self, n: int, device):
-        if n == 0:
-            return None
-        if self.buf is None or self.buf.numel() < n or self.buf.device != device:
-            self.buf = torch.empty(n, dtype=torch.float32, device=device)
-        return self.buf
-
-
-_gat_ws = GatWorkspace()
+_gat_ws = _Workspace()      # partial slots of the single-pass GAT kernel
 
 
 @_timed("gta_gat_aggregate_f32")
@@ -180,7 +165,7 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
     """GAT ops 3-13 in one pass (online softmax): returns ``out`` or ``(out, rowmax, rowsum)``."""
     lib = _cabi.load()
     _require_cuda(el, er, z)
-    sched = sched or g.schedule()
+    sched = sched or g.schedule_for(_ld(z) * 4)
     f = int(z.shape[1])
     heads = int(el.shape[1])
     rows = sched.row_end - sched.row_begin
@@ -193,8 +178,8 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
         rowsum = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
     stride = int(lib.gta_gat_partial_stride(f, heads))
     partials = _gat_ws.get(sched.num_slots * stride, z.device)
-    _cabi.check(lib.gta_gat_aggregate_f32(_cabi.ptr(sched.items), sched.num_items, sched.num_slots,
-                                          _cabi.ptr(g.indptr), _cabi.ptr(g.indices), _cabi.ptr(el), _cabi.ptr(er),
+    _cabi.check(lib.gta_gat_aggregate_f32(_cabi.ptr(sched.items), sched.num_items, _cabi.ptr(sched.row_slots), rows,
+                                          sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el), _cabi.ptr(er),
                                           heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o), _ld(o), f, epilogue,
                                           _cabi.ptr(rowmax), _cabi.ptr(rowsum), _cabi.ptr(partials), _stream()),
                 "gta_gat_aggregate_f32")

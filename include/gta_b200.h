@@ -97,15 +97,22 @@ size_t gta_reorder_workspace(int64_t num_nodes);
 int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm,
                 void* workspace, size_t workspace_bytes, void* stream);
 
-/* Work list for the aggregation kernels: rows [row_begin,row_end) cut into items of at
- * most `chunk` edges (deterministic, fixed shape).  items: int32[4] per item =
- * {row, edge_begin, edge_count, partial_slot (-1 = single-item row)}.
- * h_counts[0] = number of items, h_counts[1] = number of partial slots (host, after sync). */
-size_t gta_schedule_workspace(int64_t num_rows);
-int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chunk);
-int gta_schedule_build(const int64_t* indptr, int64_t row_begin, int64_t row_end, int32_t chunk,
-                       int32_t* items, int64_t items_capacity, int64_t* h_counts,
-                       void* workspace, size_t workspace_bytes, void* stream);
+/* Work list for the aggregation kernels (schedule.cu).  Rows [row_begin,row_end) are cut into
+ * ITEMS: at most `chunk` consecutive CSR edges of one destination row whose sources all fall in
+ * one column block of `col_block` source ids (col_block <= 0 or >= num_sources: no blocking).
+ * Items are ordered by (column block, row, position) so the CTAs resident at any moment gather
+ * from one L2-sized slice of the source table; this is the B200 form of the reference's
+ * TR x TC tile walk (interpreter.py:85-106; simulator.py:262-263,292).
+ *   items     int32[4] per item = {row - row_begin, edge_begin, edge_count, partial slot | -1}
+ *   row_slots int32[rows+1]: slots of row r are [row_slots[r], row_slots[r+1]) (empty if 1 item)
+ * h_counts[0] = number of items, h_counts[1] = number of partial slots (host, after a sync). */
+size_t gta_schedule_workspace(int64_t num_rows, int64_t num_sources, int64_t col_block);
+int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chunk,
+                               int64_t num_sources, int64_t col_block);
+int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
+                       int64_t row_end, int64_t num_sources, int32_t chunk, int64_t col_block,
+                       int32_t* items, int64_t items_capacity, int32_t* row_slots,
+                       int64_t* h_counts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * COMP_MM (applynode)  --  interpreter.py:145-161 with Weight_Size; simulator.py:338-341.
@@ -130,11 +137,11 @@ int gta_gemm_get_mode(void);
  * interpreter.py:575-638) and plain COMP_ADD gather (interpreter.py:85-106):
  *   out[i,:] = epi( sum_{k in row i, ascending src} weight(k) (x) x[src(k),:] )
  * `w` is [E,wh] (wh = 1 scalar per edge, or wh = heads, head h covering f/wh features);
- * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Rows are the schedule's items; `partials`
- * holds n_slots*f floats for rows cut into several items (combined in item order).
+ * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Work comes from gta_schedule_build; `partials`
+ * holds num_slots*f floats for rows that own several items (combined in slot order).
  * ------------------------------------------------------------------------------------ */
-int gta_aggregate_f32(const int32_t* items, int64_t num_items, int64_t num_slots,
-                      const int64_t* indptr, const int32_t* indices,
+int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
+                      int64_t num_rows, int64_t num_slots, const int32_t* indices,
                       int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
                       int32_t epilogue, float* partials, void* stream);
@@ -149,8 +156,8 @@ int gta_aggregate_f32(const int32_t* items, int64_t num_items, int64_t num_slots
  * Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip).
  * ------------------------------------------------------------------------------------ */
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads);
-int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, int64_t num_slots,
-                          const int64_t* indptr, const int32_t* indices,
+int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
+                          int64_t num_rows, int64_t num_slots, const int32_t* indices,
                           const float* el, const float* er, int32_t heads, float slope,
                           const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum,

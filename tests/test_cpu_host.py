@@ -72,7 +72,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.gta_abi_version() == 1
-    assert lib.gta_schedule_max_items(10, 100, 32) == 14
+    assert lib.gta_schedule_max_items(10, 100, 32, 10, 0) == 14
+    assert lib.gta_schedule_max_items(10, 100, 32, 10, 3) == 44      # 4 column blocks
     assert lib.gta_gat_partial_stride(128, 4) == 136 and lib.gta_gat_partial_stride(16, 1) == 20
 
 

@@ -87,25 +87,44 @@ def test_partition_and_reorder_bit_exact(T, parts):
 
 
 @pytest.mark.parametrize("chunk", [32, 1024])
-def test_schedule_covers_every_edge_once(T, chunk):
+@pytest.mark.parametrize("col_block", [0, 700, 64])
+def test_schedule_covers_every_edge_once(T, chunk, col_block):
     g = _graph("skew", 3000, 90000, 2, 3.0)
-    indptr, _, _ = O.csr_build(g.dst, g.src, g.num_nodes)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, g.num_nodes)
     dg = T.graph.csr_from_coo(g.dst, g.src, g.num_nodes)
-    s = dg.schedule(chunk)
+    s = dg.schedule(chunk, col_block)
     items = s.items.cpu().numpy()[:s.num_items]
-    deg = np.diff(indptr)
-    want_items = np.maximum(1, -(-deg // chunk))
-    assert s.num_items == int(want_items.sum())
-    assert s.num_slots == int(want_items[want_items > 1].sum())
+    row_slots = s.row_slots.cpu().numpy()
+    n = g.num_nodes
+    # expected item count: per (row, column block) segment, ceil(len / chunk); empty rows get one item
+    blk = (indices // col_block) if col_block else np.zeros_like(indices)
+    n_cb = int(-(-n // col_block)) if col_block else 1
+    seg = np.bincount(O.row_ids(indptr) * n_cb + blk, minlength=n * n_cb).reshape(n, n_cb)
+    per_row = (-(-seg // chunk)).sum(axis=1)
+    per_row[per_row == 0] = 1
+    assert s.num_items == int(per_row.sum())
+    assert s.num_slots == int(per_row[per_row > 1].sum())
+    assert np.array_equal(np.diff(row_slots), np.where(per_row > 1, per_row, 0))
     assert np.all(items[:, 2] <= chunk)
     cover = np.zeros(g.num_edges, np.int32)
+    order_key = []
+    next_slot = row_slots[:-1].copy()
     for r, b, c, slot in items:
         cover[b:b + c] += 1
         assert indptr[r] <= b and b + c <= indptr[r + 1]
-        assert (slot >= 0) == (deg[r] > chunk)
+        assert (slot >= 0) == (per_row[r] > 1)
+        cb = int(indices[b] // col_block) if (col_block and c) else 0
+        if col_block and c:
+            assert int(indices[b + c - 1] // col_block) == cb      # an item never straddles column blocks
+        order_key.append((cb, r, b))
     assert np.all(cover == 1)
-    slots = items[items[:, 3] >= 0, 3]
-    assert np.array_equal(np.sort(slots), np.arange(s.num_slots))
+    assert order_key == sorted(order_key)                         # (column block, row, position) order
+    # slots of a row are consecutive and numbered in edge order
+    multi = items[items[:, 3] >= 0]
+    for r, b, c, slot in multi[np.lexsort((multi[:, 1], multi[:, 0]))]:
+        assert slot == next_slot[r]
+        next_slot[r] += 1
+    assert np.array_equal(next_slot, np.where(per_row > 1, row_slots[1:], row_slots[:-1]))
 
 
 @pytest.fixture(params=["simt", "tc"])
@@ -157,8 +176,8 @@ def test_gemm_attention_projections(T, gemm_mode, heads):
 
 @pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
 @pytest.mark.parametrize("f", [16, 64, 128, 256, 500])
-@pytest.mark.parametrize("chunk", [32, 1024])
-def test_aggregate_scalar_weight(T, name, n, e, seed, i0, f, chunk):
+@pytest.mark.parametrize("chunk,col_block", [(32, 0), (1024, 0), (64, 500), (1024, 60)])
+def test_aggregate_scalar_weight(T, name, n, e, seed, i0, f, chunk, col_block):
     g = _graph(name, n, e, seed, i0)
     indptr, indices, _ = O.csr_build(g.dst, g.src, n)
     dg = T.graph.csr_from_coo(g.dst, g.src, n)
@@ -166,13 +185,13 @@ def test_aggregate_scalar_weight(T, name, n, e, seed, i0, f, chunk):
     x = rng.standard_normal((n, f), dtype=np.float32)
     w = synthetic.gcn_edge_norm(indptr, indices)
     xd = T.k.to_table(_dev(T, x))
-    got = T.k.aggregate(dg, xd, _dev(T, w), sched=dg.schedule(chunk)).cpu().numpy()
+    got = T.k.aggregate(dg, xd, _dev(T, w), sched=dg.schedule(chunk, col_block)).cpu().numpy()
     want = O.spmm(indptr, indices, w, x)
     scale = O.spmm(indptr, indices, np.abs(w), np.abs(x))
     assert_close_rowscale(got, want, scale, what=f"aggregate f={f} chunk={chunk}")
     # plain gather ADD (no weights) and run-to-run bitwise reproducibility
-    plain = T.k.aggregate(dg, xd, None, sched=dg.schedule(chunk))
-    again = T.k.aggregate(dg, xd, None, sched=dg.schedule(chunk))
+    plain = T.k.aggregate(dg, xd, None, sched=dg.schedule(chunk, col_block))
+    again = T.k.aggregate(dg, xd, None, sched=dg.schedule(chunk, col_block))
     assert T.torch.equal(plain, again)
     assert_close_rowscale(plain.cpu().numpy(), O.spmm(indptr, indices, None, x),
                           O.spmm(indptr, indices, None, np.abs(x)), what="plain gather")
@@ -180,8 +199,8 @@ def test_aggregate_scalar_weight(T, name, n, e, seed, i0, f, chunk):
 
 @pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
 @pytest.mark.parametrize("f,heads", [(128, 4), (128, 8), (128, 16), (128, 1), (64, 4), (64, 16), (16, 4), (16, 2), (256, 8)])
-@pytest.mark.parametrize("chunk", [32, 1024])
-def test_gat_single_pass(T, name, n, e, seed, i0, f, heads, chunk):
+@pytest.mark.parametrize("chunk,col_block", [(32, 0), (1024, 0), (64, 500), (1024, 60)])
+def test_gat_single_pass(T, name, n, e, seed, i0, f, heads, chunk, col_block):
     g = _graph(name, n, e, seed, i0)
     indptr, indices, _ = O.csr_build(g.dst, g.src, n)
     dg = T.graph.csr_from_coo(g.dst, g.src, n)
@@ -193,8 +212,8 @@ def test_gat_single_pass(T, name, n, e, seed, i0, f, heads, chunk):
     # oracle on the SAME fp32 inputs the kernel sees
     r2 = _gat_from_z(indptr, indices, z32, el32, er32)
     out, rowmax, rowsum = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)),
-                                            sched=dg.schedule(chunk), want_stats=True)
-    out2 = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)), sched=dg.schedule(chunk))
+                                            sched=dg.schedule(chunk, col_block), want_stats=True)
+    out2 = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)), sched=dg.schedule(chunk, col_block))
     assert T.torch.equal(out, out2), "not bitwise reproducible"
     scale = O.gat_rowscale(indptr, indices, z32.astype(np.float64), r2["alpha"])
     assert_close_rowscale(out.cpu().numpy(), r2["Y"], scale, what=f"GAT f={f} H={heads} chunk={chunk}")

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kinds", nargs="*", default=["gat", "spmm"])
+    ap.add_argument("--col-blocks", nargs="*", type=int, default=[1], help="column blocks to try (1 = none)")
     args = ap.parse_args()
     for case in args.cases:
         name, n, e, f, h = case.split(":")
@@ -40,13 +41,13 @@ def main():
         dst, src = device_powerlaw(n, e)
         g = graph.csr_from_coo(dst, src, n)
         del dst, src
-        sched = g.schedule(args.chunk)
         z = kernels.alloc_table(n, f, "cuda")
         z.normal_()
         el = torch.randn(n, h, device="cuda")
         er = torch.randn(n, h, device="cuda")
         w = torch.rand(e, 1, device="cuda")
-        for kind in args.kinds:
+        for kind, ncb in [(k, c) for k in args.kinds for c in args.col_blocks]:
+            sched = g.schedule(args.chunk, 0 if ncb <= 1 else -(-n // ncb))
             fn = (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched)) if kind == "gat" else \
                  (lambda: kernels.aggregate(g, z, w, sched=sched))
             for _ in range(3):
@@ -60,9 +61,9 @@ def main():
             torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / args.iters
             byt = e * (4 + f * 4 + (h * 4 if kind == "gat" else 4)) + n * (f * 4 + 8)
-            print(f"{name:8s} {kind:5s} N={n} E={e} F={f} H={h} items={sched.num_items} slots={sched.num_slots} "
+            print(f"{name:8s} {kind:5s} cb={ncb} chunk={args.chunk} N={n} E={e} F={f} H={h} items={sched.num_items} slots={sched.num_slots} "
                   f"{ms:8.3f} ms  {e / ms / 1e6:7.2f} GTEPS  {byt / ms / 1e6:8.1f} GB/s algorithmic", flush=True)
-        del g, z, el, er, w, sched
+        del g, z, el, er, w
         torch.cuda.empty_cache()
 
 
