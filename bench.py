@@ -169,7 +169,7 @@ def run_reference_arm(args, wl):
         d = np.maximum(deg, 1).astype(np.float64)
         rows = np.repeat(np.arange(sample_rows), np.diff(indptr_s))
         ew = (1.0 / np.sqrt(d[rows] * d[indices_s])).astype(np.float32)
-    c_oracle.load()
+    c_oracle.use_all_cores()
     times = []
     for it in range(args.warmup + args.steps):
         tg, te = cpu_layer_sample(network, indptr_s, indices_s, 0, x, w, al, ar, ew)
@@ -218,6 +218,9 @@ def main():
     ap.add_argument("--cpu-sample-edges", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="honour every STORE_* of the program")
+    ap.add_argument("--chunks", type=int, default=4,
+                    help="multi-GPU: pieces the source all-gather is cut into (overlapped with the aggregation)")
+    ap.add_argument("--no-graph", action="store_true", help="issue kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
@@ -257,7 +260,7 @@ def main():
     full = graph.csr_from_coo(coo.dst, coo.src, n)
     torch.cuda.synchronize()
     if world > 1:
-        part = gdist.make_partition(full, rank, world)
+        part = gdist.make_partition(full, rank, world, chunks=args.chunks)
         g, r0, r1 = part.local, part.row_begin, part.row_end
         exchange = gdist.SourceExchange(part)
     else:
@@ -303,32 +306,61 @@ def main():
         y = step(x_d)
     barrier()
 
+    # the timed step: the same execute() call, captured once into a CUDA graph and replayed
+    graphed = None
+    graph_note = "eager"
+    if world > 1:
+        # capturing the NCCL all-gathers of torch.distributed into the graph hung on the B200 box
+        # (round 1, 2 ranks); multi-rank steps are issued eagerly
+        graph_note = "eager (multi-rank: NCCL all-gather not graph-captured)"
+    elif not args.no_graph:
+        try:
+            graphed = executor.GraphedExecution(lambda: step(x_d))
+            graph_note = "cuda graph replay of execute()"
+        except Exception as exc:      # capture is an optimisation, never a requirement
+            graphed = None
+            graph_note = "eager (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
+            torch.cuda.synchronize()
+    run_step = (lambda: graphed.replay()) if graphed is not None else (lambda: step(x_d))
+    for _ in range(args.warmup):
+        y = run_step()
+    barrier()
+
     # ---- timed region: K steps, resident inputs ---------------------------------------------
     props = torch.cuda.get_device_properties(dev)
     sampler = ClockSampler("GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local_rank))
     if rank == 0:
         sampler.start()
-    kernels.EVENT_LOG = []
     lib.gta_launch_count_reset()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    host_t0 = time.perf_counter()
     for _ in range(args.steps):
-        y = step(x_d)
+        y = run_step()
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps      # CPU time to ENQUEUE a step
     ev1.record()
     barrier()
-    launches = int(lib.gta_launch_count())
     elapsed_ms = ev0.elapsed_time(ev1)
-    log, kernels.EVENT_LOG = kernels.EVENT_LOG, None
     clocks = sampler.stop() if rank == 0 else None
-    per_kernel = {}
-    for name, a, b in log:
-        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = e / (ms_per_step * 1e-3) / 1e9
+
+    # per-kernel durations: the same K steps issued eagerly with CUDA events around every kernel
+    kernels.EVENT_LOG = []
+    lib.gta_launch_count_reset()
+    barrier()
+    for _ in range(args.steps):
+        y = step(x_d)
+    barrier()
+    launches = int(lib.gta_launch_count())
+    log, kernels.EVENT_LOG = kernels.EVENT_LOG, None
+    per_kernel = {}
+    for name, a, b in log:
+        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
 
     # ---- e2e: host features in, result out, through execute() -------------------------------
     # Every step copies ITS features from pinned host memory and ITS result back; the copies of
@@ -399,7 +431,7 @@ def main():
             rows = np.repeat(np.arange(sample_rows), np.diff(indptr_s))
             ew_s = (1.0 / np.sqrt(d[rows] * d[indices_s])).astype(np.float32)
         from oracle import c_oracle
-        c_oracle.load()
+        c_oracle.use_all_cores()
         cpu_layer_sample(network, indptr_s[:65], indices_s[:int(indptr_s[64])], 0, x_h, w_h, al_h, ar_h, ew_s)  # warm
         tg, te = cpu_layer_sample(network, indptr_s, indices_s, 0, x_h, w_h, al_h, ar_h, ew_s)
         e_s = int(indptr_s[-1])
@@ -414,10 +446,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, wl),
-                       "parallelism": f"dst-range partition x{world}" + (", NCCL all-gather of Z and er per layer" if world > 1 else ""),
+                       "parallelism": f"dst-range partition x{world}" + (", one NCCL all-gather of [Z|er] per layer in %d chunks overlapped with the aggregation" % args.chunks if world > 1 else ""),
                        "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
                            e * 4 / 1e6, n * fin * 4 / 1e6, n * F_OUT * 4 / 1e6),
-                       "fuse_across_blocks": not args.no_fuse, "graph_checksum": coo.checksum(),
+                       "fuse_across_blocks": not args.no_fuse, "launch": graph_note, "host_enqueue_ms_per_step": round(host_ms, 3), "graph_checksum": coo.checksum(),
                        "setup_s": round(t_setup, 1)},
             "clocks": clocks,
             "e2e": {"value": e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,

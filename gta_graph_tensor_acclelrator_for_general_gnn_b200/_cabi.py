@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libgta_b200" + ("_" + _TAG if _TAG else "") + ".
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 EPI_NONE, EPI_ELU, EPI_RELU = 0, 1, 2
 W_NONE, W_EDGE, W_EDGE_DIV = 0, 1, 2
+PHASE_MAIN, PHASE_COMBINE, PHASE_ALL = 1, 2, 3
 OPND_EDGE, OPND_DST, OPND_SRC = 0, 1, 2
 BIN_ADD, BIN_MUL, BIN_DIV = 0, 1, 2
 UN_EXP_LEAKY_RELU, UN_ELU, UN_RELU, UN_COPY = 0, 1, 2, 3
@@ -37,21 +38,23 @@ SIGNATURES = {
     "gta_tile_nnz": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "gta_tile_nnz_max": (C.c_int, [_p, _p, _i64, _i64, _p, _sz, C.POINTER(_i32), _p]),
     "gta_partition": (C.c_int, [_p, _i64, _i32, _p, _p]),
-    "gta_remap_sources": (C.c_int, [_p, _i64, _p, _i32, _i64, _p, _p]),
+    "gta_remap_sources": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _p, _p]),
     "gta_reorder_workspace": (_sz, [_i64]),
     "gta_reorder": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "gta_schedule_workspace": (_sz, [_i64, _i64, _i64]),
     "gta_schedule_max_items": (_i64, [_i64, _i64, _i32, _i64, _i64]),
-    "gta_schedule_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i64, _p, C.POINTER(_i64), _p, _sz, _p]),
+    "gta_schedule_col_blocks": (_i32, [_i64, _i64]),
+    "gta_schedule_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i64, _p, C.POINTER(_i64),
+                                     C.POINTER(_i64), _p, _sz, _p]),
     "gta_gemm_workspace": (_sz, [_i32, _i32]),
     "gta_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "gta_gemm_set_mode": (C.c_int, [C.c_int]),
     "gta_gemm_get_mode": (C.c_int, []),
     "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
-                                    _p, _p]),
+                                    _p, _i32, _p]),
     "gta_gat_partial_stride": (_i32, [_i32, _i32]),
-    "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _i32, _f32, _p, _i64, _p, _i64, _i32,
-                                        _i32, _p, _p, _p, _p]),
+    "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _i64,
+                                        _i32, _i32, _p, _p, _p, _i32, _p]),
     "gta_gat_logits_f32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "gta_edge_binary_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _i32, _i32, _i64, _p, _i32,
                                       _i64, _p]),

@@ -102,6 +102,7 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
                  const float* __restrict__ w, int wh, const float* __restrict__ rowden,
                  const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo,
                  int f, int epilogue, float* __restrict__ partials) {
+  __shared__ uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
   const uint64_t pol_stream = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();
   const int lane = threadIdx.x & 31;
@@ -114,6 +115,8 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
   const int count = have ? it.z : 0;
   const int max_count = (LANES == 32) ? count : warp_max_i32(count);
   const int32_t* idx_base = indices + it.y;
+  uint2* se = s_a[threadIdx.x >> 5];
+  const uint2* mine = se + (lane & ~(LANES - 1));
   const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
   const float* xf = x + (active ? fo : 0);
   int head = 0;
@@ -139,31 +142,35 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
       idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
       if (WKIND == 1) w_nxt = ld_stream_f32(w_base + base + LANES + l, pol_stream);
     }
+    // stage {source id, weight} of the batch in shared memory: one LDS.64 per edge in the gather loop
+    se[lane] = make_uint2(uint32_t(my_idx), __float_as_uint(WKIND == 1 ? my_w : 1.f));
+    __syncwarp();
     const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
     if (full) {
       // whole batch, no predicates: kUnroll loads in flight, then their FMAs (the outer loop stays
       // rolled: unrolled, ptxas hoists every load of the batch and spills)
+      if (LANES < 32 || active) {
 #pragma unroll 1
-      for (int j = 0; j < LANES; j += kUnroll) {
-        float4 v[kUnroll];
-        float wv[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          if (j + u < LANES) {
-            const int src = __shfl_sync(0xffffffffu, my_idx, j + u, LANES);
-            wv[u] = 1.f;
-            if (WKIND == 1) wv[u] = __shfl_sync(0xffffffffu, my_w, j + u, LANES);
-            if (LANES < 32 || active) v[u] = ld_row_f32x4(xf + int64_t(src) * ldx, pol_keep);
-            if (WKIND == 2) {
-              wv[u] = __ldg(w_base + int64_t(base + j + u) * wh + head);
-              if (DIV) wv[u] = wv[u] / den;
-            }
-          }
-        }
-        if (LANES < 32 || active) {
+        for (int j = 0; j < LANES; j += kUnroll) {
+          uint2 ed[kUnroll];
+          float4 v[kUnroll];
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) fma4(acc, wv[u], v[u]);
+            if (j + u < LANES) ed[u] = mine[j + u];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) v[u] = ld_row_f32x4(xf + int64_t(ed[u].x) * ldx, pol_keep);
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            if (j + u < LANES) {
+              float ws = __uint_as_float(ed[u].y);
+              if (WKIND == 2) {
+                ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
+                if (DIV) ws = ws / den;
+              }
+              fma4(acc, ws, v[u]);
+            }
+          }
         }
       }
     } else {
@@ -174,12 +181,11 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           if (j + u < LANES) {
-            const int src = __shfl_sync(0xffffffffu, my_idx, j + u, LANES);
-            float ws = 1.f;
-            if (WKIND == 1) ws = __shfl_sync(0xffffffffu, my_w, j + u, LANES);
+            const uint2 ed = mine[j + u];
             const bool ok = active && (j + u) < n;
+            float ws = __uint_as_float(ed.y);
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v[u] = ld_row_f32x4(xf + int64_t(src) * ldx, pol_keep);
+            if (ok) v[u] = ld_row_f32x4(xf + int64_t(ed.x) * ldx, pol_keep);
             if (WKIND == 2) {
               ws = ok ? __ldg(w_base + int64_t(base + j + u) * wh + head) : 0.f;
               if (DIV) ws = ws / den;
@@ -192,6 +198,7 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
           if (j + u < LANES) fma4(acc, wv[u], v[u]);
       }
     }
+    __syncwarp();
   }
   if (!active) return;
   if (it.w < 0) {
@@ -254,7 +261,7 @@ __device__ __forceinline__ float pick(const float (&v)[H], int h) {
 template <int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? kAggMinBlocks : (kAggMinBlocks + 1) / 2)
 gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
-                     const float* __restrict__ el, const float* __restrict__ er, float slope,
+                     const float* __restrict__ el, const float* __restrict__ er, int64_t lder, float slope,
                      const float* __restrict__ z, int64_t ldz, float* __restrict__ out, int64_t ldo,
                      int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
                      float* __restrict__ partials) {
@@ -292,7 +299,7 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
   if (l < count) {
     idx_cur = ld_stream_i32(idx_base + l, pol_stream);
-    load_heads<H>(er + int64_t(idx_cur) * H, er_cur);
+    load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
   }
   if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
 
@@ -305,7 +312,7 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
     for (int h = 0; h < H; ++h) e[h] = (l < n) ? leaky(elr[h] + er_cur[h], slope) : -INFINITY;
     // prefetch: er of the next batch (its ids arrived during the previous iteration), ids of the one after
     idx_cur = idx_nxt;
-    if (base + LANES + l < count) load_heads<H>(er + int64_t(idx_cur) * H, er_cur);
+    if (base + LANES + l < count) load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
     if (base + 2 * LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + 2 * LANES + l, pol_stream);
     float my_scale = 1.f;
 #pragma unroll
@@ -492,11 +499,11 @@ static void dispatch_aggregate(int wkind, bool div, dim3 grid, cudaStream_t st, 
 
 template <int H>
 static int dispatch_gat(int lanes, dim3 grid, cudaStream_t st, const int4* items, int64_t num_items,
-                        const int32_t* indices, const float* el, const float* er, float slope, const float* z,
-                        int64_t ldz, float* out, int64_t ldo, int f, int epi, float* rowmax, float* rowsum,
-                        float* partials) {
+                        const int32_t* indices, const float* el, const float* er, int64_t lder, float slope,
+                        const float* z, int64_t ldz, float* out, int64_t ldo, int f, int epi, float* rowmax,
+                        float* rowsum, float* partials) {
 #define GTA_GAT(L) \
-  gat_aggregate_kernel<L, H><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, slope, z, ldz, out, ldo, f, epi, rowmax, rowsum, partials)
+  gat_aggregate_kernel<L, H><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, lder, slope, z, ldz, out, ldo, f, epi, rowmax, rowsum, partials)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
     case 8: if (H <= 8) { GTA_GAT(8); return GTA_OK; } break;
@@ -518,9 +525,9 @@ int32_t gta_gat_partial_stride(int32_t f, int32_t heads) { return gat_partial_st
 int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_rows,
                       int64_t num_slots, const int32_t* indices, int32_t wmode, const float* w, int32_t wh,
                       const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
-                      int32_t epilogue, float* partials, void* stream_) {
+                      int32_t epilogue, float* partials, int32_t phases, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (num_items == 0) return GTA_OK;
+  if (num_items == 0 && !(phases & GTA_PHASE_COMBINE)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
   GTA_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f, "gta_aggregate_f32: leading dimensions must be multiples of 4 and >= f");
@@ -542,6 +549,7 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
   int lanes = lanes_for(f);
   int64_t threads = num_items * lanes;
   dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
+  if ((phases & GTA_PHASE_MAIN) && num_items > 0) {
   switch (lanes) {
     case 4: dispatch_aggregate<4>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
     case 8: dispatch_aggregate<8>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
@@ -549,7 +557,8 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
     default: dispatch_aggregate<32>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
   }
   GTA_CHECK_LAUNCH("aggregate_kernel");
-  if (num_slots > 0) {
+  }
+  if ((phases & GTA_PHASE_COMBINE) && num_slots > 0) {
     int64_t cthreads = num_rows * 32;
     aggregate_combine_kernel<<<(unsigned)((cthreads + kAggThreads - 1) / kAggThreads), kAggThreads, 0, st>>>(
         row_slots, num_rows, partials, out, ldo, f, epilogue);
@@ -559,11 +568,12 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
 }
 
 int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_rows,
-                          int64_t num_slots, const int32_t* indices, const float* el, const float* er, int32_t heads,
-                          float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
-                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, void* stream_) {
+                          int64_t num_slots, const int32_t* indices, const float* el, const float* er, int64_t lder,
+                          int32_t heads, float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t phases,
+                          void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (num_items == 0) return GTA_OK;
+  if (num_items == 0 && !(phases & GTA_PHASE_COMBINE)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
   GTA_REQUIRE(ldz % 4 == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f, "gta_gat_aggregate_f32: leading dimensions must be multiples of 4 and >= f");
@@ -571,6 +581,8 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
               (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
               "gta_gat_aggregate_f32: tables must be 16-byte aligned");
   GTA_REQUIRE(heads >= 1 && f % heads == 0, "gta_gat_aggregate_f32: heads=%d must divide f=%d", heads, f);
+  GTA_REQUIRE(lder >= heads && (heads % 4 != 0 || lder % 4 == 0) && (heads % 2 != 0 || lder % 2 == 0),
+              "gta_gat_aggregate_f32: er row stride %lld breaks the vector alignment of %d heads", (long long)lder, heads);
   GTA_REQUIRE(num_slots == 0 || (partials && row_slots), "gta_gat_aggregate_f32: partials and row_slots required for %lld slots", (long long)num_slots);
   if ((f / heads) % 4 != 0) {
     set_error("gta_gat_aggregate_f32: per-head width f/heads=%d is not a multiple of 4", f / heads);
@@ -581,7 +593,8 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   int64_t threads = num_items * lanes;
   dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
   int rc = GTA_ERR_UNSUPPORTED;
-#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, grid, st, items, num_items, indices, el, er, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials)
+  if ((phases & GTA_PHASE_MAIN) && num_items > 0) {
+#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, grid, st, items, num_items, indices, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials)
   switch (heads) {
     case 1: GTA_GAT_H(1); break;
     case 2: GTA_GAT_H(2); break;
@@ -596,7 +609,8 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
     return rc;
   }
   GTA_CHECK_LAUNCH("gat_aggregate_kernel");
-  if (num_slots > 0) {
+  }
+  if ((phases & GTA_PHASE_COMBINE) && num_slots > 0) {
     int64_t cthreads = num_rows * 32;
     unsigned cgrid = (unsigned)((cthreads + kAggThreads - 1) / kAggThreads);
 #define GTA_COMB(HH) gat_combine_kernel<HH><<<cgrid, kAggThreads, 0, st>>>(row_slots, num_rows, partials, out, ldo, f, epilogue, rowmax, rowsum)

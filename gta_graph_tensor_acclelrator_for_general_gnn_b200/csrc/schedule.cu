@@ -103,6 +103,8 @@ using namespace gta;
 
 extern "C" {
 
+int32_t gta_schedule_col_blocks(int64_t num_sources, int64_t col_block) { return col_blocks_for(num_sources, col_block); }
+
 size_t gta_schedule_workspace(int64_t num_rows, int64_t num_sources, int64_t col_block) {
   const int64_t n_cb = col_blocks_for(num_sources, col_block);
   const int64_t n = num_rows * n_cb + 1;
@@ -119,8 +121,8 @@ int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chun
 
 int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t row_begin, int64_t row_end,
                        int64_t num_sources, int32_t chunk, int64_t col_block, int32_t* items,
-                       int64_t items_capacity, int32_t* row_slots, int64_t* h_counts, void* workspace,
-                       size_t workspace_bytes, void* stream_) {
+                       int64_t items_capacity, int32_t* row_slots, int64_t* h_counts, int64_t* h_block_begin,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(indptr && items && row_slots && h_counts && workspace, "gta_schedule_build: null pointer");
   GTA_REQUIRE(chunk >= 32, "gta_schedule_build: chunk must be >= 32");
@@ -130,6 +132,8 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
   GTA_REQUIRE(n_cb == 1 || indices, "gta_schedule_build: column blocking needs the CSR indices");
   const int64_t rows = row_end - row_begin;
   h_counts[0] = h_counts[1] = 0;
+  if (h_block_begin)
+    for (int32_t cb = 0; cb <= n_cb; ++cb) h_block_begin[cb] = 0;
   if (rows == 0) return GTA_OK;
   const size_t need = gta_schedule_workspace(rows, num_sources, col_block);
   if (workspace_bytes < need) {
@@ -155,6 +159,10 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
   GTA_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, slots_in, row_slots, rows + 1, stream));
   count_launch(4);
   int32_t totals[2];
+  int32_t block_first[kMaxColBlocks];
+  if (h_block_begin)
+    for (int32_t cb = 0; cb < n_cb; ++cb)
+      GTA_CUDA(cudaMemcpyAsync(&block_first[cb], item_off + int64_t(cb) * rows, 4, cudaMemcpyDeviceToHost, stream));
   GTA_CUDA(cudaMemcpyAsync(&totals[0], item_off + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
   GTA_CUDA(cudaMemcpyAsync(&totals[1], row_slots + rows, 4, cudaMemcpyDeviceToHost, stream));
   GTA_CUDA(cudaStreamSynchronize(stream));
@@ -167,6 +175,10 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
   GTA_CHECK_LAUNCH("sched_fill_kernel");
   h_counts[0] = totals[0];
   h_counts[1] = totals[1];
+  if (h_block_begin) {
+    for (int32_t cb = 0; cb < n_cb; ++cb) h_block_begin[cb] = block_first[cb];
+    h_block_begin[n_cb] = totals[0];
+  }
   return GTA_OK;
 }
 

@@ -203,10 +203,27 @@ class _Run:
 
     def _gat_single_pass(self, numer: Value, z_value: Value, epilogue: int, pos: int):
         sm = self._is_softmax_numerator(numer)
-        el, er = self.force(sm[0]), self.o["source_table"](self.force(sm[1]))
-        z = self.o["source_table"](kernels.to_table(self.force(z_value)))
+        el = self.force(sm[0])
+        ex = self.o["source_table"]
         self.kernel_log.append(("gta_gat_aggregate_f32", pos))
+        if hasattr(ex, "gather_pair"):
+            # partitioned run: [z | er] travel in one gathered table, chunk by chunk on the communication
+            # stream; column block q of the work list starts as soon as chunk q has landed
+            z, er, events = ex.gather_pair(kernels.to_table(self.force(z_value)), self.force(sm[1]), overlap=True)
+            sched = self.g.schedule(col_block=ex.part.col_block) if events is not None else None
+            return kernels.gat_aggregate(self.g, el, er, z, self.o["slope"], epilogue, sched=sched, block_events=events)
+        er = ex(self.force(sm[1]))
+        z = ex(kernels.to_table(self.force(z_value)))
         return kernels.gat_aggregate(self.g, el, er, z, self.o["slope"], epilogue)
+
+    def _gather_sources(self, x: torch.Tensor):
+        """(table, schedule, chunk events) of a source-side table for the fused aggregate kernels."""
+        ex = self.o["source_table"]
+        if hasattr(ex, "gather_one") and x.shape[0] == ex.part.rows:
+            table, events = ex.gather_one(x, overlap=True)
+            sched = self.g.schedule(col_block=ex.part.col_block) if events is not None else None
+            return table, sched, events
+        return ex(x), None, None
 
     def _force_gather(self, v: Value, epilogue: int) -> torch.Tensor:
         k = kernels
@@ -215,9 +232,9 @@ class _Run:
         if src.forced and "rowsum" in src.extra and epilogue == _cabi.EPI_NONE:
             return src.extra["rowsum"]
         if src.kind == "scatter" and src.side == "C" and not src.forced:
-            x = self.o["source_table"](k.to_table(self.force(src.args[0])))
+            x, sched, events = self._gather_sources(k.to_table(self.force(src.args[0])))
             self.kernel_log.append(("gta_aggregate_f32:sum", v.pos))
-            return k.aggregate(self.g, x, None, None, epilogue)
+            return k.aggregate(self.g, x, None, None, epilogue, sched=sched, block_events=events)
         sp = self._split_mul(src)
         if sp is not None:
             xv, wv = sp
@@ -236,11 +253,12 @@ class _Run:
                     if pt.shape[1] == 1 or (x.shape[1] // pt.shape[1]) % 4 == 0:
                         self.kernel_log.append(("gta_aggregate_f32:w/rowden", v.pos))
                         return k.aggregate(self.g, x, pt, dt, epilogue)
-            x = self.o["source_table"](k.to_table(self.force(xv)))
             wt = self.force(wv)
-            if wt.dim() == 1 or wt.shape[1] == 1 or (x.shape[1] // wt.shape[1]) % 4 == 0:
+            xl = k.to_table(self.force(xv))
+            if wt.dim() == 1 or wt.shape[1] == 1 or (xl.shape[1] // wt.shape[1]) % 4 == 0:
+                x, sched, events = self._gather_sources(xl)
                 self.kernel_log.append(("gta_aggregate_f32:w", v.pos))
-                return k.aggregate(self.g, x, wt, None, epilogue)
+                return k.aggregate(self.g, x, wt, None, epilogue, sched=sched, block_events=events)
         # generic: materialise the edge tensor and segment-sum it (identity gather)
         et = k.to_table(self.force(src))
         if "arange" not in self.g.schedules:
@@ -479,3 +497,31 @@ def execute_files(tile_size_list, dataset, network, layer, isReorder, graph: Dev
     isa_path = os.path.join(root, "Results", "Insts", f"{network}-{dataset}-{layer}-{m}.yaml")
     return execute(isa_path, op_path, graph, node_inputs, weights, edge_inputs, network=network,
                    is_reorder=isReorder, **kw)
+
+
+class GraphedExecution:
+    """A program execution captured into a CUDA graph (launch-bound regime: a Cora- or an
+    8-GPU-Reddit-size layer is ~1 ms of kernels, comparable to the Python and launch overhead of
+    issuing them one by one).  ``fn()`` must read only buffers that stay allocated (update them in
+    place between replays) and return its output tensors; NCCL all-gathers inside are captured too.
+
+        g = GraphedExecution(lambda: execute(program, op_info, graph, {0: x_static}, weights, ...))
+        out = g.replay()          # same tensors every time, refreshed contents
+    """
+
+    def __init__(self, fn, warmup: int = 2):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):     # builds work lists / workspaces (these synchronise) outside capture
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs

@@ -40,6 +40,11 @@ class Schedule:
     col_block: int
     row_begin: int
     row_end: int
+    block_begin: list = None  # first item of every column block, then the item count (host ints)
+
+    @property
+    def num_blocks(self) -> int:
+        return len(self.block_begin) - 1
 
 
 #: a gathered table larger than this is walked in column blocks of about COL_BLOCK_BYTES so the
@@ -72,7 +77,7 @@ class DeviceGraph:
     def num_rows(self) -> int:
         return int(self.indptr.shape[0]) - 1
 
-    def schedule(self, chunk: int = DEFAULT_CHUNK, col_block: int = 0) -> Schedule:
+    def schedule(self, chunk: int = DEFAULT_CHUNK, col_block: int = 0) -> Schedule:  # noqa: D401
         """Cached work list; ``col_block`` = source ids per column block (0 = no blocking)."""
         key = (chunk, col_block)
         if key not in self.schedules:
@@ -123,11 +128,14 @@ def build_schedule(indptr: torch.Tensor, indices: torch.Tensor, row_begin: int, 
     ws_bytes = lib.gta_schedule_workspace(rows, num_sources, col_block)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=indptr.device)
     counts = (C.c_int64 * 2)()
+    n_cb = int(lib.gta_schedule_col_blocks(num_sources, col_block))
+    block_begin = (C.c_int64 * (n_cb + 1))()
     _cabi.check(lib.gta_schedule_build(_cabi.ptr(indptr), _cabi.ptr(indices), row_begin, row_end, num_sources, chunk,
-                                       col_block, _cabi.ptr(items), cap, _cabi.ptr(row_slots), counts,
+                                       col_block, _cabi.ptr(items), cap, _cabi.ptr(row_slots), counts, block_begin,
                                        _cabi.ptr(ws), ws_bytes, _stream()), "gta_schedule_build")
     n_items, n_slots = int(counts[0]), int(counts[1])
-    return Schedule(items[:max(n_items, 1)], row_slots, n_items, n_slots, chunk, col_block, row_begin, row_end)
+    return Schedule(items[:max(n_items, 1)], row_slots, n_items, n_slots, chunk, col_block, row_begin, row_end,
+                    [int(v) for v in block_begin])
 
 
 # ---- tile tables: calculate_sparsity / cal_min_sparsity / gen_size -------------------------

@@ -43,6 +43,13 @@ extern "C" {
 #define GTA_EPI_ELU 1
 #define GTA_EPI_RELU 2
 
+/* which part of an aggregation call runs: the item kernel, the merge of multi-item rows, or both.
+ * Callers that overlap a chunked all-gather launch MAIN once per column block (items of that block
+ * only, see h_block_begin) and COMBINE once at the end. */
+#define GTA_PHASE_MAIN 1
+#define GTA_PHASE_COMBINE 2
+#define GTA_PHASE_ALL 3
+
 /* how the per-edge weight of gta_aggregate_f32 is formed */
 #define GTA_W_NONE 0       /* plain sum                       (gather ADD, no applyedge)      */
 #define GTA_W_EDGE 1       /* w[k,h]                          (applyedge MUL, GCN op 1 / GAT 11) */
@@ -86,11 +93,13 @@ int gta_tile_nnz_max(const int64_t* indptr, const int32_t* indices, int64_t num_
 int gta_partition(const int64_t* indptr, int64_t num_nodes, int32_t parts, int64_t* bounds,
                   void* stream);
 
-/* Destination-partitioned execution: the all-gathered source table is [parts, stride, F]
- * (each rank's rows padded to `stride`); out[k] = p*stride + (indices[k] - bounds[p]) with p the
- * owner of indices[k].  Monotonic, so every row keeps its ascending-source order. */
+/* Destination-partitioned execution: the all-gathered source table is [chunks, parts, stride/chunks, F]
+ * (each rank's rows padded to `stride`, cut into `chunks` equal pieces; chunk q of every rank is
+ * contiguous so it can be all-gathered and aggregated while chunk q+1 is in flight).
+ * out[k] = q*(parts*cs) + p*cs + (o - q*cs), p = owner of indices[k], o = indices[k] - bounds[p],
+ * cs = stride/chunks, q = o/cs.  chunks = 1 gives p*stride + o, monotonic in the source id. */
 int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* bounds,
-                      int32_t parts, int64_t stride, int32_t* out, void* stream);
+                      int32_t parts, int64_t stride, int32_t chunks, int32_t* out, void* stream);
 
 /* Degree reorder: perm[new] = old, descending in-degree, stable. */
 size_t gta_reorder_workspace(int64_t num_nodes);
@@ -105,14 +114,18 @@ int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm,
  * TR x TC tile walk (interpreter.py:85-106; simulator.py:262-263,292).
  *   items     int32[4] per item = {row - row_begin, edge_begin, edge_count, partial slot | -1}
  *   row_slots int32[rows+1]: slots of row r are [row_slots[r], row_slots[r+1]) (empty if 1 item)
- * h_counts[0] = number of items, h_counts[1] = number of partial slots (host, after a sync). */
+ * h_counts[0] = number of items, h_counts[1] = number of partial slots; h_block_begin[cb] = first
+ * item of column block cb, h_block_begin[n_cb] = number of items (host arrays, after a sync;
+ * n_cb = gta_schedule_col_blocks(num_sources, col_block)). */
+int32_t gta_schedule_col_blocks(int64_t num_sources, int64_t col_block);
 size_t gta_schedule_workspace(int64_t num_rows, int64_t num_sources, int64_t col_block);
 int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chunk,
                                int64_t num_sources, int64_t col_block);
 int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
                        int64_t row_end, int64_t num_sources, int32_t chunk, int64_t col_block,
                        int32_t* items, int64_t items_capacity, int32_t* row_slots,
-                       int64_t* h_counts, void* workspace, size_t workspace_bytes, void* stream);
+                       int64_t* h_counts, int64_t* h_block_begin, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * COMP_MM (applynode)  --  interpreter.py:145-161 with Weight_Size; simulator.py:338-341.
@@ -144,24 +157,25 @@ int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* ro
                       int64_t num_rows, int64_t num_slots, const int32_t* indices,
                       int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
-                      int32_t epilogue, float* partials, void* stream);
+                      int32_t epilogue, float* partials, int32_t phases, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * GAT edge phase in ONE pass (ops 3-13 of genGraphOP.py:52-62; ISA blocks
  * [4,5,6,7,8] + [3,9,10,11,12,13] of SURVEY Appendix B3 collapsed, online softmax):
  *   s = el[i,h] + er[j,h]; e = leaky_relu(s, slope); alpha = softmax_row(e);
  *   out[i,:] = epi( sum_k alpha[k,h(f)] * z[j,:] )
- * el [rows,H] is indexed by LOCAL row, er/z by source id.
+ * el [rows,H] (dense) is indexed by LOCAL row; er (row stride `lder` elements, so it can live in
+ * the same gathered table as z: [.., F | H] per source) and z by source id.
  * partials: n_slots * gta_gat_partial_stride(f,H) floats  (= f + roundup4(2*H)).
  * Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip).
  * ------------------------------------------------------------------------------------ */
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads);
 int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
                           int64_t num_rows, int64_t num_slots, const int32_t* indices,
-                          const float* el, const float* er, int32_t heads, float slope,
+                          const float* el, const float* er, int64_t lder, int32_t heads, float slope,
                           const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum,
-                          float* partials, void* stream);
+                          float* partials, int32_t phases, void* stream);
 
 /* GAT block [4,5,6,7,8] alone (COMP_ADD 6, COMP_SF 7, STORE_E 7, COMP_ADD 8 gather):
  *   p[k,h] = exp(leaky_relu(el[i,h] + er[j,h]) - rowmax[i,h]),  rowsum[i,h] = sum_k p[k,h].

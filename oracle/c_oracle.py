@@ -44,6 +44,19 @@ def threads() -> int:
     return int(load().gta_oracle_threads())
 
 
+def use_all_cores() -> int:
+    """Lift the OMP_NUM_THREADS=1 that torchrun exports: OpenMP (this library) and the BLAS behind
+    numpy both get every host core.  Returns the OpenMP thread count."""
+    n = os.cpu_count() or 1
+    load().gta_oracle_set_threads(C.c_int(n))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return threads()
+
+
 def _suffix(dtype):
     return {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}[np.dtype(dtype)]
 

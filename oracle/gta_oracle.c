@@ -24,6 +24,15 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core */
+void gta_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int gta_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -73,3 +73,32 @@ def test_remap_formula_matches_partition_layout():
     rows = O.row_ids(indptr)
     same_row = rows[1:] == rows[:-1]
     assert np.all(np.diff(remapped)[same_row] > 0)
+
+
+def _worker_chunked(rank, world, port, bounds, stride, chunks, width, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    part = gdist.Partition(rank, world, bounds, stride, None, bounds[-1], chunks)
+    ex = gdist.SourceExchange(part)
+    local = torch.arange(part.rows * width, dtype=torch.float32).reshape(part.rows, width) + 1000.0 * (rank + 1)
+    full = ex(local)
+    np.save(os.path.join(out_dir, f"chunked_{rank}.npy"), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_chunked_exchange_layout_world2_gloo(tmp_path):
+    """chunks = 2: the gathered table is [chunks, world, stride/chunks, F]; a source with owner p and
+    local offset o sits at q*(world*cs) + p*cs + (o - q*cs) -- the formula gta_remap_sources applies."""
+    bounds, stride, chunks, width = [0, 5, 8], 8, 2, 4
+    port = _free_port()
+    mp.spawn(_worker_chunked, args=(2, port, bounds, stride, chunks, width, str(tmp_path)), nprocs=2, join=True)
+    f0 = np.load(tmp_path / "chunked_0.npy")
+    assert np.array_equal(f0, np.load(tmp_path / "chunked_1.npy")) and f0.shape == (16, width)
+    cs = stride // chunks
+    for p in range(2):
+        rows = bounds[p + 1] - bounds[p]
+        want = np.arange(rows * width, dtype=np.float32).reshape(rows, width) + 1000.0 * (p + 1)
+        for o in range(rows):
+            q = o // cs
+            assert np.array_equal(f0[q * (2 * cs) + p * cs + (o - q * cs)], want[o])
