@@ -218,8 +218,9 @@ def main():
     ap.add_argument("--cpu-sample-edges", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="honour every STORE_* of the program")
-    ap.add_argument("--chunks", type=int, default=4,
-                    help="multi-GPU: pieces the source all-gather is cut into (overlapped with the aggregation)")
+    ap.add_argument("--chunks", type=int, default=1,
+                    help="multi-GPU: pieces the source all-gather is cut into; > 1 overlaps the transfer with the "
+                         "aggregation (measured slower on 8 B200: NCCL's CTAs compete with the gather kernel)")
     ap.add_argument("--no-graph", action="store_true", help="issue kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -446,7 +447,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, wl),
-                       "parallelism": f"dst-range partition x{world}" + (", one NCCL all-gather of [Z|er] per layer in %d chunks overlapped with the aggregation" % args.chunks if world > 1 else ""),
+                       "parallelism": f"dst-range partition x{world}" + (", one NCCL all-gather of [Z|er] per layer" + (" in %d overlapped chunks" % args.chunks if args.chunks > 1 else "") if world > 1 else ""),
                        "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
                            e * 4 / 1e6, n * fin * 4 / 1e6, n * F_OUT * 4 / 1e6),
                        "fuse_across_blocks": not args.no_fuse, "launch": graph_note, "host_enqueue_ms_per_step": round(host_ms, 3), "graph_checksum": coo.checksum(),

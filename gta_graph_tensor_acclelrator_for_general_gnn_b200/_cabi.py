@@ -47,7 +47,8 @@ SIGNATURES = {
     "gta_schedule_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i64, _p, C.POINTER(_i64),
                                      C.POINTER(_i64), _p, _sz, _p]),
     "gta_gemm_workspace": (_sz, [_i32, _i32]),
-    "gta_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _p, _sz, _p]),
+    "gta_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _i64, _p, _sz,
+                               _p]),
     "gta_gemm_set_mode": (C.c_int, [C.c_int]),
     "gta_gemm_get_mode": (C.c_int, []),
     "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,

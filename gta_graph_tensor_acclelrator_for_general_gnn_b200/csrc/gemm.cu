@@ -8,11 +8,11 @@ namespace gta {
 int gemm_simt_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
                      int k, int f, cudaStream_t st);
 int attn_project_launch(const float* z, int64_t ldz, int64_t num_rows, int f, const float* al, const float* ar,
-                        int heads, float* el, float* er, cudaStream_t st);
+                        int heads, float* el, float* er, int64_t lder, cudaStream_t st);
 // returns GTA_ERR_UNSUPPORTED when the shape is outside the tensor-core kernel's rules
 int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
-                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, void* workspace,
-                   size_t workspace_bytes, cudaStream_t st);
+                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, int64_t lder,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t gemm_tc_workspace(int k, int f);
 }  // namespace gta
 
@@ -33,7 +33,7 @@ size_t gta_gemm_workspace(int32_t k, int32_t f) { return (k > 0 && f > 0) ? gemm
 
 int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
                  int32_t k, int32_t f, const float* al, const float* ar, int32_t heads, float* el, float* er,
-                 void* workspace, size_t workspace_bytes, void* stream_) {
+                 int64_t lder, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (num_rows == 0) return GTA_OK;
   GTA_REQUIRE(x && w && z, "gta_gemm_f32: null pointer");
@@ -41,8 +41,10 @@ int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float
   GTA_REQUIRE(ldx >= k && ldw >= f && ldz >= f, "gta_gemm_f32: leading dimension smaller than the row");
   const bool want_attn = (el && al) || (er && ar);
   GTA_REQUIRE(!want_attn || heads >= 1, "gta_gemm_f32: heads must be >= 1 when el/er are requested");
+  if (lder <= 0) lder = heads;
+  GTA_REQUIRE(!want_attn || lder >= heads, "gta_gemm_f32: er row stride %lld < heads %d", (long long)lder, heads);
   if (g_gemm_mode != 1) {
-    int rc = gemm_tc_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, al, ar, heads, el, er, workspace, workspace_bytes, st);
+    int rc = gemm_tc_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, al, ar, heads, el, er, lder, workspace, workspace_bytes, st);
     if (rc == GTA_OK) return GTA_OK;
     if (rc != GTA_ERR_UNSUPPORTED) return rc;
     if (g_gemm_mode == 2) {
@@ -53,7 +55,7 @@ int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float
   }
   int rc = gemm_simt_launch(x, ldx, w, ldw, z, ldz, num_rows, k, f, st);
   if (rc != GTA_OK) return rc;
-  if (want_attn) return attn_project_launch(z, ldz, num_rows, f, al, ar, heads, el, er, st);
+  if (want_attn) return attn_project_launch(z, ldz, num_rows, f, al, ar, heads, el, er, lder, st);
   return GTA_OK;
 }
 

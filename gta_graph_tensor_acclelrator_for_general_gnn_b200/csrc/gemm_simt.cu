@@ -123,7 +123,8 @@ gemm_simt_kernel(const float* __restrict__ x, int64_t ldx, const float* __restri
 // GAT ops 1 and 2 (applynode MM with [F,H] weights): el = Z.Al, er = Z.Ar; warp per row.
 __global__ void __launch_bounds__(256)
 attn_project_kernel(const float* __restrict__ z, int64_t ldz, int64_t num_rows, int f, const float* __restrict__ al,
-                    const float* __restrict__ ar, int heads, float* __restrict__ el, float* __restrict__ er) {
+                    const float* __restrict__ ar, int heads, float* __restrict__ el, float* __restrict__ er,
+                    int64_t lder) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (r >= num_rows) return;
@@ -141,7 +142,7 @@ attn_project_kernel(const float* __restrict__ z, int64_t ldz, int64_t num_rows, 
     }
     if (lane == 0) {
       if (el) el[r * heads + h] = sl;
-      if (er) er[r * heads + h] = sr;
+      if (er) er[r * lder + h] = sr;
     }
   }
 }
@@ -164,8 +165,8 @@ int gemm_simt_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, f
 }
 
 int attn_project_launch(const float* z, int64_t ldz, int64_t num_rows, int f, const float* al, const float* ar,
-                        int heads, float* el, float* er, cudaStream_t st) {
-  attn_project_kernel<<<(unsigned)((num_rows * 32 + 255) / 256), 256, 0, st>>>(z, ldz, num_rows, f, al, ar, heads, el, er);
+                        int heads, float* el, float* er, int64_t lder, cudaStream_t st) {
+  attn_project_kernel<<<(unsigned)((num_rows * 32 + 255) / 256), 256, 0, st>>>(z, ldz, num_rows, f, al, ar, heads, el, er, lder);
   GTA_CHECK_LAUNCH("attn_project_kernel");
   return GTA_OK;
 }

@@ -35,6 +35,7 @@ struct TcParams {
   int k_blocks;
   int f;
   int heads;
+  int64_t lder;      // row stride of er (it may live beside z in a gathered [F | H] table)
   const float* al;
   const float* ar;
   float* el;
@@ -278,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         for (int h = 0; h < HR; ++h) {
           if (h < p.heads) {
             if (p.el) p.el[row * p.heads + h] = sl[h];
-            if (p.er) p.er[row * p.heads + h] = sr[h];
+            if (p.er) p.er[row * p.lder + h] = sr[h];
           }
         }
       }
@@ -371,8 +372,8 @@ size_t gemm_tc_workspace(int k, int f) {
 }
 
 int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
-                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, void* workspace,
-                   size_t workspace_bytes, cudaStream_t st) {
+                   int k, int f, const float* al, const float* ar, int heads, float* el, float* er, int64_t lder,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const bool want_attn = (el && al) || (er && ar);
   if (f % 16 != 0 || f < 16 || f > 256) return GTA_ERR_UNSUPPORTED;
   if (ldx % 4 != 0 || ldz % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(z) & 15))
@@ -400,6 +401,7 @@ int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, flo
   TcParams p{};
   p.z = z; p.ldz = ldz; p.num_rows = num_rows; p.k_blocks = kp / kTcBK; p.f = f;
   p.heads = want_attn ? heads : 0;
+  p.lder = lder;
   p.al = want_attn ? al : nullptr; p.ar = want_attn ? ar : nullptr;
   p.el = want_attn ? el : nullptr; p.er = want_attn ? er : nullptr;
   p.tiles = int((num_rows + kTcBM - 1) / kTcBM);

@@ -118,6 +118,17 @@ class SourceExchange:
             if hi > lo:
                 buf[q, p.rank, :hi - lo, col:col + w].copy_(t[lo:hi])
 
+    def local_views(self, f: int, h: int, device):
+        """``(z [rows, f], er [rows, h])`` views of this rank's slot of the gathered ``[F | H]`` table,
+        for producers (the GEMM) that write there directly.  Only when the slot is one contiguous
+        piece (chunks == 1); otherwise None."""
+        p = self.part
+        if p.chunks != 1:
+            return None
+        width = f + (h + 3) // 4 * 4
+        slot = self.buffer(width, device)[0, p.rank, :p.rows]
+        return slot[:, :f], slot[:, f:f + h]
+
     # -- collective -------------------------------------------------------------------------------
     def gather(self, width: int, device, overlap: bool = False):
         """All-gather every chunk in place.  ``overlap=False``: the current stream waits for all of
@@ -149,8 +160,11 @@ class SourceExchange:
         ``[z (F) | er (H)]``.  Returns ``(z_view, er_view, events | None)`` (strided views)."""
         f, h = int(z.shape[1]), int(er.shape[1])
         width = f + (h + 3) // 4 * 4
-        self.store_local(z, width, 0)
-        self.store_local(er, width, f)
+        views = self.local_views(f, h, z.device)
+        in_place = views is not None and views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()
+        if not in_place:             # the producer did not write into the slot: copy
+            self.store_local(z, width, 0)
+            self.store_local(er, width, f)
         if overlap and self.part.chunks > 1:
             full, events = self.gather(width, z.device, overlap=True)
         else:

@@ -451,7 +451,13 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
             kids = [q for q in ops if env[q].kind == "mm" and env[q].args[0] is v and not env[q].forced]
             if len(kids) == 2 and env[kids[0]].width == env[kids[1]].width and env[kids[0]].width <= 16:
                 x = kernels.to_table(run.force(v.args[0]))
-                z, el, er = kernels.gemm(x, v.weight, env[kids[0]].weight, env[kids[1]].weight)
+                ex = opts["source_table"]
+                views = None
+                if hasattr(ex, "local_views") and x.shape[0] == ex.part.rows:
+                    # partitioned run: Z and er go straight into this rank's slot of the gathered table
+                    views = ex.local_views(int(v.weight.shape[1]), env[kids[1]].width, x.device)
+                z, el, er = kernels.gemm(x, v.weight, env[kids[0]].weight, env[kids[1]].weight,
+                                         out=views[0] if views else None, er_out=views[1] if views else None)
                 v.tensor, env[kids[0]].tensor, env[kids[1]].tensor = z, el, er
                 run.kernel_log.append(("gta_gemm_f32+el/er", p))
 

@@ -93,9 +93,10 @@ def set_gemm_mode(mode: str) -> None:
 
 @_timed("gta_gemm_f32")
 def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: torch.Tensor | None = None,
-         out: torch.Tensor | None = None):
+         out: torch.Tensor | None = None, er_out: torch.Tensor | None = None):
     """COMP_MM applynode: ``Z = X.W`` and optionally the fused GAT ops 1/2 ``el = Z.Al``,
-    ``er = Z.Ar``.  Returns ``Z`` or ``(Z, el, er)``."""
+    ``er = Z.Ar``.  Returns ``Z`` or ``(Z, el, er)``.  ``out`` / ``er_out`` may be (strided) views of a
+    larger table, e.g. this rank's slot of the gathered ``[F | H]`` source table."""
     lib = _cabi.load()
     _require_cuda(x, w, al, ar)
     n, k = x.shape
@@ -113,11 +114,14 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
             el = torch.empty((n, heads), dtype=torch.float32, device=x.device)
         if ar is not None:
             ar = ar.contiguous()
-            er = torch.empty((n, heads), dtype=torch.float32, device=x.device)
+            er = er_out if er_out is not None else torch.empty((n, heads), dtype=torch.float32, device=x.device)
+            if er.stride(1) != 1 or er.shape != (n, heads):
+                raise ValueError("er_out must be an [N, H] view with unit column stride")
     ws_bytes = int(lib.gta_gemm_workspace(k, f))
     ws = _gemm_ws.get((ws_bytes + 3) // 4, x.device)
     _cabi.check(lib.gta_gemm_f32(_cabi.ptr(x), _ld(x), _cabi.ptr(w), f, _cabi.ptr(z), _ld(z), n, k, f,
                                  _cabi.ptr(al), _cabi.ptr(ar), heads, _cabi.ptr(el), _cabi.ptr(er),
+                                 (int(er.stride(0)) if er is not None and n > 1 else heads),
                                  _cabi.ptr(ws), ws_bytes, _stream()),
                 "gta_gemm_f32")
     if al is None and ar is None:

@@ -131,7 +131,9 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
  * COMP_MM (applynode)  --  interpreter.py:145-161 with Weight_Size; simulator.py:338-341.
  * Z[N,F] = X[N,K] . W[K,F]  (template/ISA_defination.yaml:28-31, einsum j,ij->i).
  * Optional fused GAT ops 1,2 (genGraphOP.py:50-51): el = Z.Al, er = Z.Ar with Al,Ar [F,H]
- * row-major dense; pass NULL to skip.  fp32 in / fp32 out, fp32-accurate (rtol 1e-5).
+ * row-major dense; pass NULL to skip.  el is dense [N,H]; er has row stride `lder` elements
+ * (0 = dense), so a partitioned run can write z and er straight into its slot of the gathered
+ * [F | H] source table.  fp32 in / fp32 out, fp32-accurate (rtol 1e-5).
  * ------------------------------------------------------------------------------------ */
 /* `workspace` (gta_gemm_workspace(k,f) bytes, 128-byte aligned) holds the hi/lo TF32 split of W
  * for the tensor-core kernel; without it the call takes the FFMA kernel. */
@@ -139,7 +141,7 @@ size_t gta_gemm_workspace(int32_t k, int32_t f);
 int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw,
                  float* z, int64_t ldz, int64_t num_rows, int32_t k, int32_t f,
                  const float* al, const float* ar, int32_t heads, float* el, float* er,
-                 void* workspace, size_t workspace_bytes, void* stream);
+                 int64_t lder, void* workspace, size_t workspace_bytes, void* stream);
 /* kernel choice of gta_gemm_f32: 0 = auto (tcgen05 3xTF32 when the shape is eligible, else
  * FFMA), 1 = force the FFMA kernel, 2 = force tcgen05 (GTA_ERR_UNSUPPORTED if ineligible). */
 int gta_gemm_set_mode(int mode);
