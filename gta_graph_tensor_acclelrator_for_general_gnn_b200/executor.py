@@ -393,19 +393,22 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
         typ, comp, order_ = op["TYPE"], op["COMP_TYPE"], op["ORDER"]
         wout = _width(op["OUTPUT"]["size_per_feature"])
         args = []
+        n_ext = 0
         for slot, q in enumerate(prods[pos]):
             if q == -1:
-                if typ in ("applyedge", "gather"):
-                    if pos not in edge_inputs:
-                        raise ExecutionError(f"op {pos} needs an external edge input (edge_inputs[{pos}])")
-                    t = edge_inputs[pos]
-                    t = t if t.dim() == 2 else t[:, None]
-                    args.append(Value("edge", tensor=t.contiguous(), width=int(t.shape[1]), pos=pos))
-                else:
-                    if pos not in node_inputs:
-                        raise ExecutionError(f"op {pos} needs an external node input (node_inputs[{pos}])")
-                    t = node_inputs[pos]
-                    args.append(Value("node", tensor=t, width=int(t.shape[1]), pos=pos))
+                # external ('-1') input: one tensor, or a list when the op has several (GIN op 3: [x, eps])
+                table, label = (edge_inputs, "edge_inputs") if typ in ("applyedge", "gather") else (node_inputs, "node_inputs")
+                if pos not in table:
+                    raise ExecutionError(f"op {pos} needs an external input ({label}[{pos}])")
+                t = table[pos]
+                if isinstance(t, (list, tuple)):
+                    if n_ext >= len(t):
+                        raise ExecutionError(f"op {pos} has more external inputs than {label}[{pos}] provides")
+                    t = t[n_ext]
+                n_ext += 1
+                t = t if t.dim() == 2 else t[:, None]
+                kind = "edge" if typ in ("applyedge", "gather") else "node"
+                args.append(Value(kind, tensor=t.contiguous() if kind == "edge" else t, width=int(t.shape[1]), pos=pos))
             else:
                 args.append(env[q])
         if not prods[pos]:

@@ -186,6 +186,31 @@ def tile_tables(g: DeviceGraph, start: int, end: int):
     return sizes, [cal_min_sparsity(g, s) for s in sizes]
 
 
+def write_tile_tables(g: DeviceGraph, dataset: str, sizes, root: str = ".") -> tuple:
+    """Write the files the reference's preprocessing CLI writes (code/preprocessing.py:83-96), in its
+    format (``yaml.dump`` of plain int lists): ``dataset/<ds>/adj_<ds>_<SR>_1.yaml`` for every tile
+    size, ``sizelist_<ds>.yaml`` and ``maxlist_<ds>.yaml`` -- computed on device from the CSR, no dense
+    ``N x N`` adjacency.  Returns ``(sizelist, maxlist)``; these are what ``compile()`` reads
+    (vTCAD/code/compiler.py:504-505) and what ``simulate()`` reads (simulator.py:481-482)."""
+    import os
+
+    import yaml
+    d = os.path.join(root, "dataset", dataset)
+    os.makedirs(d, exist_ok=True)
+    sizes = [int(s) for s in sizes]
+    maxlist = []
+    for sr in sizes:
+        table = calculate_sparsity(g, sr).cpu().tolist()
+        with open(os.path.join(d, f"adj_{dataset}_{sr}_1.yaml"), "w") as f:
+            yaml.dump(table, f)
+        maxlist.append(max((max(row) for row in table if row), default=0))
+    with open(os.path.join(d, f"sizelist_{dataset}.yaml"), "w") as f:
+        yaml.dump(sizes, f)
+    with open(os.path.join(d, f"maxlist_{dataset}.yaml"), "w") as f:
+        yaml.dump(maxlist, f)
+    return sizes, maxlist
+
+
 # ---- partition / reorder -----------------------------------------------------------------------
 
 def partition_bounds(g: DeviceGraph, parts: int) -> torch.Tensor:

@@ -141,14 +141,14 @@ def main():
     with open("dataset/cora/maxlist_cora.yaml", "w") as f:
         yaml.dump([min(s, 168) for s in sizes], f)
     # (some compile() plans crash the reference's own interpret(); take the first that lowers)
-    for reorder in (True, False):
-        for rank, cand in enumerate(comp.compile("cora", "GAT", "layer1", reorder, False, True, False)[0]):
+    for network, reorder in (("GAT", True), ("GAT", False), ("SGC", False), ("GraphSAGE", False), ("GIN", False)):
+        for rank, cand in enumerate(comp.compile("cora", network, "layer1", reorder, False, True, False)[0]):
             try:
-                interp.interpret("cora", "GAT", reorder, "layer1", cand[0], cand[1])
+                interp.interpret("cora", network, reorder, "layer1", cand[0], cand[1])
             except Exception:
                 continue
-            programs.append(("GAT", "cora", 1, reorder, [list(b) for b in cand[0]], [list(t) for t in cand[1]]))
-            print("GAT cora reorder=%s: compile() plan rank %d lowers: %s" % (reorder, rank, cand[0]))
+            programs.append((network, "cora", 1, reorder, [list(b) for b in cand[0]], [list(t) for t in cand[1]]))
+            print("%s cora reorder=%s: compile() plan rank %d lowers: %s" % (network, reorder, rank, cand[0]))
             break
     for network, ds, layer, reorder, op_array, tiles in programs:
         interp.interpret(ds, network, reorder, f"layer{layer}", op_array, tiles)
@@ -187,6 +187,12 @@ def main():
         for sr in sizes:
             prep.save(tables[str(sr)], f"dataset/{tag}/adj_{tag}_{sr}_1.yaml")
         maxlist = [prep.cal_min_sparsity(tag, sr) for sr in sizes]
+        # the reference's own on-disk files for one graph (byte-for-byte targets of graph.write_tile_tables)
+        if tag == "g97":
+            prep.save(sizes, f"dataset/{tag}/sizelist_{tag}.yaml")
+            prep.save(maxlist, f"dataset/{tag}/maxlist_{tag}.yaml")
+            for name in [f"adj_{tag}_{sr}_1.yaml" for sr in sizes] + [f"sizelist_{tag}.yaml", f"maxlist_{tag}.yaml"]:
+                shutil.copy(f"dataset/{tag}/{name}", os.path.join(out, "tiles", name))
         manifest["tiles"].append({"file": f"tiles/{tag}.npz", "sizes": sizes, "maxlist": [int(v) for v in maxlist],
                                   "gen_size_16_100": prep.gen_size(16, 100)})
     np.count_nonzero = _cnz

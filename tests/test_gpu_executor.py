@@ -45,12 +45,16 @@ def _inputs(op_info, n, e, seed=0):
                 rng.uniform(-0.1, 0.1, size=(widths[0], fout)).astype(np.float32)
         if not ins:
             node_inputs[pos] = rng.standard_normal((n, widths[0]), dtype=np.float32)
+        ext = []
         for slot, q in enumerate(ins):
             if q == -1:
                 if op["TYPE"] in ("applyedge", "gather"):
-                    edge_inputs[pos] = rng.uniform(0.05, 1.0, size=(e, 1)).astype(np.float32)
+                    ext.append(rng.uniform(0.05, 1.0, size=(e, 1)).astype(np.float32))
                 else:
-                    node_inputs[pos] = rng.standard_normal((n, widths[slot]), dtype=np.float32)
+                    ext.append(rng.standard_normal((n, widths[slot]), dtype=np.float32))
+        if ext:
+            target = edge_inputs if op["TYPE"] in ("applyedge", "gather") else node_inputs
+            target[pos] = ext[0] if len(ext) == 1 else ext
     return node_inputs, weights, edge_inputs
 
 
@@ -89,7 +93,8 @@ def test_program_matches_oracle(rt, prog, fuse):
     node_inputs, weights, edge_inputs = _inputs(op_info, n, e)
     sem = O.NETWORK_SEMANTICS.get((prog["network"], prog["reorder"]), {})
     ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, semantics=sem, stabilize=True)
-    dev = lambda d: {k: rt.torch.from_numpy(v).cuda() for k, v in d.items()}
+    up = lambda v: [rt.torch.from_numpy(a).cuda() for a in v] if isinstance(v, list) else rt.torch.from_numpy(v).cuda()
+    dev = lambda d: {k: up(v) for k, v in d.items()}
     out, log = rt.ex.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs),
                              network=prog["network"], is_reorder=prog["reorder"], fuse_across_blocks=fuse,
                              check_shapes=(prog["dataset"] == "cora"), return_log=True)
@@ -105,8 +110,10 @@ def test_program_matches_oracle(rt, prog, fuse):
     if prog["network"] == "GAT" and fuse:
         assert "gta_gat_aggregate_f32" in names, names     # the edge phase collapsed to one pass
         assert not any(k.startswith("gta_edge_") for k in names), names
-    if prog["network"] == "GCN":
+    if prog["network"] in ("GCN", "SGC", "GraphSAGE", "GIN"):
         assert any(k.startswith("gta_aggregate_f32") for k in names), names
+        if fuse:        # E x Fin scatters stay virtual: no materialising copy, no generic edge kernel
+            assert not any(k.startswith("gta_edge_") for k in names), names
 
 
 def test_intermediate_outputs_on_request(rt):
@@ -154,3 +161,25 @@ def test_rejects_bad_programs(rt):
     with pytest.raises(rt.ex.ExecutionError, match="generated for"):
         small = rt.graph.csr_from_coo(np.array([0, 1], np.int32), np.array([1, 0], np.int32), 2)
         rt.ex.execute(records, op_info, small, {}, {})
+
+
+def test_chrome_timeline_export(rt, tmp_path):
+    """GPU timeline in the simulator's chrome_timeline.json schema (simulator.py:360-382)."""
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import trace
+    prog = next(p for p in PROGRAMS if p["file"].endswith("GCN-cora-layer1-trans__0_1-2-3.yaml"))
+    op_info = _load(prog["opgraph"])
+    g, _, _, dg = _graph(rt, "cora")
+    node_inputs, weights, edge_inputs = _inputs(op_info, g.num_nodes, g.num_edges)
+    dev = lambda d: {k: rt.torch.from_numpy(v).cuda() for k, v in d.items()}
+    rt.k.EVENT_LOG = []
+    try:
+        _, log = rt.ex.execute(_load(prog["file"]), op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs),
+                               network="GCN", is_reorder=True, return_log=True)
+        path = trace.save_timeline(rt.k.EVENT_LOG, log, str(tmp_path))
+    finally:
+        rt.k.EVENT_LOG = None
+    events = json.load(open(path))
+    assert [e["name"] for e in events] == ["COMP_MM", "COMP_MUL_COMP_ADD"]
+    assert [e["pid"] for e in events] == ["MM", "VEC_ALU"]
+    assert all(e["ph"] == "X" and e["dur"] > 0 and set(e) == {"name", "cat", "ph", "ts", "dur", "pid", "tid"} for e in events)
+    assert events[0]["ts"] == 0 and events[1]["ts"] >= events[0]["dur"] * 0.5

@@ -291,3 +291,19 @@ def test_errors_are_loud(T):
                           T.torch.zeros((64, 16), device="cuda"))
     with pytest.raises(RuntimeError):
         T.k.aggregate(dg, T.torch.zeros((64, 8)))          # CPU tensor: no CPU fallback
+
+
+def test_tile_table_files_match_the_reference_byte_for_byte(T, golden_dir, tmp_path):
+    """graph.write_tile_tables writes what code/preprocessing.py's CLI writes (adj_<ds>_<SR>_1.yaml,
+    sizelist, maxlist) -- compared with the files the unmodified reference produced."""
+    import os
+    z = np.load(os.path.join(golden_dir, "tiles", "g97.npz"))
+    n = int(z["num_nodes"])
+    dg = T.graph.csr_from_coo(z["dst"], z["src"], n)
+    sizes = sorted(int(k.split("_")[1]) for k in z.files if k.startswith("table_"))
+    T.graph.write_tile_tables(dg, "g97", sizes, root=str(tmp_path))
+    names = [f"adj_g97_{sr}_1.yaml" for sr in sizes] + ["sizelist_g97.yaml", "maxlist_g97.yaml"]
+    for name in names:
+        want = open(os.path.join(golden_dir, "tiles", name), "rb").read()
+        got = open(os.path.join(str(tmp_path), "dataset", "g97", name), "rb").read()
+        assert got == want, name
