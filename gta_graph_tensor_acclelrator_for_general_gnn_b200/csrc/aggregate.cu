@@ -77,6 +77,13 @@ __device__ __forceinline__ float4 ld_row_f32x4(const float* p, uint64_t pol_keep
 #endif
   return v;
 }
+// address of a gathered row: base + id * row_bytes as ONE mad.wide.u32 (a 64-bit multiply by the
+// leading dimension costs five integer instructions per edge; profiles/r01_gat_aggregate_v2)
+__device__ __forceinline__ const float* row_ptr(const float* base, uint32_t id, uint32_t row_bytes) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(id), "r"(row_bytes), "l"(base));
+  return reinterpret_cast<const float*>(r);
+}
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.x = fmaf(w, v.x, acc.x);
   acc.y = fmaf(w, v.y, acc.y);
@@ -119,6 +126,7 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
   const uint2* mine = se + (lane & ~(LANES - 1));
   const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
   const float* xf = x + (active ? fo : 0);
+  const uint32_t row_bytes = uint32_t(ldx) * 4u;
   int head = 0;
   float den = 1.f;
   if (WKIND == 2) head = active ? fo / (f / wh) : 0;
@@ -159,7 +167,7 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
             if (j + u < LANES) ed[u] = mine[j + u];
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) v[u] = ld_row_f32x4(xf + int64_t(ed[u].x) * ldx, pol_keep);
+            if (j + u < LANES) v[u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
             if (j + u < LANES) {
@@ -185,7 +193,7 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
             const bool ok = active && (j + u) < n;
             float ws = __uint_as_float(ed.y);
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v[u] = ld_row_f32x4(xf + int64_t(ed.x) * ldx, pol_keep);
+            if (ok) v[u] = ld_row_f32x4(row_ptr(xf, ed.x, row_bytes), pol_keep);
             if (WKIND == 2) {
               ws = ok ? __ldg(w_base + int64_t(base + j + u) * wh + head) : 0.f;
               if (DIV) ws = ws / den;
@@ -282,6 +290,7 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   const int32_t* idx_base = indices + it.y;
   const int head = active ? fo / (f / H) : 0;
   const float* zf = z + (active ? fo : 0);
+  const uint32_t row_bytes = uint32_t(ldz) * 4u;
   uint2* se = s_e[threadIdx.x >> 5];
   const uint2* mine = se + gbase * H + head;
 
@@ -340,7 +349,7 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
             if (j + u < LANES) ed[u] = mine[(j + u) * H];
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) v[u] = ld_row_f32x4(zf + int64_t(ed[u].x) * ldz, pol_keep);
+            if (j + u < LANES) v[u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u)
             if (j + u < LANES) fma4(acc, __uint_as_float(ed[u].y), v[u]);
@@ -357,7 +366,7 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
             const uint2 ed = mine[(j + u) * H];
             pv[u] = __uint_as_float(ed.y);
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && (j + u) < n) v[u] = ld_row_f32x4(zf + int64_t(ed.x) * ldz, pol_keep);
+            if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, ed.x, row_bytes), pol_keep);
           }
         }
 #pragma unroll
@@ -530,7 +539,7 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
   if (num_items == 0 && !(phases & GTA_PHASE_COMBINE)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
-  GTA_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f, "gta_aggregate_f32: leading dimensions must be multiples of 4 and >= f");
+  GTA_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f && ldx < (int64_t(1) << 30), "gta_aggregate_f32: leading dimensions must be multiples of 4, >= f and < 2^30");
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gta_aggregate_f32: tables must be 16-byte aligned");
   GTA_REQUIRE(wmode >= GTA_W_NONE && wmode <= GTA_W_EDGE_DIV, "gta_aggregate_f32: bad wmode %d", wmode);
   GTA_REQUIRE(num_slots == 0 || (partials && row_slots), "gta_aggregate_f32: partials and row_slots required for %lld slots", (long long)num_slots);
@@ -576,7 +585,7 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   if (num_items == 0 && !(phases & GTA_PHASE_COMBINE)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
-  GTA_REQUIRE(ldz % 4 == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f, "gta_gat_aggregate_f32: leading dimensions must be multiples of 4 and >= f");
+  GTA_REQUIRE(ldz % 4 == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f && ldz < (int64_t(1) << 30), "gta_gat_aggregate_f32: leading dimensions must be multiples of 4, >= f and < 2^30");
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
               "gta_gat_aggregate_f32: tables must be 16-byte aligned");
