@@ -144,8 +144,9 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
     int n = count - base;
     n = n < 0 ? 0 : (n > LANES ? LANES : n);
     const int my_idx = idx_nxt;
-    float my_w = w_nxt;
-    if (WKIND == 1 && DIV) my_w = my_w / den;
+    float my_w = (l < n) ? w_nxt : 0.f;
+    // divide only where an edge exists: a neighbouring group's empty row has den = 0 (0/0 = NaN)
+    if (WKIND == 1 && DIV && l < n) my_w = my_w / den;
     if (base + LANES + l < count) {
       idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
       if (WKIND == 1) w_nxt = ld_stream_f32(w_base + base + LANES + l, pol_stream);
@@ -191,12 +192,15 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
           if (j + u < LANES) {
             const uint2 ed = mine[j + u];
             const bool ok = active && (j + u) < n;
-            float ws = __uint_as_float(ed.y);
+            float ws = ok ? __uint_as_float(ed.y) : 0.f;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) v[u] = ld_row_f32x4(row_ptr(xf, ed.x, row_bytes), pol_keep);
             if (WKIND == 2) {
-              ws = ok ? __ldg(w_base + int64_t(base + j + u) * wh + head) : 0.f;
-              if (DIV) ws = ws / den;
+              ws = 0.f;
+              if (ok) {
+                ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
+                if (DIV) ws = ws / den;
+              }
             }
             wv[u] = ws;
           }
@@ -449,6 +453,147 @@ gat_combine_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, cons
 }
 
 // ----------------------------------------------------------------------------------------
+// GAT edge phase, lane-local-head variant (any H with (F/H) % 4 == 0; used for H >= 8)
+//
+// The staged kernel above keeps el/max/sum/er for ALL heads in every lane (5H registers: H = 16
+// spills and runs at a quarter of the H = 4 speed).  Here a lane tracks only the head its own 4
+// features belong to: one scalar er gather per edge (the 32 lanes of a row read the H
+// consecutive floats of er[j]: one wavefront), online softmax over groups of kUnroll edges, no
+// per-head arrays, no shuffles.  Lanes of one head see the same edges in the same order, so their
+// (max, sum) are bit-identical.
+// ----------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
+gat_aggregate_llh_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
+                         const float* __restrict__ el, const float* __restrict__ er, int64_t lder, int heads,
+                         float slope, const float* __restrict__ z, int64_t ldz, float* __restrict__ out,
+                         int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
+                         float* __restrict__ rowsum, float* __restrict__ partials) {
+  __shared__ uint32_t s_id[kAggWarps][32];
+  const uint64_t pol_stream = policy_evict_first();
+  const uint64_t pol_keep = policy_evict_last();
+  const int lane = threadIdx.x & 31;
+  const int l = lane & (LANES - 1);
+  const int64_t group = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) / LANES;
+  const int fo = blockIdx.y * 128 + 4 * l;
+  const bool have = group < num_items;
+  const bool active = have && fo < f;
+  int4 it = have ? items[group] : make_int4(0, 0, 0, -1);
+  const int count = have ? it.z : 0;
+  const int max_count = (LANES == 32) ? count : warp_max_i32(count);
+  const int32_t* idx_base = indices + it.y;
+  const int d = f / heads;
+  const int head = active ? fo / d : 0;
+  const float* zf = z + (active ? fo : 0);
+  const float* erh = er + head;
+  const uint32_t row_bytes = uint32_t(ldz) * 4u;
+  const uint32_t er_bytes = uint32_t(lder) * 4u;
+  uint32_t* sid = s_id[threadIdx.x >> 5];
+  const uint32_t* mine = sid + (lane & ~(LANES - 1));
+  const float elh = have ? __ldg(el + int64_t(it.x) * heads + head) : 0.f;
+
+  float m = -INFINITY, s = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int idx_nxt = 0;
+  if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+  for (int base = 0; base < max_count; base += LANES) {
+    int n = count - base;
+    n = n < 0 ? 0 : (n > LANES ? LANES : n);
+    sid[lane] = uint32_t(idx_nxt);
+    if (base + LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
+    __syncwarp();
+    const int nmax = (LANES == 32) ? n : LANES;
+#pragma unroll 1
+    for (int j = 0; j < nmax; j += kUnroll) {
+      float e[kUnroll];
+      float4 v[kUnroll];
+      uint32_t id[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const bool ok = (j + u) < n;
+        e[u] = ok ? leaky(elh + __ldg(row_ptr(erh, id[u], er_bytes)), slope) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, id[u], row_bytes), pol_keep);
+      }
+      float bm = e[0];
+#pragma unroll
+      for (int u = 1; u < kUnroll; ++u) bm = fmaxf(bm, e[u]);
+      const float mn = fmaxf(m, bm);
+      if (mn != -INFINITY) {          // at least one edge seen so far
+        const float sc = expf(m - mn);          // m = -inf on the first group: sc = 0, acc and s are 0 anyway
+        acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+        s *= sc;
+        m = mn;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          // e = -inf for the padding of the last group: p = 0.  ex2.approx path: the argument is <= 0 and
+          // terms that matter have small |e - mn|; relative error < 2e-6, inside the 1e-5 tolerance
+          const float p = __expf(e[u] - mn);
+          s += p;
+          fma4(acc, p, v[u]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!active) return;
+  const bool head_leader = (fo % d) == 0;       // one lane per head publishes the statistics
+  if (it.w < 0) {
+    st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, s > 0.f ? 1.f / s : 0.f, epilogue));
+    if (head_leader) {
+      if (rowmax) rowmax[int64_t(it.x) * heads + head] = (count > 0) ? m : 0.f;
+      if (rowsum) rowsum[int64_t(it.x) * heads + head] = s;
+    }
+  } else {
+    float* part = partials + int64_t(it.w) * gat_partial_stride(f, heads);
+    *reinterpret_cast<float4*>(part + fo) = acc;
+    if (head_leader) {
+      part[f + head] = m;
+      part[f + heads + head] = s;
+    }
+  }
+}
+
+// merge of the (max, sum, acc) triples for any H: every lane handles the head of its own columns
+__global__ void __launch_bounds__(kAggThreads)
+gat_combine_llh_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, const float* __restrict__ partials,
+                       float* __restrict__ out, int64_t ldo, int f, int heads, int epilogue,
+                       float* __restrict__ rowmax, float* __restrict__ rowsum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
+  if (r >= num_rows) return;
+  const int s0 = row_slots[r], s1 = row_slots[r + 1];
+  if (s1 == s0) return;
+  const int stride = gat_partial_stride(f, heads);
+  const int d = f / heads;
+  for (int fo = 4 * lane; fo < f; fo += 128) {
+    const int head = fo / d;
+    float gm = -INFINITY;
+    for (int c = s0; c < s1; ++c) gm = fmaxf(gm, partials[int64_t(c) * stride + f + head]);
+    float gs = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = s0; c < s1; ++c) {
+      const float* part = partials + int64_t(c) * stride;
+      const float mc = part[f + head];
+      if (mc == -INFINITY) continue;
+      const float sc = expf(mc - gm);
+      gs = fmaf(part[f + heads + head], sc, gs);
+      fma4(acc, sc, *reinterpret_cast<const float4*>(part + fo));
+    }
+    *reinterpret_cast<float4*>(out + r * ldo + fo) = epilogue4(acc, gs > 0.f ? 1.f / gs : 0.f, epilogue);
+    if ((fo % d) == 0) {
+      if (rowmax) rowmax[r * heads + head] = (gm == -INFINITY) ? 0.f : gm;
+      if (rowsum) rowsum[r * heads + head] = gs;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // GAT block [4,5,6,7,8]: numerators p[E,H] (STORE_E) and row sums S[N,H]; warp per row
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -601,36 +746,50 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   int lanes = lanes_for(f);
   int64_t threads = num_items * lanes;
   dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
-  int rc = GTA_ERR_UNSUPPORTED;
+  // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
+  // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint)
+  const bool staged = heads == 1 || heads == 2 || heads == 4;
   if ((phases & GTA_PHASE_MAIN) && num_items > 0) {
+    if (staged) {
+      int rc = GTA_ERR_UNSUPPORTED;
 #define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, grid, st, items, num_items, indices, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials)
-  switch (heads) {
-    case 1: GTA_GAT_H(1); break;
-    case 2: GTA_GAT_H(2); break;
-    case 4: GTA_GAT_H(4); break;
-    case 8: GTA_GAT_H(8); break;
-    case 16: GTA_GAT_H(16); break;
-    default: break;
-  }
+      switch (heads) {
+        case 1: GTA_GAT_H(1); break;
+        case 2: GTA_GAT_H(2); break;
+        default: GTA_GAT_H(4); break;
+      }
 #undef GTA_GAT_H
-  if (rc != GTA_OK) {
-    set_error("gta_gat_aggregate_f32: no kernel for heads=%d, f=%d", heads, f);
-    return rc;
-  }
-  GTA_CHECK_LAUNCH("gat_aggregate_kernel");
+      if (rc != GTA_OK) {
+        set_error("gta_gat_aggregate_f32: no kernel for heads=%d, f=%d", heads, f);
+        return rc;
+      }
+    } else {
+#define GTA_LLH(L) gat_aggregate_llh_kernel<L><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, lder, heads, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials)
+      switch (lanes) {
+        case 4: GTA_LLH(4); break;
+        case 8: GTA_LLH(8); break;
+        case 16: GTA_LLH(16); break;
+        default: GTA_LLH(32); break;
+      }
+#undef GTA_LLH
+    }
+    GTA_CHECK_LAUNCH("gat_aggregate_kernel");
   }
   if ((phases & GTA_PHASE_COMBINE) && num_slots > 0) {
     int64_t cthreads = num_rows * 32;
     unsigned cgrid = (unsigned)((cthreads + kAggThreads - 1) / kAggThreads);
+    if (staged) {
 #define GTA_COMB(HH) gat_combine_kernel<HH><<<cgrid, kAggThreads, 0, st>>>(row_slots, num_rows, partials, out, ldo, f, epilogue, rowmax, rowsum)
-    switch (heads) {
-      case 1: GTA_COMB(1); break;
-      case 2: GTA_COMB(2); break;
-      case 4: GTA_COMB(4); break;
-      case 8: GTA_COMB(8); break;
-      default: GTA_COMB(16); break;
-    }
+      switch (heads) {
+        case 1: GTA_COMB(1); break;
+        case 2: GTA_COMB(2); break;
+        default: GTA_COMB(4); break;
+      }
 #undef GTA_COMB
+    } else {
+      gat_combine_llh_kernel<<<cgrid, kAggThreads, 0, st>>>(row_slots, num_rows, partials, out, ldo, f, heads, epilogue,
+                                                            rowmax, rowsum);
+    }
     GTA_CHECK_LAUNCH("gat_combine_kernel");
   }
   return GTA_OK;

@@ -141,14 +141,16 @@ def main():
     with open("dataset/cora/maxlist_cora.yaml", "w") as f:
         yaml.dump([min(s, 168) for s in sizes], f)
     # (some compile() plans crash the reference's own interpret(); take the first that lowers)
-    for network, reorder in (("GAT", True), ("GAT", False), ("SGC", False), ("GraphSAGE", False), ("GIN", False)):
-        for rank, cand in enumerate(comp.compile("cora", network, "layer1", reorder, False, True, False)[0]):
+    for network, reorder, layer in (("GAT", True, 1), ("GAT", False, 1), ("SGC", False, 1), ("GraphSAGE", False, 1),
+                                    ("GIN", False, 1), ("GAT", False, 2), ("GAT", False, 3), ("GCN", True, 2),
+                                    ("GCN", True, 3)):
+        for rank, cand in enumerate(comp.compile("cora", network, f"layer{layer}", reorder, False, True, False)[0]):
             try:
-                interp.interpret("cora", network, reorder, "layer1", cand[0], cand[1])
+                interp.interpret("cora", network, reorder, f"layer{layer}", cand[0], cand[1])
             except Exception:
                 continue
-            programs.append((network, "cora", 1, reorder, [list(b) for b in cand[0]], [list(t) for t in cand[1]]))
-            print("%s cora reorder=%s: compile() plan rank %d lowers: %s" % (network, reorder, rank, cand[0]))
+            programs.append((network, "cora", layer, reorder, [list(b) for b in cand[0]], [list(t) for t in cand[1]]))
+            print("%s cora layer%d reorder=%s: compile() plan rank %d lowers: %s" % (network, layer, reorder, rank, cand[0]))
             break
     for network, ds, layer, reorder, op_array, tiles in programs:
         interp.interpret(ds, network, reorder, f"layer{layer}", op_array, tiles)

@@ -235,7 +235,7 @@ def _gat_from_z(indptr, indices, z, el, er):
     return {"p": p, "S": s, "rowmax": mx, "alpha": alpha, "O": o, "Y": O.elu(o)}
 
 
-@pytest.mark.parametrize("heads,f", [(4, 128), (16, 128), (4, 64)])
+@pytest.mark.parametrize("heads,f", [(4, 128), (16, 128), (4, 64), (16, 64), (8, 64), (2, 16)])
 def test_gat_two_block_path(T, heads, f):
     """ISA blocks [4,5,6,7,8] then [3,9,10,11,12,13] as separate kernels (STORE_E p honoured)."""
     g = _graph("skew", 3000, 90000, 2, 3.0)
@@ -307,3 +307,22 @@ def test_tile_table_files_match_the_reference_byte_for_byte(T, golden_dir, tmp_p
         want = open(os.path.join(golden_dir, "tiles", name), "rb").read()
         got = open(os.path.join(str(tmp_path), "dataset", "g97", name), "rb").read()
         assert got == want, name
+
+
+def test_divided_weights_next_to_an_empty_row(T):
+    """Two rows share a warp when F <= 64; an EMPTY row (rowden = 0) beside a non-empty one must stay 0,
+    not 0/0 (regression: GAT layer 2 with STORE_* honoured)."""
+    n, f, h = 8, 64, 16
+    dst = np.array([1, 1, 1, 3, 3], dtype=np.int32)      # rows 0, 2, 4..7 have no edges
+    src = np.array([0, 2, 5, 1, 7], dtype=np.int32)
+    dg = T.graph.csr_from_coo(dst, src, n)
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((n, f), dtype=np.float32)
+    el = rng.standard_normal((n, h), dtype=np.float32)
+    er = rng.standard_normal((n, h), dtype=np.float32)
+    p, _, rowsum = T.k.gat_logits(dg, _dev(T, el), _dev(T, er))
+    out = T.k.aggregate(dg, T.k.to_table(_dev(T, z)), p, rowden=rowsum, epilogue=T.cabi.EPI_ELU).cpu().numpy()
+    assert np.all(np.isfinite(out))
+    assert np.all(out[[0, 2, 4, 5, 6, 7]] == 0)
+    scalar = T.k.aggregate(dg, T.k.to_table(_dev(T, z)), p[:, :1].contiguous(), rowden=rowsum[:, :1].contiguous()).cpu().numpy()
+    assert np.all(np.isfinite(scalar)) and np.all(scalar[[0, 2, 4, 5, 6, 7]] == 0)

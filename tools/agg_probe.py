@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kinds", nargs="*", default=["gat", "spmm"])
     ap.add_argument("--col-blocks", nargs="*", type=int, default=[1], help="column blocks to try (1 = none)")
+    ap.add_argument("--split-launch", action="store_true", help="gate per column block (block 0, then the rest)")
     args = ap.parse_args()
     for case in args.cases:
         name, n, e, f, h = case.split(":")
@@ -48,8 +49,9 @@ def main():
         w = torch.rand(e, 1, device="cuda")
         for kind, ncb in [(k, c) for k in args.kinds for c in args.col_blocks]:
             sched = g.schedule(args.chunk, 0 if ncb <= 1 else -(-n // ncb))
-            fn = (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched)) if kind == "gat" else \
-                 (lambda: kernels.aggregate(g, z, w, sched=sched))
+            ev = [None] * sched.num_blocks if args.split_launch else None
+            fn = (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched, block_events=ev)) if kind == "gat" else \
+                 (lambda: kernels.aggregate(g, z, w, sched=sched, block_events=ev))
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
