@@ -249,6 +249,10 @@ def main():
     ap.add_argument("--chunks", type=int, default=1,
                     help="multi-GPU: pieces the source all-gather is cut into; > 1 overlaps the transfer with the "
                          "aggregation (measured slower on 8 B200: NCCL's CTAs compete with the gather kernel)")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="multi-GPU source exchange: NCCL all-gather, or peer-to-peer copies on the copy engines")
+    ap.add_argument("--alt", default="", help="multi-GPU: also time these exchanges in the same process, "
+                                               "e.g. 'p2p:1,p2p:4,nccl:4' (exchange:chunks), reported in config.alt")
     ap.add_argument("--no-graph", action="store_true", help="issue kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -292,6 +296,15 @@ def main():
         part = gdist.make_partition(full, rank, world, chunks=args.chunks)
         g, r0, r1 = part.local, part.row_begin, part.row_end
         exchange = gdist.SourceExchange(part)
+        if args.exchange == "p2p":
+            try:
+                probe = gdist.PeerExchange(part)
+                probe._setup(F_OUT + 4 if network == "GAT" else F_OUT, dev)      # all ranks agree or all raise
+                exchange = probe
+            except RuntimeError as exc:
+                if rank == 0:
+                    print("p2p exchange unavailable, using the NCCL all-gather: %s" % exc, file=sys.stderr)
+                args.exchange = "nccl"
     else:
         g, r0, r1, exchange = full, 0, n, None
     edge_w = None
@@ -308,7 +321,7 @@ def main():
         sample_rows = int(min(n, max(64, np.searchsorted(np.cumsum(deg_h), args.cpu_sample_edges) + 1)))
         e_s = int(host_csr[0][sample_rows])
         host_csr = (host_csr[0][:sample_rows + 1].copy(), full.indices[:e_s].cpu().numpy(), sample_rows, deg_h)
-    if world > 1:
+    if world > 1 and not args.alt:
         del full
         torch.cuda.empty_cache()
     g.schedule()
@@ -390,6 +403,39 @@ def main():
     per_kernel = {}
     for name, a, b in log:
         per_kernel.setdefault(name, []).append(a.elapsed_time(b))
+
+    # ---- optional: other exchange strategies on the same graph, same process --------------------
+    alt_results = {}
+    if world > 1 and args.alt:
+        for spec in args.alt.split(","):
+            kind, ch = spec.split(":")
+            part_a = gdist.make_partition(full, rank, world, chunks=int(ch))
+            if edge_inputs is not None and int(ch) > 1:
+                continue          # the GCN edge weights would need the re-sorted edge order
+            try:
+                ex_a = gdist.PeerExchange(part_a) if kind == "p2p" else gdist.SourceExchange(part_a)
+                if kind == "p2p":
+                    ex_a._setup(F_OUT + 4 if network == "GAT" else F_OUT, dev)
+            except RuntimeError:
+                alt_results[spec] = None
+                continue
+            g_a = part_a.local
+
+            def step_a(x_dev, g_a=g_a, ex_a=ex_a):
+                return executor.execute(program, op_info, g_a, {0: x_dev}, weights, edge_inputs, network=network,
+                                        is_reorder=reorder, fuse_across_blocks=not args.no_fuse, source_table=ex_a,
+                                        check_shapes=False)[final_op]
+            for _ in range(args.warmup):
+                step_a(x_d)
+            barrier()
+            ev0.record()
+            for _ in range(args.steps):
+                step_a(x_d)
+            ev1.record()
+            barrier()
+            ta = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            alt_results[spec] = round(float(ta.item()) / args.steps, 4)
 
     # ---- e2e: host features in, result out, through execute() -------------------------------
     # Every step copies ITS features from pinned host memory and ITS result back; the copies of
@@ -475,10 +521,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, wl),
-                       "parallelism": f"dst-range partition x{world}" + (", one NCCL all-gather of [Z|er] per layer" + (" in %d overlapped chunks" % args.chunks if args.chunks > 1 else "") if world > 1 else ""),
+                       "parallelism": f"dst-range partition x{world}" + ((", one NCCL all-gather of [Z|er] per layer" if args.exchange == "nccl" else ", [Z|er] pulled from the peers' IPC-mapped slots by copy engines")
+                                        + (" in %d overlapped chunks" % args.chunks if args.chunks > 1 else "") if world > 1 else ""),
                        "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
                            e * 4 / 1e6, n * fin * 4 / 1e6, n * F_OUT * 4 / 1e6),
-                       "fuse_across_blocks": not args.no_fuse, "launch": graph_note, "host_enqueue_ms_per_step": round(host_ms, 3), "graph_checksum": coo.checksum(),
+                       "fuse_across_blocks": not args.no_fuse, "alt_ms_per_step": alt_results or None, "launch": graph_note, "host_enqueue_ms_per_step": round(host_ms, 3), "graph_checksum": coo.checksum(),
                        "setup_s": round(t_setup, 1)},
             "clocks": clocks,
             "e2e": {"value": e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,

@@ -39,6 +39,12 @@ SIGNATURES = {
     "gta_tile_nnz_max": (C.c_int, [_p, _p, _i64, _i64, _p, _sz, C.POINTER(_i32), _p]),
     "gta_partition": (C.c_int, [_p, _i64, _i32, _p, _p]),
     "gta_remap_sources": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _p, _p]),
+    "gta_ipc_alloc": (C.c_int, [_sz, C.POINTER(_p)]),
+    "gta_ipc_free": (C.c_int, [_p]),
+    "gta_ipc_export": (C.c_int, [_p, C.c_char_p]),
+    "gta_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_p)]),
+    "gta_ipc_close": (C.c_int, [_p]),
+    "gta_copy_many": (C.c_int, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_i64), _i32, _p]),
     "gta_reorder_workspace": (_sz, [_i64]),
     "gta_reorder": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "gta_schedule_workspace": (_sz, [_i64, _i64, _i64]),

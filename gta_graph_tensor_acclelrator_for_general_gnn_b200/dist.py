@@ -185,3 +185,170 @@ class SourceExchange:
         if t.shape[0] != self.part.rows:
             return t            # already a gathered table
         return self.gather_one(t)[0]
+
+
+# ---- peer-to-peer exchange on the copy engines --------------------------------------------------
+
+class _IpcBuffer:
+    """fp32 buffer cudaMalloc'ed by the library (so its CUDA IPC handle names a base pointer), exposed
+    to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, shape):
+        import ctypes as C
+        self.lib = _cabi.load()
+        self.shape = tuple(int(v) for v in shape)
+        n = 4
+        for v in self.shape:
+            n *= v
+        ptr = C.c_void_p()
+        _cabi.check(self.lib.gta_ipc_alloc(n, C.byref(ptr)), "gta_ipc_alloc")
+        self.ptr = int(ptr.value)
+        self.nbytes = n
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self) -> torch.Tensor:
+        return torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def handle(self) -> bytes:
+        import ctypes as C
+        buf = C.create_string_buffer(64)
+        _cabi.check(self.lib.gta_ipc_export(self.ptr, buf), "gta_ipc_export")
+        return buf.raw
+
+    def close(self):
+        if self.ptr:
+            self.lib.gta_ipc_free(self.ptr)
+            self.ptr = 0
+
+
+class PeerExchange(SourceExchange):
+    """Same contract as :class:`SourceExchange`, but the transfer is a set of device-to-device copies
+    from the peers' IPC-mapped slot buffers on a copy stream (copy engines over NVLink, no SMs), so it
+    really overlaps the aggregation kernel.  Per step: a one-element NCCL all-reduce on the compute
+    stream (every rank's slot is written), then ``chunks`` groups of ``world`` copies, one event per
+    chunk.  The slot buffers are double-buffered: a peer may still be pulling step i while this rank
+    already writes step i+1.  Raises ``RuntimeError`` on every rank if any rank cannot map its peers
+    (the caller falls back to the NCCL all-gather)."""
+
+    def __init__(self, part: Partition, group=None):
+        super().__init__(part, group)
+        self._state = {}
+
+    def _setup(self, width: int, device):
+        import ctypes as C
+        key = (width, torch.device(device))
+        if key in self._state:
+            return self._state[key]
+        p = self.part
+        lib = _cabi.load()
+        ld = (width + 3) // 4 * 4
+        cs = p.chunk_rows
+        st = {"step": 0, "ld": ld}
+        ok = 1
+        err = ""
+        try:
+            st["mine"] = [_IpcBuffer((p.chunks, cs, ld)) for _ in range(2)]
+            st["mine_t"] = [m.tensor() for m in st["mine"]]
+            handles = [m.handle() for m in st["mine"]]
+        except Exception as exc:          # keep going to the collective below so every rank agrees
+            ok, err, handles = 0, str(exc), [b"", b""]
+        gathered = [None] * p.world
+        dist.all_gather_object(gathered, handles, group=self.group)
+        peer = [[0, 0] for _ in range(p.world)]
+        if ok:
+            try:
+                for r in range(p.world):
+                    for b in range(2):
+                        if r == p.rank:
+                            peer[r][b] = st["mine"][b].ptr
+                        else:
+                            mapped = C.c_void_p()
+                            _cabi.check(lib.gta_ipc_open(gathered[r][b], C.byref(mapped)), "gta_ipc_open")
+                            peer[r][b] = int(mapped.value)
+            except Exception as exc:
+                ok, err = 0, str(exc)
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            raise RuntimeError("peer-to-peer exchange unavailable on at least one rank" + (": " + err if err else ""))
+        table = self.buffer(width, device)
+        chunk_bytes = cs * ld * 4
+        plans = []
+        for b in range(2):
+            per_chunk = []
+            for q in range(p.chunks):
+                dsts, srcs, sizes = [], [], []
+                for k in range(p.world):
+                    r = (p.rank + k) % p.world            # own slot first, then round the ring
+                    rows_r = p.bounds[r + 1] - p.bounds[r]
+                    valid = max(0, min(cs, rows_r - q * cs))
+                    if valid == 0:
+                        continue
+                    dsts.append(table.data_ptr() + (q * p.world + r) * chunk_bytes)
+                    srcs.append(peer[r][b] + q * chunk_bytes)
+                    sizes.append(valid * ld * 4)
+                n = len(dsts)
+                per_chunk.append(((C.c_void_p * n)(*dsts), (C.c_void_p * n)(*srcs), (C.c_int64 * n)(*sizes), n))
+            plans.append(per_chunk)
+        st.update(peer=peer, plans=plans, sync=torch.zeros(1, dtype=torch.float32, device=device),
+                  stream=torch.cuda.Stream(), events=[torch.cuda.Event() for _ in range(p.chunks)])
+        self._state[key] = st
+        return st
+
+    def local_views(self, f: int, h: int, device):
+        p = self.part
+        if p.chunks != 1:
+            return None
+        st = self._setup(f + (h + 3) // 4 * 4, device)
+        slot = st["mine_t"][st["step"] % 2][0, :p.rows]
+        return slot[:, :f], slot[:, f:f + h]
+
+    def _store(self, st, t: torch.Tensor, col: int):
+        p = self.part
+        mine = st["mine_t"][st["step"] % 2]
+        cs, w = p.chunk_rows, int(t.shape[1])
+        for q in range(p.chunks):
+            lo, hi = q * cs, min((q + 1) * cs, p.rows)
+            if hi > lo:
+                mine[q, :hi - lo, col:col + w].copy_(t[lo:hi])
+
+    def _pull(self, st, width: int, device, overlap: bool):
+        lib = _cabi.load()
+        p = self.part
+        cur = torch.cuda.current_stream()
+        dist.all_reduce(st["sync"], group=self.group)       # on the compute stream: every slot is written
+        copy = st["stream"]
+        copy.wait_stream(cur)
+        b = st["step"] % 2
+        for q in range(p.chunks):
+            dsts, srcs, sizes, n = st["plans"][b][q]
+            _cabi.check(lib.gta_copy_many(dsts, srcs, sizes, n, copy.cuda_stream), "gta_copy_many")
+            st["events"][q].record(copy)
+        st["step"] += 1
+        buf = self.buffer(width, device)
+        table = buf.view(-1, buf.shape[-1])[:, :width]
+        if overlap and p.chunks > 1:
+            return table, list(st["events"])
+        cur.wait_event(st["events"][-1])
+        return table, None
+
+    @kernels._timed("p2p_gather")
+    def gather_pair(self, z: torch.Tensor, er: torch.Tensor, overlap: bool = False):
+        f, h = int(z.shape[1]), int(er.shape[1])
+        width = f + (h + 3) // 4 * 4
+        st = self._setup(width, z.device)
+        views = self.local_views(f, h, z.device)
+        in_place = views is not None and views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()
+        if not in_place:
+            self._store(st, z, 0)
+            self._store(st, er, f)
+        full, events = self._pull(st, width, z.device, overlap)
+        return full[:, :f], full[:, f:f + h], events
+
+    @kernels._timed("p2p_gather")
+    def gather_one(self, t: torch.Tensor, overlap: bool = False):
+        width = int(t.shape[1])
+        st = self._setup(width, t.device)
+        self._store(st, t, 0)
+        return self._pull(st, width, t.device, overlap)

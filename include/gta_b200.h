@@ -101,6 +101,20 @@ int gta_partition(const int64_t* indptr, int64_t num_nodes, int32_t parts, int64
 int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* bounds,
                       int32_t parts, int64_t stride, int32_t chunks, int32_t* out, void* stream);
 
+/* Peer-to-peer exchange without SMs (ipc.cu): each rank publishes a slot buffer through CUDA IPC at
+ * setup and pulls its peers' slots with device-to-device copies on a copy stream (copy engines over
+ * NVLink), so the transfer hides under the aggregation kernel.  gta_ipc_alloc'ed buffers are the only
+ * memory this library owns; free them with gta_ipc_free.  handle64 is a 64-byte cudaIpcMemHandle_t. */
+int gta_ipc_alloc(size_t bytes, void** ptr);
+int gta_ipc_free(void* ptr);
+int gta_ipc_export(void* ptr, uint8_t* handle64);
+int gta_ipc_open(const uint8_t* handle64, void** mapped);
+int gta_ipc_close(void* mapped);
+/* dst[i] <- src[i] (bytes[i]) for i < n, asynchronously on `stream`; pointers may be peer mappings.
+ * h_ arrays live on the host. */
+int gta_copy_many(void* const* h_dst, const void* const* h_src, const int64_t* h_bytes, int32_t n,
+                  void* stream);
+
 /* Degree reorder: perm[new] = old, descending in-degree, stable. */
 size_t gta_reorder_workspace(int64_t num_nodes);
 int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm,

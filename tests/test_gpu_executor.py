@@ -187,3 +187,38 @@ def test_chrome_timeline_export(rt, tmp_path):
     assert [e["pid"] for e in events] == ["MM", "VEC_ALU"]
     assert all(e["ph"] == "X" and e["dur"] > 0 and set(e) == {"name", "cat", "ph", "ts", "dur", "pid", "tid"} for e in events)
     assert events[0]["ts"] == 0 and events[1]["ts"] >= events[0]["dur"] * 0.5
+
+
+def test_host_pipeline_matches_direct_execution(rt):
+    """pipeline.HostPipeline (copy-in / compute / copy-out streams, 2 staging buffers) returns exactly what
+    execute() returns on resident inputs, for every batch of a sequence."""
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import pipeline
+    torch = rt.torch
+    prog = next(p for p in PROGRAMS if p["file"].endswith("GCN-cora-layer1-trans__0_1-2-3.yaml"))
+    op_info = _load(prog["opgraph"])
+    records = _load(prog["file"])
+    g, _, _, dg = _graph(rt, "cora")
+    n, fin = g.num_nodes, 1433
+    node_inputs, weights, edge_inputs = _inputs(op_info, n, g.num_edges)
+    dev = lambda d: {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    w_d, e_d = dev(weights), dev(edge_inputs)
+
+    def run(x_dev):
+        return rt.ex.execute(records, op_info, dg, {0: x_dev}, w_d, e_d, network="GCN", is_reorder=True)[3]
+
+    rng = np.random.default_rng(5)
+    batches = [rng.standard_normal((n, fin), dtype=np.float32) for _ in range(5)]
+    want = [run(rt.k.to_table(torch.from_numpy(b).cuda())).cpu() for b in batches]
+    pipe = pipeline.HostPipeline(run, n, fin, "cuda", depth=2)
+    xs, ys = [], []
+    for b in batches:
+        xp = pipeline.pinned_table(n, fin)
+        xp.copy_(torch.from_numpy(b))
+        xs.append(xp)
+        ys.append(torch.empty((n, 128), dtype=torch.float32).pin_memory())
+    for xp, yp in zip(xs, ys):
+        pipe.submit(xp, yp)
+    ms = pipe.finish()
+    assert ms > 0
+    for got, ref in zip(ys, want):
+        assert torch.equal(got, ref)
