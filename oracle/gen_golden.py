@@ -96,7 +96,7 @@ def main():
     # ---- 1. op graphs (gen_yaml, unmodified) ------------------------------------------
     shapes = {k: synthetic.SHAPES[k] for k in ("cora", "flickr", "reddit")}
     for ds, (n, e, f) in shapes.items():
-        for network in ("GCN", "GAT", "SGC", "GraphSAGE", "GIN"):
+        for network in ("GCN", "GAT", "SGC", "GraphSAGE", "GIN", "DGN", "PNA"):
             for layer in (1, 2, 3):
                 for reorder in (False, True):
                     p = net_path(network, ds, layer, reorder)

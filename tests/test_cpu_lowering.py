@@ -72,3 +72,70 @@ def test_plans_the_reference_cannot_lower_are_rejected():
     del legacy[0]["COMP_TYPE"]
     with pytest.raises(KeyError, match="COMP_TYPE"):
         lowering.lower(legacy, [[0]], [[16, 1]], 2708)
+
+
+# ---- opgraph.py: gen_yaml / modify_yaml mirrors ------------------------------------------------
+import re
+import shutil
+
+from gta_graph_tensor_acclelrator_for_general_gnn_b200 import opgraph, synthetic
+
+_OPGRAPHS = sorted(f for f in os.listdir(os.path.join(GOLDEN, "opgraph")) if "-layer" in f)
+
+
+@pytest.mark.parametrize("name", _OPGRAPHS, ids=[f[:-5] for f in _OPGRAPHS])
+def test_gen_yaml_is_byte_identical_to_the_reference(name, tmp_path):
+    net, ds, layer, mode = re.match(r"(\w+)-(\w+)-layer(\d)-(original|trans)\.yaml", name).groups()
+    n, e, f = synthetic.SHAPES[ds]
+    path = tmp_path / opgraph.network_path(net, ds, int(layer), mode == "trans")
+    opgraph.gen_yaml(str(path), n, e, f, net, int(layer), mode == "trans", repair=True)
+    assert path.read_text() == open(os.path.join(GOLDEN, "opgraph", name)).read()
+
+
+def test_gen_yaml_keeps_the_published_gcn_trans_form_by_default():
+    """Without repair=True the reordered GCN is what the reference writes:
+    consumers shifted by one and a 1-entry feature_number on the 2-input edge op."""
+    raw = opgraph.build(2708, 10556, 1433, "GCN", 1, True)
+    assert [r["OUTPUT"]["output_list"] for r in raw] == [[1], [1], [2], []]
+    assert raw[2]["INPUT"]["feature_number"] == [10556] and raw[2]["INPUT"]["input_g_num"] == 2
+    fixed = opgraph.repair_gcn_trans(opgraph.build(2708, 10556, 1433, "GCN", 1, True))
+    assert fixed == _load("opgraph/GCN-cora-layer1-trans.yaml")
+
+
+def test_gen_yaml_rejects_unknown_network_and_layer():
+    with pytest.raises(opgraph.OpGraphError):
+        opgraph.build(10, 20, 8, "GraphConv", 1, False)
+    with pytest.raises(opgraph.OpGraphError):
+        opgraph.build(10, 20, 8, "GCN", 4, False)
+
+
+@pytest.mark.parametrize("src,dst", [("cora", "reddit"), ("reddit", "cora")])
+def test_modify_yaml_restamps_like_the_reference(src, dst, tmp_path):
+    """The re-stamper overwrites every size field, so re-stamping one golden file (made by the
+    unmodified reference from V2/GAT_Cora.yaml) to the other's shape must reproduce the other."""
+    p = tmp_path / "GAT_Cora.yaml"
+    shutil.copy(os.path.join(GOLDEN, "opgraph", f"GAT-{src}-restamped-h4.yaml"), p)
+    opgraph.modify_yaml(str(p), *synthetic.SHAPES[dst], [])
+    assert p.read_text() == open(os.path.join(GOLDEN, "opgraph", f"GAT-{dst}-restamped-h4.yaml")).read()
+
+
+def test_modify_yaml_rejects_a_short_file(tmp_path):
+    p = tmp_path / "short.yaml"
+    p.write_text(opgraph.dumps(opgraph.build(10, 20, 8, "GCN", 1, False)))
+    with pytest.raises(opgraph.OpGraphError):
+        opgraph.modify_yaml(str(p), 10, 20, 8, [])
+
+
+def test_generate_connections_lists_op_edges(tmp_path):
+    p = tmp_path / "g.yaml"
+    opgraph.gen_yaml(str(p), 10, 20, 8, "GCN", 1, False)
+    assert opgraph.generate_connections(str(p)) == [[0, 1], [1, 2], [2, 3]]
+
+
+def test_generated_graph_lowers_to_the_golden_program():
+    """gen_yaml -> lower, no reference file on the way: still the program the reference emitted."""
+    prog = next(p for p in MANIFEST["programs"] if p["file"].endswith("GCN-flickr-layer1-trans__0_1-2-3.yaml"))
+    n, e, f = synthetic.SHAPES["flickr"]
+    op_info = opgraph.build(n, e, f, "GCN", 1, True, repair=True)
+    blocks = lowering.lower(op_info, prog["op_array"], prog["tile_size_list"], n)
+    assert lowering.dumps(blocks) == open(os.path.join(GOLDEN, prog["file"])).read()
