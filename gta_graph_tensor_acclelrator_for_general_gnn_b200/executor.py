@@ -24,6 +24,8 @@ gather(MUL(scatterC(x), p / scatterR(S)))        gta_aggregate_f32 (W_EDGE_DIV)
 SF(ADD(scatterR(el), scatterC(er))) + its sum    gta_gat_logits_f32
 whole GAT edge phase (ops 3..13 / trans 3..12)   gta_gat_aggregate_f32 (single pass)
 applynode SF after a gather                      epilogue of the aggregate kernel
+MM(scatter(x), W) on edges (PNA ops 3/4)         scatter(gta_gemm_f32(x, W)): N rows instead of E, same bits
+MM(e, W) on any other edge tensor (DGN op 3)     gta_gemm_f32 over the E rows
 anything else                                    gta_edge_* / gta_node_* generic kernels
 =============================================  ==========================================
 
@@ -56,6 +58,9 @@ DEFAULT_SEMANTICS = {
 NETWORK_SEMANTICS = {
     ("GAT", False): {9: "div"},      # alpha = p / S[dst]        inputs [7, 10]
     ("GAT", True): {11: "rdiv"},     # O = O' / S                inputs [9 (S), 10 (O')]
+    # PNA's edge SF closes the message MLP (genGraphOP.py:130,142); unnamed upstream, pinned to ReLU
+    ("PNA", False): {7: "relu"},
+    ("PNA", True): {7: "relu"},
 }
 
 
@@ -76,6 +81,10 @@ def repair_op_graph(op_info, network: str | None, is_reorder: bool):
     if (network == "GAT" and not is_reorder and len(op_info) == 14 and prods[10] == [7]
             and op_info[8]["TYPE"] == "gather" and op_info[10]["TYPE"] == "scatter"):
         prods[10] = [8]
+    for pos, ins in enumerate(prods):
+        if ins == [pos]:
+            # PNA-trans ops 0/1 name themselves as producer (genGraphOP.py:136-137): an external input
+            prods[pos] = []
     return prods
 
 
@@ -99,7 +108,7 @@ class Value:
 
     @property
     def on_edges(self) -> bool:
-        return self.kind in ("edge", "scatter", "edge_expr")
+        return self.kind in ("edge", "scatter", "edge_expr", "edge_mm")
 
 
 class _Run:
@@ -159,6 +168,11 @@ class _Run:
             x = k.to_table(self.force(v.args[0]))
             v.tensor = k.gemm(x, v.weight)
             self.kernel_log.append(("gta_gemm_f32", v.pos))
+        elif v.kind == "edge_mm":
+            self._guard(v.args[0].width, f"the input of edge COMP_MM op {v.pos}")
+            self._guard(v.width, f"edge COMP_MM op {v.pos}")
+            v.tensor = k.gemm(k.to_table(self.force(v.args[0])), v.weight)
+            self.kernel_log.append(("gta_gemm_f32:edges", v.pos))
         elif v.kind == "scatter":
             self._guard(v.width, f"scatter op {v.pos}")
             t, kind = self._operand(v)
@@ -411,11 +425,19 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                 args.append(Value(kind, tensor=t.contiguous() if kind == "edge" else t, width=int(t.shape[1]), pos=pos))
             else:
                 args.append(env[q])
+        on_edges = typ in ("applyedge", "gather")
+
+        def external(what):
+            table, label = (edge_inputs, "edge_inputs") if on_edges else (node_inputs, "node_inputs")
+            if pos not in table:
+                raise ExecutionError(f"op {pos} {what}: pass {label}[{pos}]")
+            t = table[pos]
+            t = t if t.dim() == 2 else t[:, None]
+            return Value("edge" if on_edges else "node", tensor=t.contiguous() if on_edges else t,
+                         width=int(t.shape[1]), pos=pos)
+
         if not prods[pos]:
-            if pos not in node_inputs:
-                raise ExecutionError(f"op {pos} has no producer: pass node_inputs[{pos}]")
-            t = node_inputs[pos]
-            args.append(Value("node", tensor=t, width=int(t.shape[1]), pos=pos))
+            args.append(external("has no producer"))
         if typ == "scatter":
             if order_ not in ("R", "C"):
                 raise IsaError(f"op {pos}: ORDER {order_!r}")
@@ -427,18 +449,27 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
             return Value("gather", args=(args[0],), width=args[0].width, pos=pos,
                          extra={"consumers": consumers[pos]})
         if comp == "MM":
-            if typ == "applyedge":
-                raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute",
-                                           f"op {pos}: COMP_MM on edges (DGN/PNA) is not built yet")
             if pos not in weights:
                 raise ExecutionError(f"op {pos} is COMP_MM: pass weights[{pos}]")
             w = weights[pos]
             if int(w.shape[0]) != args[0].width:
                 raise ExecutionError(f"op {pos}: weight is {tuple(w.shape)} but the input is {args[0].width} wide")
+            if typ == "applyedge":
+                a = args[0]
+                if a.kind == "scatter" and not a.forced:
+                    # row k of scatter(x).W is the row x[src k].W of x.W: transform the N node rows once
+                    # and keep the scatter virtual (what the reference's PNA-trans graph does by hand)
+                    inner = Value("mm", args=(a.args[0],), weight=w, width=int(w.shape[1]), pos=pos)
+                    return Value("scatter", args=(inner,), side=a.side, width=inner.width, pos=pos)
+                return Value("edge_mm", args=(a,), weight=w, width=int(w.shape[1]), pos=pos)
             return Value("mm", args=(args[0],), weight=w, width=int(w.shape[1]), pos=pos)
         kind = sem.get(pos, DEFAULT_SEMANTICS.get((typ, comp)))
         if kind is None:
             raise IsaError(f"op {pos}: no semantics for {typ} COMP_{comp}")
+        if kind in ("add", "mul", "div", "rdiv") and len(args) == 1:
+            # one declared input on a binary op (DGN/PNA op 9, the degree scaler, genGraphOP.py:120,132):
+            # the second operand is the external tensor supplied under the op's own position
+            args.append(external(f"is COMP_{comp} with one graph input; its second operand is external"))
         if kind in ("add", "mul", "div", "rdiv") and len(args) != 2:
             raise IsaError(f"op {pos}: COMP_{comp} needs two inputs, has {len(args)}")
         width = max(a.width for a in args)

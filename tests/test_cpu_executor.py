@@ -1,0 +1,149 @@
+"""execute()'s HOST logic on CPU: every golden ISA program is run through the real executor with
+the kernel wrappers replaced by the torch-CPU test double (tests/host_kernels.py) and compared with
+the op-by-op oracle.  What this checks is the executor itself -- dataflow from the YAML, block order,
+the pattern matching onto fused kernels, dead stores, refusals; the CUDA kernels are checked on the
+GPU (test_gpu_executor.py runs the same programs there)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import host_kernels
+import test_gpu_executor as shared
+from oracle import gta_oracle as O
+from gta_graph_tensor_acclelrator_for_general_gnn_b200 import _cabi, executor, graph, isa, lowering, opgraph, synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(GOLDEN, "manifest.json")) as _f:
+    PROGRAMS = json.load(_f)["programs"]
+N, E = 700, 9000
+
+
+def _load(rel):
+    with open(os.path.join(GOLDEN, rel)) as f:
+        return yaml.safe_load(f)
+
+
+@pytest.fixture()
+def host(monkeypatch):
+    """executor wired to the test double; work lists are a kernel-side structure, so none is built"""
+    monkeypatch.setattr(executor, "kernels", host_kernels)
+    monkeypatch.setattr(graph.DeviceGraph, "schedule", lambda self, *a, **k: None)
+    g = synthetic.powerlaw_graph(N, E, seed=11, i0=20.0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, N)
+    dg = graph.DeviceGraph(N, g.num_edges, torch.from_numpy(indptr), torch.from_numpy(indices.astype(np.int32)),
+                           num_sources=N)
+    return g, indptr, indices, dg
+
+
+def _t(d):
+    up = lambda v: [torch.from_numpy(a) for a in v] if isinstance(v, list) else torch.from_numpy(v)
+    return {k: up(v) for k, v in d.items()}
+
+
+def _run(host, op_info, records, network, reorder, fuse=True, **kw):
+    g, indptr, indices, dg = host
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
+    sem = O.NETWORK_SEMANTICS.get((network, reorder), {})
+    ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, semantics=sem, stabilize=True)
+    out, log = executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network=network,
+                                is_reorder=reorder, fuse_across_blocks=fuse, check_shapes=False, return_log=True, **kw)
+    return out, ref, [k for k, _ in log]
+
+
+@pytest.mark.parametrize("prog", PROGRAMS, ids=[p["file"].split("/")[-1][:-5] for p in PROGRAMS])
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "stores-honoured"])
+def test_golden_program_dataflow(host, prog, fuse):
+    op_info = _load(prog["opgraph"])
+    out, ref, names = _run(host, op_info, _load(prog["file"]), prog["network"], prog["reorder"], fuse)
+    finals = [p for p in range(len(op_info)) if not op_info[p]["OUTPUT"]["output_list"]]
+    assert sorted(out) == finals
+    for p in finals:
+        y64 = ref[p]
+        np.testing.assert_allclose(out[p].numpy(), y64, rtol=1e-4, atol=2e-5 * np.abs(y64).max(), err_msg=str(names))
+    if prog["network"] == "GAT" and fuse:
+        f_out, heads = op_info[0]["OUTPUT"]["size_per_feature"] // 4, op_info[1]["OUTPUT"]["size_per_feature"] // 4
+        if (f_out // heads) % 4 == 0:
+            assert "gta_gat_aggregate_f32" in names and not any(k.startswith("gta_edge_") for k in names), names
+        else:
+            assert "gta_gat_logits_f32" in names, names
+    if prog["network"] in ("GCN", "SGC", "GraphSAGE", "GIN"):
+        assert any(k.startswith("gta_aggregate_f32") for k in names), names
+        if fuse:
+            assert not any(k.startswith("gta_edge_") for k in names), names
+
+
+def test_generate_lower_execute_without_any_reference_file(host):
+    """opgraph.build -> lowering.lower -> execute: the whole host chain of this package."""
+    n_ref = synthetic.SHAPES["cora"][0]
+    for network, reorder, plan, tiles in (("GCN", True, [[0], [1, 2, 3]], [[512, 1], [512, 1]]),
+                                          ("GraphSAGE", False, [[0, 1, 2, 3], [4, 5, 6]], [[64, 1], [64, 1]])):
+        op_info = opgraph.build(*synthetic.SHAPES["cora"], network, 2, reorder, repair=True)
+        records = lowering.lower(op_info, plan, tiles, n_ref)
+        out, ref, names = _run(host, op_info, records, network, reorder)
+        (p, y), = out.items()
+        np.testing.assert_allclose(y.numpy(), ref[p], rtol=1e-4, atol=2e-5 * np.abs(ref[p]).max())
+
+
+def test_refusals_need_no_gpu(host):
+    g, indptr, indices, dg = host
+    prog = next(p for p in PROGRAMS if p["file"].endswith("GCN-cora-layer1-original__0_1-2-3.yaml"))
+    op_info, records = _load(prog["opgraph"]), _load(prog["file"])
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
+    with pytest.raises(executor.ExecutionError, match="max_edge_bytes"):
+        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="GCN",
+                         fuse_across_blocks=False, max_edge_bytes=1 << 20, check_shapes=False)
+    with pytest.raises(executor.ExecutionError, match="generated for"):
+        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="GCN")
+    with pytest.raises(executor.ExecutionError, match="weights"):
+        executor.execute(records, op_info, dg, _t(node_inputs), {}, _t(edge_inputs), network="GCN", check_shapes=False)
+    with pytest.raises(executor.ExecutionError, match="edge_inputs"):
+        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), {}, network="GCN", check_shapes=False)
+    col = [dict(op) for op in op_info]
+    col[2] = dict(col[2], ORDER="C")
+    with pytest.raises(_cabi.GtaUnsupported, match="ORDER C"):
+        executor.execute(records, col, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="GCN", check_shapes=False)
+    with pytest.raises(isa.IsaError):
+        executor.execute([[dict(records[0][0], TYPE="COMP_FOO")]], op_info, dg, {}, {})
+
+
+# ---- DGN / PNA: COMP_MM on edges, one-input binaries, PNA-trans' self references ---------------
+WIDE = [("DGN", False, "per-op"), ("DGN", False, "one-block"), ("PNA", False, "per-op"), ("PNA", False, "one-block"),
+        ("PNA", True, "per-op")]
+
+
+def wide_program(network, reorder, plan_kind, layer=2):
+    """(op graph, ISA records) built by this package's own generator + lowering (Cora shape)."""
+    shape = synthetic.SHAPES["cora"]
+    op_info = opgraph.build(*shape, network, layer, reorder)
+    n_ops = len(op_info)
+    plan = [[i] for i in range(n_ops)] if plan_kind == "per-op" else [list(range(n_ops))]
+    return op_info, lowering.lower(op_info, plan, [[64, 1]] * len(plan), shape[0])
+
+
+@pytest.mark.parametrize("network,reorder,plan_kind", WIDE, ids=[f"{n}-{'trans' if r else 'original'}-{k}" for n, r, k in WIDE])
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "stores-honoured"])
+def test_dgn_pna_dataflow(host, network, reorder, plan_kind, fuse):
+    op_info, records = wide_program(network, reorder, plan_kind)
+    out, ref, names = _run(host, op_info, records, network, reorder, fuse)
+    (p, y), = out.items()
+    np.testing.assert_allclose(y.numpy(), ref[p], rtol=1e-4, atol=2e-5 * np.abs(ref[p]).max(), err_msg=str(names))
+    assert "gta_gemm_f32:edges" in names              # DGN op 3 / PNA op 2: a real E-row GEMM
+    if network == "PNA" and not reorder and fuse:
+        # ops 3/4 = MM(scatter(x)): commuted to scatter(MM(x)) -> two N-row GEMMs, one E-row GEMM (op 2)
+        assert names.count("gta_gemm_f32:edges") == 1 and names.count("gta_gemm_f32") == 3, names
+
+
+def test_edge_mm_respects_the_edge_budget(host):
+    g, indptr, indices, dg = host
+    op_info, records = wide_program("DGN", False, "one-block")
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
+    with pytest.raises(executor.ExecutionError, match="max_edge_bytes"):
+        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="DGN",
+                         max_edge_bytes=1 << 16, check_shapes=False)
+    node_inputs.pop(9)
+    with pytest.raises(executor.ExecutionError, match=r"node_inputs\[9\]"):
+        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="DGN", check_shapes=False)

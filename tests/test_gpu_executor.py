@@ -43,8 +43,15 @@ def _inputs(op_info, n, e, seed=0):
             fout = op["OUTPUT"]["size_per_feature"] // 4
             weights[pos] = synthetic.glorot(rng, widths[0], fout) if fout > 16 else \
                 rng.uniform(-0.1, 0.1, size=(widths[0], fout)).astype(np.float32)
-        if not ins:
-            node_inputs[pos] = rng.standard_normal((n, widths[0]), dtype=np.float32)
+        on_edges = op["TYPE"] in ("applyedge", "gather")
+        if not ins or ins == [pos]:       # no producer (or PNA-trans' self reference): external tensor
+            if on_edges:
+                edge_inputs[pos] = rng.standard_normal((e, widths[0]), dtype=np.float32)
+            else:
+                node_inputs[pos] = rng.standard_normal((n, widths[0]), dtype=np.float32)
+        elif op["COMP_TYPE"] in ("MUL", "ADD") and len(ins) == 1:     # DGN/PNA op 9: external degree scaler
+            (edge_inputs if on_edges else node_inputs)[pos] = \
+                rng.uniform(0.5, 1.5, size=(e if on_edges else n, 1)).astype(np.float32)
         ext = []
         for slot, q in enumerate(ins):
             if q == -1:
