@@ -27,6 +27,8 @@ applynode SF after a gather                      epilogue of the aggregate kerne
 MM(scatter(x), W) on edges (PNA ops 3/4)         scatter(gta_gemm_f32(x, W)): N rows instead of E, same bits
 MM(e, W) on any other edge tensor (DGN op 3)     gta_gemm_f32 over the E rows
 anything else                                    gta_edge_* / gta_node_* generic kernels
+gather with ORDER C (sum per SOURCE)             gta_csr_build over (source, edge id) once, then
+                                                 gta_aggregate_f32 gathering rows of the edge tensor
 =============================================  ==========================================
 
 ``fuse_across_blocks=True`` (default) treats a ``STORE_E``/``LOAD_E`` pair whose tensor has
@@ -44,7 +46,7 @@ import torch
 import yaml
 
 from . import _cabi, kernels
-from .graph import DeviceGraph
+from .graph import DeviceGraph, csr_from_coo
 from .isa import IsaError, Program
 
 #: COMP_TYPE -> arithmetic where the YAML alone is ambiguous (the reference only names ops)
@@ -239,9 +241,24 @@ class _Run:
             return table, sched, events
         return ex(x), None, None
 
+    def _by_source(self) -> DeviceGraph:
+        """The CSC walk as a graph over EDGE ids: row j lists the CSR positions of the edges whose
+        source is j, ascending (= ascending destination), so an ORDER C gather is the same
+        deterministic segment sum, gathering rows of the edge tensor instead of rows of a node table."""
+        if "by_source" not in self.g.schedules:
+            e = self.g.num_edges
+            ids = torch.arange(max(e, 1), dtype=torch.int32, device=self.g.indices.device)[:e]
+            t = csr_from_coo(self.g.indices, ids, self.g.num_sources or self.g.num_nodes)
+            self.g.schedules["by_source"] = DeviceGraph(t.num_nodes, e, t.indptr, t.indices, num_sources=max(e, 1))
+        return self.g.schedules["by_source"]
+
     def _force_gather(self, v: Value, epilogue: int) -> torch.Tensor:
         k = kernels
         src = v.args[0]
+        if v.side == "C":
+            et = k.to_table(self.force(src))
+            self.kernel_log.append(("gta_aggregate_f32:by_source", v.pos))
+            return k.aggregate(self._by_source(), et, None, None, epilogue)
         # S = gather(p) where p came out of the logits kernel: the row sums are already there
         if src.forced and "rowsum" in src.extra and epilogue == _cabi.EPI_NONE:
             return src.extra["rowsum"]
@@ -256,7 +273,7 @@ class _Run:
             if (wv.kind == "edge_expr" and wv.op == "div" and not wv.forced):
                 p, den = wv.args
                 if (den.kind == "scatter" and den.side == "R" and den.args[0].kind == "gather"
-                        and den.args[0].args[0] is p and not p.forced and not den.args[0].forced
+                        and den.args[0].side == "R" and den.args[0].args[0] is p and not p.forced and not den.args[0].forced
                         and self._is_softmax_numerator(p) is not None and xv.width % p.width == 0
                         and (xv.width // p.width) % 4 == 0):
                     return self._gat_single_pass(p, xv, epilogue, v.pos)
@@ -314,7 +331,7 @@ class _Run:
         if v.kind != "node_expr" or v.op not in ("div", "rdiv") or v.forced:
             return None
         num, den = v.args if v.op == "div" else (v.args[1], v.args[0])
-        if num.kind != "gather" or den.kind != "gather" or num.forced or den.forced:
+        if num.kind != "gather" or den.kind != "gather" or num.forced or den.forced or "C" in (num.side, den.side):
             return None
         sp = self._split_mul(num.args[0])
         if sp is None:
@@ -443,10 +460,13 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                 raise IsaError(f"op {pos}: ORDER {order_!r}")
             return Value("scatter", args=(args[0],), side=order_, width=args[0].width, pos=pos)
         if typ == "gather":
-            if order_ != "R":
+            if order_ not in ("R", "C"):
+                raise IsaError(f"op {pos}: ORDER {order_!r}")
+            if order_ == "C" and hasattr(opts["source_table"], "part"):
                 raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute",
-                                           f"op {pos}: ORDER C gather needs a CSC walk (not built yet)")
-            return Value("gather", args=(args[0],), width=args[0].width, pos=pos,
+                                           f"op {pos}: an ORDER C gather reduces over destinations, which a "
+                                           f"destination-partitioned run does not own")
+            return Value("gather", args=(args[0],), side=order_, width=args[0].width, pos=pos,
                          extra={"consumers": consumers[pos]})
         if comp == "MM":
             if pos not in weights:

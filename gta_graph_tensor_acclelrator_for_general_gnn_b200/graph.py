@@ -125,6 +125,44 @@ def csr_from_coo(dst, src, num_nodes: int, want_perm: bool = False) -> DeviceGra
     return DeviceGraph(num_nodes, e, indptr, indices, perm, num_sources=num_nodes)
 
 
+def read_csr_npz(file_path: str):
+    """Host half of the ``.npz`` ingest: the SciPy-CSR archive the reference simulator reads
+    (``read_csr_npz``, vTCAD/code/simulator.py:74-84: arrays ``data``, ``indices``, ``indptr``,
+    ``shape``; ``KeyError`` when one is missing) expanded to COO.  Row = destination, column = source
+    (SURVEY.md Appendix A).  Returns ``(dst int32 [E], src int32 [E], data [E], N)`` in file order."""
+    with np.load(file_path) as z:
+        missing = [k for k in ("data", "indices", "indptr", "shape") if k not in z.files]
+        if missing:
+            raise KeyError(f"The required keys are not found in the .npz file: {missing}")
+        data, indices, indptr, shape = z["data"], z["indices"], z["indptr"], tuple(int(v) for v in z["shape"])
+    if len(shape) != 2 or shape[0] != shape[1]:
+        raise ValueError(f"{file_path}: adjacency must be square, shape is {shape}")
+    n = shape[0]
+    if indptr.shape[0] != n + 1 or int(indptr[0]) != 0 or int(indptr[-1]) != indices.shape[0] \
+            or data.shape[0] != indices.shape[0] or np.any(np.diff(indptr) < 0):
+        raise ValueError(f"{file_path}: inconsistent CSR arrays")
+    if indices.size and (int(indices.min()) < 0 or int(indices.max()) >= n):
+        raise ValueError(f"{file_path}: column index outside [0, {n})")
+    if n >= 2**31 or indices.shape[0] >= 2**31:
+        raise ValueError(f"{file_path}: int32 ids cannot hold this graph")
+    dst = np.repeat(np.arange(n, dtype=np.int32), np.diff(indptr).astype(np.int64))
+    return dst, indices.astype(np.int32), data, n
+
+
+def csr_from_npz(file_path: str, drop_diagonal: bool = False):
+    """SciPy-CSR ``.npz`` -> ``(DeviceGraph, edge values)``: the COO expansion is re-sorted on device by
+    ``gta_csr_build`` (the file's rows need not have ascending columns), and the stored values come back
+    as an fp32 ``[E]`` device tensor in CSR edge order (GCN's edge weight input).  ``drop_diagonal``
+    removes self loops first, which is what the tile tables count (``A - diag``, preprocessing.py:20)."""
+    dst, src, data, n = read_csr_npz(file_path)
+    if drop_diagonal:
+        keep = dst != src
+        dst, src, data = dst[keep], src[keep], data[keep]
+    g = csr_from_coo(dst, src, n, want_perm=True)
+    values = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(g.indptr.device)
+    return g, (values[g.perm] if g.num_edges else values)
+
+
 def build_schedule(indptr: torch.Tensor, indices: torch.Tensor, row_begin: int, row_end: int, num_edges: int,
                    num_sources: int, chunk: int = DEFAULT_CHUNK, col_block: int = 0) -> Schedule:
     lib = _cabi.load()

@@ -103,8 +103,8 @@ def test_refusals_need_no_gpu(host):
     with pytest.raises(executor.ExecutionError, match="edge_inputs"):
         executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), {}, network="GCN", check_shapes=False)
     col = [dict(op) for op in op_info]
-    col[2] = dict(col[2], ORDER="C")
-    with pytest.raises(_cabi.GtaUnsupported, match="ORDER C"):
+    col[2] = dict(col[2], ORDER="X")
+    with pytest.raises(isa.IsaError, match="ORDER"):
         executor.execute(records, col, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="GCN", check_shapes=False)
     with pytest.raises(isa.IsaError):
         executor.execute([[dict(records[0][0], TYPE="COMP_FOO")]], op_info, dg, {}, {})
@@ -147,3 +147,43 @@ def test_edge_mm_respects_the_edge_budget(host):
     node_inputs.pop(9)
     with pytest.raises(executor.ExecutionError, match=r"node_inputs\[9\]"):
         executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="DGN", check_shapes=False)
+
+
+# ---- ORDER C gathers (sum per source) -----------------------------------------------------------
+def _host_csr_from_coo(dst, src, num_nodes, want_perm=False):
+    """torch-CPU stand-in for graph.csr_from_coo (sort by (dst, src)), test double like host_kernels"""
+    key = dst.long() * (int(src.max()) + 1 if src.numel() else 1) + src.long()
+    order = torch.argsort(key, stable=True)
+    counts = torch.bincount(dst.long(), minlength=num_nodes)
+    indptr = torch.zeros(num_nodes + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return graph.DeviceGraph(num_nodes, int(dst.numel()), indptr, src[order].contiguous(), order if want_perm else None,
+                             num_sources=num_nodes)
+
+
+def column_gather_case():
+    """A small program whose reduction is column-wise: x -> scatter R -> x edge weight -> gather C -> MM,
+    i.e. Y = (A^T diag-weighted X) W: every node sums what it SENT.  The reference has the lowering rules
+    for ORDER C gathers (interpreter.py:55-129) but no shipped network uses one."""
+    op_info = opgraph.build(N, E, 32, "GCN", 2, False)
+    op_info[0]["ORDER"] = "R"
+    op_info[2]["ORDER"] = "C"
+    return op_info
+
+
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "stores-honoured"])
+def test_order_c_gather_sums_per_source(host, monkeypatch, fuse):
+    monkeypatch.setattr(executor, "csr_from_coo", _host_csr_from_coo)
+    op_info = column_gather_case()
+    records = lowering.lower(op_info, [[0], [1, 2, 3]], [[64, 1], [64, 1]], N)
+    out, ref, names = _run(host, op_info, records, None, False, fuse)
+    np.testing.assert_allclose(out[3].numpy(), ref[3], rtol=1e-4, atol=2e-5 * np.abs(ref[3]).max())
+    assert "gta_aggregate_f32:by_source" in names
+    # and the oracle's column-wise sum is what it says: every node sums what it sent
+    g, indptr, indices, dg = host
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
+    x = node_inputs[0].astype(np.float64)
+    rows = np.repeat(np.arange(N), np.diff(indptr))
+    direct = np.zeros((N, x.shape[1]))
+    np.add.at(direct, indices, edge_inputs[1].astype(np.float64) * x[rows])
+    np.testing.assert_allclose(ref[2], direct, rtol=1e-12)

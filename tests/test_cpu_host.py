@@ -94,3 +94,36 @@ def test_cpu_tensors_are_refused():
         graph.csr_from_coo(torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int32), 4)
     with pytest.raises((RuntimeError, AssertionError)):
         graph.csr_from_coo(np.zeros(4, np.int32), np.zeros(4, np.int32), 4)   # upload needs a GPU
+
+
+def test_read_csr_npz_expands_to_coo_and_rejects_bad_archives(tmp_path):
+    """Host half of the SciPy-CSR .npz ingest (the format simulator.py:74-84 reads)."""
+    import numpy as np
+    import scipy.sparse as sp
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import graph
+    rng = np.random.default_rng(3)
+    a = sp.random(40, 40, density=0.1, random_state=7, format="csr", dtype=np.float32)
+    p = tmp_path / "adj.npz"
+    sp.save_npz(p, a)
+    dst, src, data, n = graph.read_csr_npz(str(p))
+    coo = a.tocoo()
+    assert n == 40 and dst.dtype == np.int32 and src.dtype == np.int32
+    assert np.array_equal(dst, coo.row) and np.array_equal(src, coo.col) and np.array_equal(data, coo.data)
+    np.savez(tmp_path / "nokeys.npz", indices=a.indices, indptr=a.indptr)
+    with pytest.raises(KeyError, match="required keys"):
+        graph.read_csr_npz(str(tmp_path / "nokeys.npz"))
+    np.savez(tmp_path / "rect.npz", data=a.data, indices=a.indices, indptr=a.indptr, shape=np.array([40, 41]))
+    with pytest.raises(ValueError, match="square"):
+        graph.read_csr_npz(str(tmp_path / "rect.npz"))
+    np.savez(tmp_path / "short.npz", data=a.data, indices=a.indices, indptr=a.indptr[:-1], shape=np.array([40, 40]))
+    with pytest.raises(ValueError, match="inconsistent"):
+        graph.read_csr_npz(str(tmp_path / "short.npz"))
+    bad = a.indices.copy()
+    bad[0] = 40
+    np.savez(tmp_path / "oob.npz", data=a.data, indices=bad, indptr=a.indptr, shape=np.array([40, 40]))
+    with pytest.raises(ValueError, match="outside"):
+        graph.read_csr_npz(str(tmp_path / "oob.npz"))
+    empty = sp.csr_matrix((5, 5), dtype=np.float32)
+    sp.save_npz(tmp_path / "empty.npz", empty)
+    dst, src, data, n = graph.read_csr_npz(str(tmp_path / "empty.npz"))
+    assert n == 5 and dst.size == src.size == data.size == 0
