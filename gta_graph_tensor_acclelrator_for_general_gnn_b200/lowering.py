@@ -393,6 +393,8 @@ def interpret(data_set, network, isReorder, layer, op_array, tile_size_list):
     op_map = "trans" if isReorder else "original"
     with open(f"Network/{network}/{network}-{data_set}/{network}-{op_map}/{network}-{layer}-{op_map}.yaml") as f:
         op_info = yaml.load(f, Loader=yaml.FullLoader)
-    fusable = load_fusable("code/hardware_info.yaml")
+    # the reference requires its fusion table next to the code; without it the shipped table's five
+    # fusable patterns (hardware_info.yaml:11-68) apply
+    fusable = load_fusable("code/hardware_info.yaml") if os.path.exists("code/hardware_info.yaml") else DEFAULT_FUSABLE
     blocks = lower(op_info, op_array, tile_size_list, node_num, fusable)
     dump(blocks, os.path.join("Results/Insts", f"{network}-{data_set}-{layer}-{op_map}.yaml"))
