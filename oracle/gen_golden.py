@@ -152,6 +152,17 @@ def main():
             programs.append((network, "cora", layer, reorder, [list(b) for b in cand[0]], [list(t) for t in cand[1]]))
             print("%s cora layer%d reorder=%s: compile() plan rank %d lowers: %s" % (network, layer, reorder, rank, cand[0]))
             break
+    # DGN / PNA (COMP_MM on edges): hand-written plans, kept only where the reference's interpret() lowers them
+    for network, reorder, n_ops in (("DGN", False, 11), ("PNA", False, 11), ("PNA", True, 11)):
+        for plan in ([list(range(n_ops))], [[i] for i in range(n_ops)],
+                     [list(range(n_ops // 2)), list(range(n_ops // 2, n_ops))]):
+            tiles = [[64, 1]] * len(plan)
+            try:
+                interp.interpret("cora", network, reorder, "layer2", plan, tiles)
+            except Exception as ex:
+                print("%s reorder=%s plan of %d blocks: the reference does not lower it (%s)" % (network, reorder, len(plan), type(ex).__name__))
+                continue
+            programs.append((network, "cora", 2, reorder, plan, tiles))
     for network, ds, layer, reorder, op_array, tiles in programs:
         interp.interpret(ds, network, reorder, f"layer{layer}", op_array, tiles)
         m = "trans" if reorder else "original"
