@@ -127,3 +127,40 @@ def test_read_csr_npz_expands_to_coo_and_rejects_bad_archives(tmp_path):
     sp.save_npz(tmp_path / "empty.npz", empty)
     dst, src, data, n = graph.read_csr_npz(str(tmp_path / "empty.npz"))
     assert n == 5 and dst.size == src.size == data.size == 0
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every parameter of every prototype in include/gta_b200.h has the width/kind its ctypes binding
+    declares (an int32/int64 or pointer/scalar mismatch would corrupt arguments silently)."""
+    import ctypes as C
+    header = open(os.path.join(REPO, "include", "gta_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(gta_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", header)
+    assert {name for _, name, _ in protos} == set(_cabi.SIGNATURES)
+
+    def kind(ctype):
+        if ctype is None:
+            return "void"
+        if ctype in (C.c_void_p, C.c_char_p) or isinstance(ctype, type) and issubclass(ctype, C._Pointer):
+            return "ptr"
+        if ctype is C.c_float:
+            return "f32"
+        return {4: "i32", 8: "i64"}[C.sizeof(ctype)] if ctype is not C.c_size_t else "size"
+
+    def ckind(text):
+        text = re.sub(r"\bconst\b", "", text).strip()
+        if "*" in text:
+            return "ptr"
+        base = text.split()[0] if len(text.split()) > 1 or text in ("void", "int") else text
+        return {"void": "void", "int": "i32", "int32_t": "i32", "int64_t": "i64", "size_t": "size", "float": "f32",
+                "uint32_t": "i32", "uint64_t": "i64"}[base]
+
+    for ret, name, params in protos:
+        res, args = _cabi.SIGNATURES[name]
+        ret = re.sub(r"\b(extern|GTA_API)\b", "", ret).strip()
+        assert ckind(ret + " r") == kind(res), (name, "return", ret)
+        plist = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for i, (ptext, ctype) in enumerate(zip(plist, args)):
+            assert ckind(ptext) == kind(ctype), (name, i, ptext, ctype)
