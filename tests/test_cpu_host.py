@@ -164,3 +164,21 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert len(plist) == len(args), (name, len(plist), len(args))
         for i, (ptext, ctype) in enumerate(zip(plist, args)):
             assert ckind(ptext) == kind(ctype), (name, i, ptext, ctype)
+
+
+def test_model_times_fixture_refers_to_golden_programs():
+    """tests/golden/model_times.json (the reference simulator's modelled latency, oracle/gen_model_times.py)
+    names only programs of the manifest, and every entry is either a result or a recorded failure."""
+    import json
+    with open(os.path.join(GOLDEN, "model_times.json")) as f:
+        model = json.load(f)
+    files = {p["file"] for p in MANIFEST["programs"] if p["dataset"] == "cora"}
+    assert {m["file"] for m in model["programs"]} == files
+    done = [m for m in model["programs"] if "cycles" in m]
+    assert len(done) >= 10 and all(m["cycles"] > 0 and m["rw_bytes"] > 0 for m in done)
+    assert all("error" in m for m in model["programs"] if "cycles" not in m)
+    # known-answer anchor from the reference's own record of this plan family: the fused 3-block GAT plan is
+    # modelled faster than the unfused one
+    by = {m["file"].split("/")[-1]: m for m in done}
+    assert by["GAT-cora-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml"]["cycles"] < \
+        by["GAT-cora-layer1-original__0_1_2_3_4_5_6_7_8_9_10_11_12_13.yaml"]["cycles"]
