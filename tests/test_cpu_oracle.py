@@ -145,3 +145,47 @@ def test_synthetic_graphs_are_deterministic_simple_and_symmetric():
     r = synthetic.rmat_graph(10, seed=1)
     assert r.num_edges == 16 * 1024 and np.all(r.dst != r.src)
     assert np.unique(r.dst.astype(np.int64) * 1024 + r.src).shape[0] == r.num_edges
+
+
+@pytest.mark.parametrize("heads", [1, 4, 8])
+def test_oracle_gat_equals_dense_textbook_attention(heads):
+    """Independent restatement with library ops only: dense masked softmax attention (the form GAT is
+    published in), torch fp64 -- no segment arithmetic, no CSR.  Floats are unpinned by the reference, so
+    this is the cross-check that the oracle computes GAT and not a private variant of it."""
+    import torch
+    n, e, fin, f = 150, 1200, 40, 32
+    g = synthetic.powerlaw_graph(n, e, seed=4, i0=8.0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    x, w, al, ar = synthetic.gat_tensors(n, fin, f, heads, seed=2)
+    got = O.gat_layer(indptr, indices, x, w, al, ar)
+    X, W, AL, AR = (torch.from_numpy(a).double() for a in (x, w, al, ar))
+    Z = X @ W
+    el, er = Z @ AL, Z @ AR                                       # [N, H]
+    mask = torch.zeros(n, n, dtype=torch.bool)
+    mask[torch.from_numpy(g.dst).long(), torch.from_numpy(g.src).long()] = True
+    logits = torch.nn.functional.leaky_relu(el[:, None, :] + er[None, :, :], 0.2)     # [dst, src, H]
+    logits = logits.masked_fill(~mask[:, :, None], float("-inf"))
+    attn = torch.softmax(logits, dim=1)
+    attn = torch.where(mask[:, :, None], attn, torch.zeros_like(attn))               # rows without edges -> 0
+    d = f // heads
+    out = torch.einsum("ijh,jhd->ihd", attn, Z.view(n, heads, d)).reshape(n, f)
+    want = torch.nn.functional.elu(out).numpy()
+    np.testing.assert_allclose(got["Y"], want, rtol=1e-10, atol=1e-12)
+    assert np.array_equal(got["S"][:, 0] > 0, np.diff(indptr) > 0)
+
+
+def test_oracle_gcn_equals_scipy_sparse_product():
+    import scipy.sparse as sp
+    n, e, fin, f = 200, 1500, 30, 16
+    g = synthetic.powerlaw_graph(n, e, seed=6, i0=8.0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, fin))
+    w = rng.standard_normal((fin, f))
+    deg = np.maximum(np.diff(indptr), 1)
+    ew = synthetic.gcn_edge_norm(indptr, indices).astype(np.float64)
+    a = sp.csr_matrix((ew.ravel(), indices, indptr), shape=(n, n))
+    np.testing.assert_allclose(O.gcn_layer(indptr, indices, ew, x, w, variant="trans")["Y"], a @ (x @ w), rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(O.gcn_layer(indptr, indices, ew, x, w, variant="original")["Y"], (a @ x) @ w, rtol=1e-11, atol=1e-12)
+    rows = np.repeat(np.arange(n), np.diff(indptr))
+    np.testing.assert_allclose(ew.ravel(), 1 / np.sqrt(deg[rows] * deg[indices]), rtol=1e-6)
