@@ -290,6 +290,19 @@ class _Run:
                 x, sched, events = self._gather_sources(xl)
                 self.kernel_log.append(("gta_aggregate_f32:w", v.pos))
                 return k.aggregate(self.g, x, wt, None, epilogue, sched=sched, block_events=events)
+        if (src.kind == "edge_mm" and not src.forced and src.extra.get("consumers", 1) == 1
+                and src.pos not in self.o["wanted"]):
+            # COMP_MM_COMP_ADD (hardware_info.yaml:27-30): sum_k (e_k W) = (sum_k e_k) W -- reduce first, then the
+            # GEMM runs over N rows instead of E and the E x Fout tensor never exists
+            inner = Value("gather", args=(src.args[0],), side="R", width=src.args[0].width, pos=v.pos,
+                          extra={"consumers": 1})
+            reduced = k.to_table(self._force_gather(inner, _cabi.EPI_NONE))
+            self.kernel_log.append(("gta_gemm_f32:after_gather", src.pos))
+            out = k.gemm(reduced, src.weight)
+            if epilogue != _cabi.EPI_NONE:
+                self.kernel_log.append(("gta_node_unary_f32", v.pos))
+                out = k.node_unary(_cabi.UN_ELU if epilogue == _cabi.EPI_ELU else _cabi.UN_RELU, out, self.o["slope"])
+            return out
         # generic: materialise the edge tensor and segment-sum it (identity gather)
         et = k.to_table(self.force(src))
         if "arange" not in self.g.schedules:
@@ -481,7 +494,8 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                     # and keep the scatter virtual (what the reference's PNA-trans graph does by hand)
                     inner = Value("mm", args=(a.args[0],), weight=w, width=int(w.shape[1]), pos=pos)
                     return Value("scatter", args=(inner,), side=a.side, width=inner.width, pos=pos)
-                return Value("edge_mm", args=(a,), weight=w, width=int(w.shape[1]), pos=pos)
+                return Value("edge_mm", args=(a,), weight=w, width=int(w.shape[1]), pos=pos,
+                             extra={"consumers": consumers[pos]})
             return Value("mm", args=(args[0],), weight=w, width=int(w.shape[1]), pos=pos)
         kind = sem.get(pos, DEFAULT_SEMANTICS.get((typ, comp)))
         if kind is None:

@@ -187,3 +187,32 @@ def test_order_c_gather_sums_per_source(host, monkeypatch, fuse):
     direct = np.zeros((N, x.shape[1]))
     np.add.at(direct, indices, edge_inputs[1].astype(np.float64) * x[rows])
     np.testing.assert_allclose(ref[2], direct, rtol=1e-12)
+
+
+# ---- COMP_MM_COMP_ADD: an edge GEMM feeding a gather ----------------------------------------------
+def mm_then_gather_case(n, e, fin=32, fout=16):
+    """scatter C + scatter R -> ADD -> MM (edges) -> gather -> SF: the (applyedge, gather) / (MM, ADD) pattern of the
+    reference's fusion table (hardware_info.yaml:27-30), which no shipped network exercises."""
+    op = opgraph.gen_one_op
+    return [op(0, "NONE", "scatter", "C", [n], [], 1, 0, [], [], [fin * 4], [2], e, fin * 4),
+            op(1, "NONE", "scatter", "R", [n], [], 1, 0, [], [], [fin * 4], [2], e, fin * 4),
+            op(2, "ADD", "applyedge", "R", [e, e], [0, 1], 2, 0, [], [], [fin * 4, fin * 4], [3], e, fin * 4),
+            op(3, "MM", "applyedge", "R", [e], [2], 1, 1, [], [fin * fout * 4], [fin * 4], [4], e, fout * 4),
+            op(4, "ADD", "gather", "R", [e], [3], 1, 0, [], [], [fout * 4], [5], n, fout * 4),
+            op(5, "SF", "applynode", "R", [n], [4], 1, 0, [], [], [fout * 4], [], n, fout * 4)]
+
+
+@pytest.mark.parametrize("plan", [[[0, 1, 2, 3, 4, 5]], [[0, 1, 2], [3, 4], [5]], [[0, 1, 2, 3], [4, 5]]],
+                         ids=["one-block", "mm+gather-block", "store-between"])
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "stores-honoured"])
+def test_edge_mm_feeding_a_gather_reduces_first(host, plan, fuse):
+    g, indptr, indices, dg = host
+    op_info = mm_then_gather_case(N, g.num_edges)
+    records = lowering.lower(op_info, plan, [[64, 1]] * len(plan), N)
+    if plan != [[0, 1, 2, 3], [4, 5]]:
+        assert any(i["TYPE"] == "COMP_MM_COMP_ADD" for b in records for i in b)
+    out, ref, names = _run(host, op_info, records, None, False, fuse)
+    np.testing.assert_allclose(out[5].numpy(), ref[5], rtol=1e-4, atol=2e-5 * np.abs(ref[5]).max(), err_msg=str(names))
+    stored_between = plan == [[0, 1, 2, 3], [4, 5]] and not fuse
+    assert ("gta_gemm_f32:after_gather" in names) == (not stored_between), names
+    assert ("gta_gemm_f32:edges" in names) == stored_between, names

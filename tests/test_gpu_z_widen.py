@@ -94,3 +94,29 @@ def test_order_c_gather_on_device(fuse):
     assert any(k == "gta_aggregate_f32:by_source" for k, _ in log)
     again = executor.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs), fuse_across_blocks=fuse)
     assert torch.equal(out[3], again[3])       # deterministic
+
+
+@pytest.mark.parametrize("plan", [[[0, 1, 2, 3, 4, 5]], [[0, 1, 2, 3], [4, 5]]], ids=["one-block", "store-between"])
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused", "stores-honoured"])
+def test_edge_mm_feeding_a_gather_on_device(plan, fuse):
+    """COMP_MM_COMP_ADD: reduce first, GEMM over N rows (and the E-row GEMM when a STORE_E sits between)."""
+    import torch
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import executor, graph, lowering
+
+    class RT:
+        pass
+    rt = RT()
+    rt.graph = graph
+    g, indptr, indices, dg = shared._graph(rt, "cora")
+    n, e = g.num_nodes, g.num_edges
+    op_info = C.mm_then_gather_case(n, e)
+    records = lowering.lower(op_info, plan, [[64, 1]] * len(plan), n)
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, n, e)
+    ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs)
+    dev = lambda d: {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    out, log = executor.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs),
+                                fuse_across_blocks=fuse, return_log=True)
+    np.testing.assert_allclose(out[5].cpu().numpy(), ref[5], rtol=1e-4, atol=2e-5 * np.abs(ref[5]).max(), err_msg=str(log))
+    names = [k for k, _ in log]
+    stored_between = len(plan) == 2 and not fuse
+    assert ("gta_gemm_f32:edges" in names) == stored_between and ("gta_gemm_f32:after_gather" in names) != stored_between
