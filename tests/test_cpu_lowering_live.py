@@ -108,3 +108,28 @@ def test_random_plans_lower_like_the_live_reference(ref, network, reorder):
                 assert got == want, (network, reorder, layer, plan, tiles)
                 agree += 1
     assert agree + crashes == PLANS_PER_CASE and agree > 0
+
+
+def test_tile_tables_match_the_live_preprocessing(tmp_path):
+    """oracle tile_nnz (numpy and C) == the live reference's calculate_sparsity on random graphs with self
+    loops, duplicate-free edges, isolated nodes and tile sizes that do not divide N."""
+    import numpy as np
+    from oracle import c_oracle, gta_oracle as O
+    prep = _load(os.path.join(REF, "code", "preprocessing.py"), "live_preprocessing")
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        n = int(rng.integers(5, 140))
+        dense = (rng.random((n, n)) < rng.choice([0.02, 0.1, 0.4])).astype(np.float32)
+        dense[:, rng.integers(0, n)] = 0            # a source nobody reads
+        dense[rng.integers(0, n), :] = 0            # an isolated destination
+        np.fill_diagonal(dense, (rng.random(n) < 0.5).astype(np.float32))      # self loops the reference removes
+        npy = str(tmp_path / f"adj{trial}.npy")
+        np.save(npy, dense)
+        dst, src = np.nonzero(dense)
+        indptr, indices, _ = O.csr_build(dst.astype(np.int32), src.astype(np.int32), n)
+        for sr in sorted({1, 2, 7, 16, n - 1 or 1, n, n + 3, int(rng.integers(1, n + 1))}):
+            want = np.asarray(prep.calculate_sparsity(sr, 1, npy), dtype=np.int64)
+            got = O.tile_nnz(indptr, indices, n, sr)
+            assert got.shape == want.shape and np.array_equal(got, want), (trial, n, sr)
+            assert np.array_equal(c_oracle.tile_nnz(indptr, indices, n, sr), want), (trial, n, sr)
+        assert prep.gen_size(16, n) == O.tile_size_list(16, n)
