@@ -102,3 +102,82 @@ def test_chunked_exchange_layout_world2_gloo(tmp_path):
         for o in range(rows):
             q = o // cs
             assert np.array_equal(f0[q * (2 * cs) + p * cs + (o - q * cs)], want[o])
+
+
+# ---- end to end: a partitioned execute() over gloo, kernels replaced by the CPU test double -------------
+def _cpu_partition(indptr, indices, rank, world, n):
+    """Host restatement of dist.make_partition (gta_partition + slice + gta_remap_sources, chunks = 1)."""
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import graph
+    b = O.partition_bounds(indptr, world)
+    bounds = [int(v) for v in b]
+    stride = int(-(-max(np.diff(b)) // 4) * 4)
+    full = graph.DeviceGraph(n, int(indptr[-1]), torch.from_numpy(indptr), torch.from_numpy(indices.astype(np.int32)),
+                             num_sources=n)
+    local = graph.slice_rows(full, bounds[rank], bounds[rank + 1])
+    src = local.indices.numpy().astype(np.int64)
+    owner = np.searchsorted(b, src, side="right") - 1
+    local.indices = torch.from_numpy((owner * stride + (src - b[owner])).astype(np.int32))
+    local.num_sources = world * stride
+    return gdist.Partition(rank, world, bounds, stride, local, n), full
+
+
+def _worker_execute(rank, world, port, prog_file, op_file, network, reorder, out_dir):
+    import sys
+    import yaml
+    tests_dir = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, tests_dir)
+    import host_kernels
+    import test_gpu_executor as shared
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import executor, graph
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    executor.kernels = host_kernels
+    graph.DeviceGraph.schedule = lambda self, *a, **k: None
+    n, e = 600, 7000
+    g = synthetic.powerlaw_graph(n, e, seed=9, i0=12.0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    op_info = yaml.safe_load(open(op_file))
+    records = yaml.safe_load(open(prog_file))
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, n, g.num_edges)
+    part, full = _cpu_partition(indptr, indices, rank, world, n)
+    r0, r1 = part.row_begin, part.row_end
+    e0, e1 = int(indptr[r0]), int(indptr[r1])
+    t = torch.from_numpy
+    out = executor.execute(records, op_info, part.local, {k: t(v[r0:r1]) for k, v in node_inputs.items()},
+                           {k: t(v) for k, v in weights.items()}, {k: t(v[e0:e1]) for k, v in edge_inputs.items()},
+                           network=network, is_reorder=reorder, check_shapes=False, source_table=gdist.SourceExchange(part))
+    (p, y), = out.items()
+    np.save(os.path.join(out_dir, f"y_{rank}.npy"), y.numpy())
+    if rank == 0:       # the same program, unpartitioned, same test double
+        whole = executor.execute(records, op_info, full, {k: t(v) for k, v in node_inputs.items()},
+                                 {k: t(v) for k, v in weights.items()}, {k: t(v) for k, v in edge_inputs.items()},
+                                 network=network, is_reorder=reorder, check_shapes=False)
+        np.save(os.path.join(out_dir, "y_whole.npy"), whole[p].numpy())
+        sem = O.NETWORK_SEMANTICS.get((network, reorder), {})
+        ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, semantics=sem, stabilize=True)
+        np.save(os.path.join(out_dir, "y_ref.npy"), ref[p])
+        np.save(os.path.join(out_dir, "bounds.npy"), np.asarray(part.bounds))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,network,reorder", [
+    ("GAT-cora-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13", "GAT", False),
+    ("GCN-cora-layer1-trans__0_1-2-3", "GCN", True),
+])
+def test_partitioned_execute_world2_gloo(tmp_path, name, network, reorder):
+    """Destination-range partition, one all-gather of the source-side table per layer: the rows two ranks
+    compute (host logic of dist.py + executor.py, kernels = CPU test double) are the rows one process computes."""
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    mode = "trans" if reorder else "original"
+    port = _free_port()
+    mp.spawn(_worker_execute, args=(2, port, os.path.join(golden, "isa", name + ".yaml"),
+                                    os.path.join(golden, "opgraph", f"{network}-cora-layer1-{mode}.yaml"), network, reorder,
+                                    str(tmp_path)), nprocs=2, join=True)
+    bounds = np.load(tmp_path / "bounds.npy")
+    whole, ref = np.load(tmp_path / "y_whole.npy"), np.load(tmp_path / "y_ref.npy")
+    parts = [np.load(tmp_path / f"y_{r}.npy") for r in range(2)]
+    assert [p.shape[0] for p in parts] == list(np.diff(bounds)) and 0 < bounds[1] < bounds[2]
+    got = np.concatenate(parts)
+    assert np.array_equal(got, whole)                       # same reduction order -> same bits
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
