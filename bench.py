@@ -72,6 +72,15 @@ def graph_of(shape):
 METRIC = "GTEPS per GAT/GCN layer (Reddit shape)"
 
 
+def baseline_metric():
+    """BASELINE.json's metric string, verbatim (``METRIC`` is its GTEPS half; the roofline object is the other)."""
+    try:
+        with open(os.path.join(REPO, "BASELINE.json")) as f:
+            return json.load(f).get("metric")
+    except (OSError, ValueError):
+        return None
+
+
 def load_yaml(rel):
     import yaml
     with open(os.path.join(REPO, "tests", "golden", rel)) as f:
@@ -214,7 +223,7 @@ def run_reference_arm(args, wl):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tg + te) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": workload_name(args, wl)},
+            "data": "synthetic", "config": {"workload": workload_name(args, wl), "baseline_metric": baseline_metric()},
             "cpu_baseline": {"value": value, "unit": "GTEPS", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -527,7 +536,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args, wl),
+            "config": {"workload": workload_name(args, wl), "baseline_metric": baseline_metric(),
                        "parallelism": f"dst-range partition x{world}" + ((", one NCCL all-gather of [Z|er] per layer" if args.exchange == "nccl" else ", [Z|er] pulled from the peers' IPC-mapped slots by copy engines")
                                         + (" in %d overlapped chunks" % args.chunks if args.chunks > 1 else "") if world > 1 else ""),
                        "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
