@@ -47,7 +47,7 @@ import yaml
 
 from . import _cabi, kernels
 from .graph import DeviceGraph, csr_from_coo
-from .isa import IsaError, Program
+from .isa import IsaError, Program, validate_op_graph
 
 #: COMP_TYPE -> arithmetic where the YAML alone is ambiguous (the reference only names ops)
 DEFAULT_SEMANTICS = {
@@ -388,11 +388,8 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
     edge_inputs = edge_inputs or {}
     sem = dict(NETWORK_SEMANTICS.get((network, bool(is_reorder)), {}))
     sem.update(semantics or {})
+    validate_op_graph(op_info)
     for pos, op in enumerate(op_info):
-        if "COMP_TYPE" not in op:
-            raise IsaError(f"op {pos} has no COMP_TYPE (V1/V2-era YAML; re-stamp it, changeyaml.py:18-114)")
-        if op["TYPE"] not in ("applynode", "applyedge", "scatter", "gather"):
-            raise IsaError(f"op {pos}: unknown TYPE {op['TYPE']!r}")
         if check_shapes:
             want = graph.num_edges if op["TYPE"] in ("applyedge", "gather") else graph.num_nodes
             for cnt in op["INPUT"]["feature_number"]:
@@ -403,6 +400,10 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
     block_ops = program.block_ops(op_info)
     stored = program.stored_ops()
     n_ops = len(op_info)
+    for ops in stored:
+        for p in ops:
+            if not 0 <= p < n_ops:
+                raise IsaError(f"a STORE_* names op {p}, the op graph has {n_ops}")
     finals = [p for p in range(n_ops) if not op_info[p]["OUTPUT"]["output_list"]]
     wanted = list(outputs) if outputs is not None else finals
 
@@ -468,6 +469,16 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
 
         if not prods[pos]:
             args.append(external("has no producer"))
+        want_edges = typ in ("applyedge", "gather")
+        for a in args:
+            if a.on_edges != want_edges:
+                raise IsaError(f"op {pos} ({typ}) reads {'an edge' if a.on_edges else 'a node'} tensor "
+                               f"(from op {a.pos}); it needs {'edge' if want_edges else 'node'} tensors")
+            if a.kind in ("node", "edge") and a.tensor is not None:
+                rows = graph.num_edges if a.kind == "edge" else graph.num_rows
+                if a.tensor.dim() != 2 or int(a.tensor.shape[0]) != rows:
+                    raise ExecutionError(f"op {pos}: external {a.kind} input is {tuple(a.tensor.shape)}, "
+                                         f"expected [{rows}, width]")
         if typ == "scatter":
             if order_ not in ("R", "C"):
                 raise IsaError(f"op {pos}: ORDER {order_!r}")
@@ -485,6 +496,8 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
             if pos not in weights:
                 raise ExecutionError(f"op {pos} is COMP_MM: pass weights[{pos}]")
             w = weights[pos]
+            if w.dim() != 2:
+                raise ExecutionError(f"op {pos}: weight must be [Fin, Fout], got {tuple(w.shape)}")
             if int(w.shape[0]) != args[0].width:
                 raise ExecutionError(f"op {pos}: weight is {tuple(w.shape)} but the input is {args[0].width} wide")
             if typ == "applyedge":

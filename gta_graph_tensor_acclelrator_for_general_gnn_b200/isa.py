@@ -29,6 +29,51 @@ class IsaError(ValueError):
     """Malformed or unknown instruction (the executor rejects, never crashes)."""
 
 
+def _int_list(v, what, pos):
+    if not isinstance(v, list) or any(isinstance(x, bool) or not isinstance(x, int) for x in v):
+        raise IsaError(f"op {pos}: {what} must be a list of integers, got {v!r}")
+    return v
+
+
+def validate_op_graph(op_info) -> None:
+    """Schema check of an op-graph list (template/op_template.yaml:1-19 plus ``COMP_TYPE``): the fields the
+    executor reads exist and have the types it assumes.  Raises :class:`IsaError` naming the op."""
+    if not isinstance(op_info, list) or not op_info:
+        raise IsaError("an op graph is a non-empty list of op records")
+    n = len(op_info)
+    for pos, op in enumerate(op_info):
+        if not isinstance(op, dict):
+            raise IsaError(f"op {pos}: an op record is a mapping, got {type(op).__name__}")
+        if "COMP_TYPE" not in op:
+            raise IsaError(f"op {pos} has no COMP_TYPE (V1/V2-era YAML; re-stamp it, changeyaml.py:18-114)")
+        if op.get("TYPE") not in OP_TYPES:
+            raise IsaError(f"op {pos}: unknown TYPE {op.get('TYPE')!r}")
+        if op["COMP_TYPE"] not in COMP_TYPES:
+            raise IsaError(f"op {pos}: unknown COMP_TYPE {op['COMP_TYPE']!r}")
+        if op.get("ORDER") not in ("R", "C"):
+            raise IsaError(f"op {pos}: ORDER {op.get('ORDER')!r}")
+        inp, out = op.get("INPUT"), op.get("OUTPUT")
+        if not isinstance(inp, dict) or not isinstance(out, dict):
+            raise IsaError(f"op {pos}: INPUT and OUTPUT must be mappings")
+        for key in ("input_g_list", "size_per_feature", "feature_number"):
+            if key not in inp:
+                raise IsaError(f"op {pos}: INPUT.{key} is missing")
+            _int_list(inp[key], f"INPUT.{key}", pos)
+        for q in inp["input_g_list"]:
+            if q != -1 and not 0 <= q < n:
+                raise IsaError(f"op {pos}: producer {q} is not an op of this graph")
+        if len(inp["size_per_feature"]) < max(len(inp["input_g_list"]), 1):
+            raise IsaError(f"op {pos}: INPUT.size_per_feature has fewer entries than the op has inputs")
+        if "output_list" not in out:
+            raise IsaError(f"op {pos}: OUTPUT.output_list is missing")
+        _int_list(out["output_list"], "OUTPUT.output_list", pos)
+        width = out.get("size_per_feature")
+        if isinstance(width, bool) or not isinstance(width, int) or width <= 0:
+            raise IsaError(f"op {pos}: OUTPUT.size_per_feature must be a positive integer, got {width!r}")
+        if any(isinstance(w, bool) or w <= 0 for w in inp["size_per_feature"]):
+            raise IsaError(f"op {pos}: INPUT.size_per_feature must be positive")
+
+
 @dataclass(frozen=True)
 class OpRef:
     op: int        # position in the op-graph list (the reference indexes op_info by position)
@@ -70,6 +115,8 @@ class Instruction:
 
 
 def parse_id(inst_id: str) -> tuple:
+    if not isinstance(inst_id, str):
+        raise IsaError(f"instruction ID must be a string, got {type(inst_id).__name__}")
     refs = tuple(OpRef(int(m.group(1)), m.group(2), int(m.group(3))) for m in _ID_PART.finditer(inst_id))
     rebuilt = "_".join(f"{r.op}_{r.kind}_{r.slot}" for r in refs)
     if not refs or rebuilt != inst_id:
@@ -77,18 +124,31 @@ def parse_id(inst_id: str) -> tuple:
     return refs
 
 
+def _deps(rec: dict, kind: str) -> list:
+    out = []
+    for d in rec["Dependency"][kind]:
+        times = list(d["Times"])
+        if not isinstance(d["TYPE"], str) or not isinstance(d["ID"], str) or len(times) != 2:
+            raise TypeError(f"{kind} dependency {d!r}")
+        out.append((d["TYPE"], d["ID"], [int(t) for t in times]))
+    return out
+
+
 def _parse_instruction(rec: dict) -> Instruction:
+    if not isinstance(rec, dict):
+        raise IsaError(f"an instruction is a mapping, got {type(rec).__name__}")
     try:
         typ = rec["TYPE"]
+        if not isinstance(typ, str):
+            raise TypeError(f"TYPE {typ!r}")
         inst = Instruction(
             type=typ, id=rec["ID"], unit=rec.get("Hardware_Unit", ""),
             tile_times=int(rec["Tile_Times"]), tile_size=int(rec["Tile_Size"]),
             feature_length=int(rec["Feature_Length"]),
             weight_size=rec.get("Weight_Size"),
-            raw=[(d["TYPE"], d["ID"], list(d["Times"])) for d in rec["Dependency"]["RAW"]],
-            war=[(d["TYPE"], d["ID"], list(d["Times"])) for d in rec["Dependency"]["WAR"]],
+            raw=_deps(rec, "RAW"), war=_deps(rec, "WAR"),
         )
-    except (KeyError, TypeError) as exc:
+    except (KeyError, TypeError, ValueError) as exc:
         raise IsaError(f"malformed instruction record: {exc!r}") from exc
     inst.refs = parse_id(inst.id)
     if typ == "FETCH":
@@ -138,6 +198,9 @@ class Program:
             prods = [p for p in op["INPUT"]["input_g_list"] if p != -1]
             if prods and prods[0] in owner:
                 owner[pos] = owner[prods[0]]
+        beyond = sorted(p for p in owner if p >= len(op_info))
+        if beyond:
+            raise IsaError(f"the program names ops {beyond}, the op graph has {len(op_info)}")
         missing = [p for p in range(len(op_info)) if p not in owner]
         if missing:
             raise IsaError(f"ops {missing} of the op graph appear in no block of the program")

@@ -216,3 +216,86 @@ def test_edge_mm_feeding_a_gather_reduces_first(host, plan, fuse):
     stored_between = plan == [[0, 1, 2, 3], [4, 5]] and not fuse
     assert ("gta_gemm_f32:after_gather" in names) == (not stored_between), names
     assert ("gta_gemm_f32:edges" in names) == stored_between, names
+
+
+# ---- corrupted inputs are rejected, never crashed on (SURVEY 8b "Errors") ---------------------------
+_JUNK = [None, 5, "x", [], {}, "COMP_", "LOAD_Q", "9_applyedge", "a_b_c", -1, 3.5, ["a"], {"TYPE": 1}, "COMP_MM",
+         "STORE_E", "99_gather_0", "STORE_N", "LOAD_E", "1_scatter_0", "2_gather_0", "COMP_MUL_COMP_ADD", [99], [0, 0, 0],
+         "scatter", "gather", "MM", "C", 4, 6, [-1, -1]]
+_REJECTIONS = (isa.IsaError, executor.ExecutionError, _cabi.GtaUnsupported)
+
+
+def _corrupt_program(rng, rec):
+    for _ in range(rng.randint(1, 3)):
+        if not isinstance(rec, list) or not rec:
+            return rec
+        b = rng.randrange(len(rec))
+        if not isinstance(rec[b], list) or not rec[b]:
+            continue
+        i = rng.randrange(len(rec[b]))
+        m = rng.random()
+        if m < 0.2 and isinstance(rec[b][i], dict) and rec[b][i]:
+            del rec[b][i][rng.choice(list(rec[b][i]))]
+        elif m < 0.6 and isinstance(rec[b][i], dict) and rec[b][i]:
+            rec[b][i][rng.choice(["TYPE", "ID"] + list(rec[b][i]))] = rng.choice(_JUNK)
+        elif m < 0.7:
+            rec[b][i] = rng.choice(_JUNK)
+        elif m < 0.9:
+            del rec[b][i]
+        else:
+            rec[b] = rng.choice(_JUNK)
+    return rec
+
+
+def _corrupt_op_graph(rng, op_info):
+    for _ in range(rng.randint(1, 2)):
+        i = rng.randrange(len(op_info))
+        op = op_info[i]
+        if not isinstance(op, dict) or not op:
+            continue
+        m = rng.random()
+        if m < 0.25:
+            del op[rng.choice(list(op))]
+        elif m < 0.5:
+            op[rng.choice(list(op))] = rng.choice(_JUNK)
+        elif m < 0.9:
+            sub = op.get(rng.choice(["INPUT", "OUTPUT"]))
+            if isinstance(sub, dict) and sub:
+                k = rng.choice(list(sub))
+                if rng.random() < 0.3:
+                    del sub[k]
+                else:
+                    sub[k] = rng.choice(_JUNK)
+        else:
+            op_info[i] = rng.choice(_JUNK)
+    return op_info
+
+
+@pytest.mark.parametrize("what", ["program", "op-graph"])
+def test_corrupted_inputs_are_rejected_not_crashed_on(host, what):
+    """Random damage to an ISA program or to an op graph: execute() either runs or raises one of its three
+    documented error types -- never a KeyError / TypeError / IndexError from deep inside."""
+    import copy
+    import random
+    g, indptr, indices, dg = host
+    progs = [p for p in PROGRAMS if p["dataset"] == "cora" and (p["layer"] > 1 or p["network"] == "GCN")]
+    progs = [p for p in progs if p["layer"] > 1][:4] + [p for p in progs if p["layer"] == 1][:1]
+    loaded = {p["file"]: (_load(p["file"]), _load(p["opgraph"])) for p in progs}
+    tensors = {f: tuple(_t(d) for d in shared._inputs(op, N, g.num_edges)) for f, (_, op) in loaded.items()}
+    rng = random.Random(5 if what == "program" else 6)
+    ran = refused = 0
+    for trial in range(400):
+        p = rng.choice(progs)
+        records, op_info = copy.deepcopy(loaded[p["file"]][0]), copy.deepcopy(loaded[p["file"]][1])
+        node_inputs, weights, edge_inputs = tensors[p["file"]]
+        if what == "program":
+            records = _corrupt_program(rng, records)
+        else:
+            op_info = _corrupt_op_graph(rng, op_info)
+        try:
+            executor.execute(records, op_info, dg, node_inputs, weights, edge_inputs, network=p["network"],
+                             is_reorder=p["reorder"], check_shapes=False, fuse_across_blocks=bool(trial % 2))
+            ran += 1
+        except _REJECTIONS:
+            refused += 1
+    assert refused > 100 and ran + refused == 400
