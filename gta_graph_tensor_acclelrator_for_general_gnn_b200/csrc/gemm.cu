@@ -23,7 +23,7 @@ extern "C" {
 // 0 = auto (tensor cores when eligible), 1 = force FFMA, 2 = force tcgen05 (error if ineligible)
 static int g_gemm_mode = 0;
 int gta_gemm_set_mode(int mode) {
-  if (mode < 0 || mode > 2) return GTA_ERR_INVALID;
+  GTA_REQUIRE(mode >= 0 && mode <= 2, "gta_gemm_set_mode: mode %d is not 0 (auto), 1 (simt) or 2 (tc)", mode);
   g_gemm_mode = mode;
   return GTA_OK;
 }

@@ -182,3 +182,29 @@ def test_model_times_fixture_refers_to_golden_programs():
     by = {m["file"].split("/")[-1]: m for m in done}
     assert by["GAT-cora-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml"]["cycles"] < \
         by["GAT-cora-layer1-original__0_1_2_3_4_5_6_7_8_9_10_11_12_13.yaml"]["cycles"]
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Every entry point validates its arguments before it touches the device: null pointers and impossible
+    sizes come back as GTA_ERR_INVALID with a message naming the function (no launch, so this runs on CPU)."""
+    lib = _cabi.load()
+
+    def refused(name, rc):
+        assert rc == _cabi.ERR_INVALID, (name, rc)
+        assert lib.gta_last_error().decode().startswith(name), (name, lib.gta_last_error())
+
+    n = None
+    refused("gta_csr_build", lib.gta_csr_build(n, n, 10, 5, n, n, n, n, 0, n))
+    refused("gta_csr_build", lib.gta_csr_build(n, n, -1, 5, n, n, n, n, 0, n))
+    refused("gta_tile_nnz", lib.gta_tile_nnz(n, n, 10, 0, 0, 1, n, n))
+    refused("gta_partition", lib.gta_partition(n, 10, 0, n, n))
+    refused("gta_gemm_f32", lib.gta_gemm_f32(n, 0, n, 0, n, 0, 10, 4, 4, n, n, 0, n, n, 0, n, 0, n))
+    refused("gta_aggregate_f32", lib.gta_aggregate_f32(n, 1, n, 1, 0, n, 0, n, 0, n, n, 4, n, 4, 4, 0, n, 3, n))
+    refused("gta_gat_aggregate_f32", lib.gta_gat_aggregate_f32(n, 1, n, 1, 0, n, n, n, 4, 4, 0.2, n, 128, n, 128, 128, 0,
+                                                              n, n, n, 3, n))
+    refused("gta_edge_binary_f32", lib.gta_edge_binary_f32(n, n, 0, 1, 0, n, 0, 3, 3, n, 0, 4, 4, n, 4, 4, n))
+    refused("gta_node_unary_f32", lib.gta_node_unary_f32(9, 0.2, n, 4, n, 4, 4, 1, n))
+    refused("gta_schedule_build", lib.gta_schedule_build(n, n, 0, 1, 1, 0, 0, n, 0, n, n, n, n, 0, n))
+    refused("gta_copy_many", lib.gta_copy_many(n, n, n, -1, n))
+    refused("gta_gemm_set_mode", lib.gta_gemm_set_mode(7))
+    assert lib.gta_gemm_get_mode() in (0, 1, 2)
