@@ -387,6 +387,15 @@ def dumps(blocks) -> str:
     return yaml.dump(blocks, Dumper=_NoAliasDumper)
 
 
+def unfused_plan(op_info, tile_rows: int = 512):
+    """``(op_array, tile_size_list)`` with one op per block: the plan that always lowers (no instruction fusion, every
+    tensor stored), for running the chain without the reference's ``compile()``.  ``execute()`` fuses dead stores away
+    again (``fuse_across_blocks``), so on the GPU it costs nothing against a compiler-chosen plan
+    (profiles/r01_plan_vs_model.json: every GAT layer-1 plan runs in the same 75 us)."""
+    n = len(op_info)
+    return [[i] for i in range(n)], [[int(tile_rows), 1] for _ in range(n)]
+
+
 def interpret(data_set, network, isReorder, layer, op_array, tile_size_list):
     """Drop-in for the reference's ``interpret`` (same arguments, same CWD-relative files, returns None)."""
     node_num = NODE_COUNT.get(data_set, 0)

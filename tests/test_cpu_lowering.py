@@ -139,3 +139,12 @@ def test_generated_graph_lowers_to_the_golden_program():
     op_info = opgraph.build(n, e, f, "GCN", 1, True, repair=True)
     blocks = lowering.lower(op_info, prog["op_array"], prog["tile_size_list"], n)
     assert lowering.dumps(blocks) == open(os.path.join(GOLDEN, prog["file"])).read()
+
+
+@pytest.mark.parametrize("network", opgraph.NETWORKS)
+@pytest.mark.parametrize("reorder", [False, True])
+def test_unfused_plan_lowers_for_every_network(network, reorder):
+    op_info = opgraph.build(*synthetic.SHAPES["cora"], network, 1, reorder, repair=True)
+    plan, tiles = lowering.unfused_plan(op_info)
+    program = isa.Program.from_records(lowering.lower(op_info, plan, tiles, synthetic.SHAPES["cora"][0]))
+    assert program.block_ops(op_info) == plan
