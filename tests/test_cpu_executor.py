@@ -299,3 +299,21 @@ def test_corrupted_inputs_are_rejected_not_crashed_on(host, what):
         except _REJECTIONS:
             refused += 1
     assert refused > 100 and ran + refused == 400
+
+
+def test_whole_chain_on_files_without_the_reference(host, tmp_path, monkeypatch):
+    """INTEGRATION.md's stand-alone flow, on disk and CWD-relative like the reference's: gen_yaml -> unfused_plan ->
+    interpret -> execute_files (the arguments of simulate())."""
+    monkeypatch.chdir(tmp_path)
+    g, indptr, indices, dg = host
+    n, e, f = synthetic.SHAPES["cora"]
+    op_info = opgraph.gen_yaml(opgraph.network_path("GAT", "cora", 2, False), n, e, f, "GAT", 2, False)
+    op_array, tile_size_list = lowering.unfused_plan(op_info)
+    lowering.interpret("cora", "GAT", False, "layer2", op_array, tile_size_list)
+    assert os.path.exists("Results/Insts/GAT-cora-layer2-original.yaml")
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
+    out = executor.execute_files(tile_size_list, "cora", "GAT", "layer2", False, dg, _t(node_inputs), _t(weights),
+                                 _t(edge_inputs), check_shapes=False)
+    ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs,
+                        semantics=O.NETWORK_SEMANTICS[("GAT", False)], stabilize=True)
+    np.testing.assert_allclose(out[13].numpy(), ref[13], rtol=1e-4, atol=2e-5 * np.abs(ref[13]).max())
