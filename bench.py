@@ -326,7 +326,7 @@ def main():
         edge_w = (1.0 / torch.sqrt(deg[rows] * deg[src_glob])).to(torch.float32)[:, None].contiguous()
         del rows, src_glob
     host_csr = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU leg is an N = 1 item (rank 0's host cores)
         host_csr = (full.indptr.cpu().numpy(), None)
         deg_h = np.diff(host_csr[0])
         sample_rows = int(min(n, max(64, np.searchsorted(np.cumsum(deg_h), args.cpu_sample_edges) + 1)))
