@@ -133,3 +133,26 @@ def test_tile_tables_match_the_live_preprocessing(tmp_path):
             assert got.shape == want.shape and np.array_equal(got, want), (trial, n, sr)
             assert np.array_equal(c_oracle.tile_nnz(indptr, indices, n, sr), want), (trial, n, sr)
         assert prep.gen_size(16, n) == O.tile_size_list(16, n)
+
+
+def test_generators_match_the_live_reference_for_random_sizes(ref, tmp_path):
+    """gen_yaml for random (N, E, F) over every network / layer / reorder, and modify_yaml on a copy of the shipped
+    V2/GAT_Cora.yaml: same bytes as the live reference writes."""
+    rng = random.Random(99)
+    chg = _load(os.path.join(REF, "FinalVersion For Paper", "changeyaml.py"), "live_changeyaml")
+    for trial in range(6):
+        n, e, f = rng.randint(2, 10**6), rng.randint(1, 10**8), rng.randint(1, 5000)
+        for network in opgraph.NETWORKS:
+            for layer in (1, 2, 3):
+                for reorder in (False, True):
+                    theirs, ours = tmp_path / "theirs.yaml", tmp_path / "ours.yaml"
+                    ref["gen"].gen_yaml(str(theirs), n, e, f, network, layer, reorder)
+                    opgraph.gen_yaml(str(ours), n, e, f, network, layer, reorder)
+                    assert ours.read_text() == theirs.read_text(), (n, e, f, network, layer, reorder)
+        theirs, ours = tmp_path / "restamp_theirs.yaml", tmp_path / "restamp_ours.yaml"
+        for path in (theirs, ours):
+            shutil.copy(os.path.join(REF, "V2", "GAT_Cora.yaml"), path)
+        chg.modify_yaml(str(theirs), n, e, f, [])
+        opgraph.modify_yaml(str(ours), n, e, f, [])
+        assert ours.read_text() == theirs.read_text(), (n, e, f)
+        assert opgraph.generate_connections(str(ours)) == chg.generate_connections(str(theirs))
