@@ -199,3 +199,38 @@ def gcn_edge_norm(indptr: np.ndarray, indices: np.ndarray, rows: np.ndarray | No
     if rows is None:
         rows = np.repeat(np.arange(indptr.shape[0] - 1), np.diff(indptr))
     return (1.0 / np.sqrt(deg[rows] * deg[indices])).astype(np.float32)
+
+
+def opgraph_inputs(op_info, n: int, e: int, seed: int = 0):
+    """Random fp32 tensors for every external input and weight of an op graph: ``(node_inputs, weights,
+    edge_inputs)`` keyed by op position, as ``executor.execute`` takes them.  External = an op without a producer
+    (or PNA-trans' self reference), a ``-1`` entry of ``input_g_list`` (edge weights in (0.05, 1]; GIN's ``[x, eps]``
+    pair), and the second operand of a binary op that declares one input (DGN / PNA degree scaler)."""
+    rng = np.random.default_rng(seed)
+    node_inputs, weights, edge_inputs = {}, {}, {}
+    for pos, op in enumerate(op_info):
+        widths = [s // 4 for s in op["INPUT"]["size_per_feature"]]
+        ins = op["INPUT"]["input_g_list"]
+        if op["COMP_TYPE"] == "MM":
+            fout = op["OUTPUT"]["size_per_feature"] // 4
+            weights[pos] = glorot(rng, widths[0], fout) if fout > 16 else \
+                rng.uniform(-0.1, 0.1, size=(widths[0], fout)).astype(np.float32)
+        on_edges = op["TYPE"] in ("applyedge", "gather")
+        if not ins or ins == [pos]:
+            if on_edges:
+                edge_inputs[pos] = rng.standard_normal((e, widths[0]), dtype=np.float32)
+            else:
+                node_inputs[pos] = rng.standard_normal((n, widths[0]), dtype=np.float32)
+        elif op["COMP_TYPE"] in ("MUL", "ADD") and len(ins) == 1:
+            (edge_inputs if on_edges else node_inputs)[pos] = \
+                rng.uniform(0.5, 1.5, size=(e if on_edges else n, 1)).astype(np.float32)
+        ext = []
+        for slot, q in enumerate(ins):
+            if q == -1:
+                if on_edges:
+                    ext.append(rng.uniform(0.05, 1.0, size=(e, 1)).astype(np.float32))
+                else:
+                    ext.append(rng.standard_normal((n, widths[slot]), dtype=np.float32))
+        if ext:
+            (edge_inputs if on_edges else node_inputs)[pos] = ext[0] if len(ext) == 1 else ext
+    return node_inputs, weights, edge_inputs

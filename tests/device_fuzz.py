@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Random op graphs under random plans through execute() on the GPU, against the oracle: the device-side run of
 tests/test_cpu_executor_fuzz.py (which swaps the kernels for a CPU test double).  tests/test_gpu_z_widen.py runs the
-first 60 cases; this script runs as many as asked (`tools/gpu.sh -- 'python tools/fuzz_device.py --cases 300'`).
+first 60 cases; as a script it runs as many as asked (`tools/gpu.sh -- 'python tests/device_fuzz.py --cases 300'`).
 Round 1: 150 cases on a B200, 0 failed, 0 unsupported.
 
 Prints one line per failing case (seed, op, error, kernel log) and a summary; exit code 1 on any failure.
@@ -17,7 +17,7 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, os.path.join(REPO, "tests"))      # lives under tests/: it uses the oracle as its checker
 
 
 def run_cases(first: int, cases: int):

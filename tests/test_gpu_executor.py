@@ -34,35 +34,7 @@ def _small_shape(dataset):
 
 def _inputs(op_info, n, e, seed=0):
     """Random tensors for every external input / weight of an op graph (fp32)."""
-    rng = np.random.default_rng(seed)
-    node_inputs, weights, edge_inputs = {}, {}, {}
-    for pos, op in enumerate(op_info):
-        widths = [s // 4 for s in op["INPUT"]["size_per_feature"]]
-        ins = op["INPUT"]["input_g_list"]
-        if op["COMP_TYPE"] == "MM":
-            fout = op["OUTPUT"]["size_per_feature"] // 4
-            weights[pos] = synthetic.glorot(rng, widths[0], fout) if fout > 16 else \
-                rng.uniform(-0.1, 0.1, size=(widths[0], fout)).astype(np.float32)
-        on_edges = op["TYPE"] in ("applyedge", "gather")
-        if not ins or ins == [pos]:       # no producer (or PNA-trans' self reference): external tensor
-            if on_edges:
-                edge_inputs[pos] = rng.standard_normal((e, widths[0]), dtype=np.float32)
-            else:
-                node_inputs[pos] = rng.standard_normal((n, widths[0]), dtype=np.float32)
-        elif op["COMP_TYPE"] in ("MUL", "ADD") and len(ins) == 1:     # DGN/PNA op 9: external degree scaler
-            (edge_inputs if on_edges else node_inputs)[pos] = \
-                rng.uniform(0.5, 1.5, size=(e if on_edges else n, 1)).astype(np.float32)
-        ext = []
-        for slot, q in enumerate(ins):
-            if q == -1:
-                if op["TYPE"] in ("applyedge", "gather"):
-                    ext.append(rng.uniform(0.05, 1.0, size=(e, 1)).astype(np.float32))
-                else:
-                    ext.append(rng.standard_normal((n, widths[slot]), dtype=np.float32))
-        if ext:
-            target = edge_inputs if op["TYPE"] in ("applyedge", "gather") else node_inputs
-            target[pos] = ext[0] if len(ext) == 1 else ext
-    return node_inputs, weights, edge_inputs
+    return synthetic.opgraph_inputs(op_info, n, e, seed)
 
 
 @pytest.fixture(scope="module")

@@ -124,10 +124,7 @@ def test_edge_mm_feeding_a_gather_on_device(plan, fuse):
 
 def test_random_op_graphs_on_device():
     """The op-graph fuzz of tests/test_cpu_executor_fuzz.py with the CUDA kernels in place of the test double
-    (tools/fuzz_device.py; its first 150 cases ran clean on a B200 in round 1)."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
-    import fuzz_device
-    bad, unsupported, messages = fuzz_device.run_cases(0, 60)
+    (tests/device_fuzz.py; its first 150 cases ran clean on a B200 in round 1)."""
+    import device_fuzz
+    bad, unsupported, messages = device_fuzz.run_cases(0, 60)
     assert bad == 0 and unsupported == 0, "\n".join(messages)

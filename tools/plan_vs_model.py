@@ -23,7 +23,6 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "tests"))
 
 
 def main():
@@ -34,7 +33,6 @@ def main():
     import torch
     import yaml
 
-    import test_gpu_executor as shared
     from gta_graph_tensor_acclelrator_for_general_gnn_b200 import executor, graph, synthetic
 
     golden = os.path.join(REPO, "tests", "golden")
@@ -71,7 +69,7 @@ def main():
             op_info = yaml.safe_load(f)
         with open(os.path.join(golden, p["file"])) as f:
             records = yaml.safe_load(f)
-        ni, w, ei = (dev(d) for d in shared._inputs(op_info, n, e))
+        ni, w, ei = (dev(d) for d in synthetic.opgraph_inputs(op_info, n, e))
         row = {"program": os.path.basename(m["file"])[:-5], "blocks": len(p["op_array"]),
                "model_us": m["cycles"] / 1e3, "model_rw_mb": m["rw_bytes"] / 1e6}
         for label, fuse in (("stores_honoured_us", False), ("fused_us", True)):
