@@ -208,3 +208,35 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     refused("gta_copy_many", lib.gta_copy_many(n, n, n, -1, n))
     refused("gta_gemm_set_mode", lib.gta_gemm_set_mode(7))
     assert lib.gta_gemm_get_mode() in (0, 1, 2)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on stdout
+    with the contract's keys, on a small workload so the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "cora-gat",
+                          "--steps", "3", "--warmup", "3"], capture_output=True, text=True, timeout=600, check=True).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, out
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "GTEPS" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 3 and line["vs_baseline"] is None and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_bench_refuses_to_run_the_gpu_arm_without_a_gpu():
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", "cora-gat", "--steps", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
