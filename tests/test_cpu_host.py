@@ -240,3 +240,23 @@ def test_bench_refuses_to_run_the_gpu_arm_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", "cora-gat", "--steps", "1"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_committed_bench_lines_carry_the_contract_keys(n):
+    """profiles/r01_bench_n*.json: the GPU arm's lines as measured on the box (what DESIGN.md quotes)."""
+    import json
+    with open(os.path.join(REPO, "profiles", f"r01_bench_n{n}.json")) as f:
+        line = json.loads([l for l in f.read().splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in line, key
+    assert line["n_gpus"] == n and line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["dtype"] == "f32"
+    assert abs(line["value"] - 114615892 / (line["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * line["value"]
+    roof = line["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < line["value"] * 1.5
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if n == 1:
+        assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
