@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libgta_b200" + ("_" + _TAG if _TAG else "") + ".
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 EPI_NONE, EPI_ELU, EPI_RELU = 0, 1, 2
 W_NONE, W_EDGE, W_EDGE_DIV = 0, 1, 2
-PHASE_MAIN, PHASE_COMBINE, PHASE_ALL = 1, 2, 3
+PHASE_MAIN, PHASE_RESET, PHASE_ALL = 1, 2, 3
 OPND_EDGE, OPND_DST, OPND_SRC = 0, 1, 2
 BIN_ADD, BIN_MUL, BIN_DIV = 0, 1, 2
 UN_EXP_LEAKY_RELU, UN_ELU, UN_RELU, UN_COPY = 0, 1, 2, 3
@@ -57,11 +57,11 @@ SIGNATURES = {
                                _p]),
     "gta_gemm_set_mode": (C.c_int, [C.c_int]),
     "gta_gemm_get_mode": (C.c_int, []),
-    "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
-                                    _p, _i32, _p]),
+    "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
+                                    _p, _p, _i32, _p]),
     "gta_gat_partial_stride": (_i32, [_i32, _i32]),
-    "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _i64,
-                                        _i32, _i32, _p, _p, _p, _i32, _p]),
+    "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _i64,
+                                        _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "gta_gat_logits_f32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "gta_edge_binary_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _i32, _i32, _i64, _p, _i32,
                                       _i64, _p]),

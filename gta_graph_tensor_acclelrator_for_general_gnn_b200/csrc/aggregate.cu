@@ -14,9 +14,16 @@
 // column-block order of the work list.  kUnroll independent row loads are in flight per lane and a
 // full batch runs without a single predicate.
 //
-// Determinism.  Every item is reduced by exactly one group in ascending source order, and the
-// items of a row are combined in slot order by *_combine_kernel: a fixed-shape reduction, bitwise
-// reproducible run to run, no atomics.
+// Rows that own several items (long rows cut at `chunk` edges, and every row when the table is walked
+// in column blocks) form a CHAIN in slot order: an item reduces its own edges first, then waits for
+// its predecessor's published state (a release/acquire flag per slot), folds it in, and either
+// publishes the folded state or -- last item of the row -- normalises and writes the output.  The
+// wait is at the END of an item and predecessors always sit earlier in the grid (CTAs are dispatched
+// in blockIdx order), so it almost never spins; there is no separate merge launch and the last
+// partial of every row is never written (round 1: a combine kernel re-read 507 MB in 0.24 ms).
+//
+// Determinism.  Every item is reduced by exactly one group in ascending source order and the chain
+// is a left fold in slot order: a fixed-shape reduction, bitwise reproducible run to run, no atomics.
 #include "common.cuh"
 
 namespace gta {
@@ -30,13 +37,56 @@ namespace gta {
 #ifndef GTA_AGG_MINBLOCKS
 #define GTA_AGG_MINBLOCKS 6       // 128 threads x 6 blocks = 24 warps/SM => at most 80 registers (measured best)
 #endif
+#ifndef GTA_AGG_FASTEXP
+#define GTA_AGG_FASTEXP 0
+#endif
 constexpr int kAggThreads = GTA_AGG_THREADS;
 constexpr int kAggWarps = kAggThreads / 32;
 constexpr int kUnroll = GTA_AGG_UNROLL;
 constexpr int kAggMinBlocks = GTA_AGG_MINBLOCKS;
 
-// floats per partial slot of the GAT kernel: acc[f] | max[H] | sum[H], padded to 16 bytes
-__host__ __device__ inline int gat_partial_stride(int f, int heads) { return f + ((2 * heads + 3) & ~3); }
+// floats per partial slot of the GAT kernel: acc[f] | per 128-feature window: max[H] | sum[H], padded to 16 bytes
+__host__ __device__ inline int gat_stats_stride(int heads) { return (2 * heads + 3) & ~3; }
+__host__ __device__ inline int gat_partial_stride(int f, int heads) { return f + ((f + 127) / 128) * gat_stats_stride(heads); }
+
+// ---- slot chain of a multi-item row ----------------------------------------------------------
+// flag[slot] becomes 1 once the state folded over slots [first, slot] is in partials[slot].
+__device__ __forceinline__ void chain_wait(const int32_t* flag) {
+  int32_t v = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v != 0) return;
+    __nanosleep(64);
+  }
+  __trap();      // the predecessor never published: a protocol bug must not hang the GPU
+}
+__device__ __forceinline__ void chain_publish(int32_t* flag) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+// predecessor state was written by another SM during this launch: read it at L2, never from L1
+__device__ __forceinline__ float4 ld_state_f32x4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ld_state_f32(const float* p) { return __ldcg(p); }
+template <int LANES>
+__device__ __forceinline__ uint32_t group_mask(int lane) {
+  if constexpr (LANES == 32) return 0xffffffffu;
+  else return ((1u << LANES) - 1u) << (lane & ~(LANES - 1));
+}
+// Run `body` once per group of the warp, groups in ascending order (one pass when the warp is a single
+// group or no group of it sits in a chain): a predecessor that lives in the SAME warp has then
+// published before its successor waits.
+template <int LANES, typename F>
+__device__ __forceinline__ void for_groups_in_order(int lane, bool chained, F&& body) {
+  if (LANES == 32 || !__any_sync(0xffffffffu, chained)) {
+    body();
+  } else {
+#pragma unroll 1
+    for (int g = 0; g < 32 / LANES; ++g) {
+      if (lane / LANES == g) body();
+      __syncwarp();
+    }
+  }
+}
 
 template <int LANES>
 __device__ __forceinline__ float group_max(float v) {
@@ -77,12 +127,20 @@ __device__ __forceinline__ float4 ld_row_f32x4(const float* p, uint64_t pol_keep
 #endif
   return v;
 }
-// address of a gathered row: base + id * row_bytes as ONE mad.wide.u32 (a 64-bit multiply by the
-// leading dimension costs five integer instructions per edge; profiles/r01_gat_aggregate_v2)
+// address of a gathered row: base + id * row_bytes.  Written as a 64-bit multiply-add of two 32-bit
+// values so ptxas emits ONE IMAD.WIDE.U32 with the lane's base pointer as the addend (the round-1 inline
+// mad.wide.u32 was split into IMAD.WIDE + IADD3 + IADD3.X once the base pair was not register-aligned).
 __device__ __forceinline__ const float* row_ptr(const float* base, uint32_t id, uint32_t row_bytes) {
-  uint64_t r;
-  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(id), "r"(row_bytes), "l"(base));
-  return reinterpret_cast<const float*>(r);
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + uint64_t(id) * row_bytes);
+}
+// exp of a non-positive softmax exponent.  GTA_AGG_FASTEXP=1: ex2.approx path (relative error about
+// 2e-7 + |x| 1e-7; terms that matter have small |x|), two instructions instead of about ten.
+__device__ __forceinline__ float softmax_exp(float x) {
+#if GTA_AGG_FASTEXP
+  return __expf(x);
+#else
+  return expf(x);
+#endif
 }
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
   acc.x = fmaf(w, v.x, acc.x);
@@ -105,13 +163,13 @@ __device__ __forceinline__ float4 epilogue4(float4 a, float scale, int epi) {
 // ----------------------------------------------------------------------------------------
 template <int LANES, int WKIND, bool DIV>
 __global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
-aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
+aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ row_slots,
+                 int64_t num_slots, const int32_t* __restrict__ indices,
                  const float* __restrict__ w, int wh, const float* __restrict__ rowden,
-                 const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo,
-                 int f, int epilogue, float* __restrict__ partials) {
-  __shared__ uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
-  const uint64_t pol_stream = policy_evict_first();
-  const uint64_t pol_keep = policy_evict_last();
+                 const float* __restrict__ x, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
+                 int f, int epilogue, float* partials, int32_t* chain_flags, const uint64_t pol_stream,
+    const uint64_t pol_keep) {
+  __shared__ __align__(16) uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int64_t group = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) / LANES;
@@ -124,9 +182,9 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
   const int32_t* idx_base = indices + it.y;
   uint2* se = s_a[threadIdx.x >> 5];
   const uint2* mine = se + (lane & ~(LANES - 1));
+  const uint4* mine2 = reinterpret_cast<const uint4*>(mine);      // two staged edges per LDS.128
   const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
   const float* xf = x + (active ? fo : 0);
-  const uint32_t row_bytes = uint32_t(ldx) * 4u;
   int head = 0;
   float den = 1.f;
   if (WKIND == 2) head = active ? fo / (f / wh) : 0;
@@ -161,18 +219,22 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
       if (LANES < 32 || active) {
 #pragma unroll 1
         for (int j = 0; j < LANES; j += kUnroll) {
-          uint2 ed[kUnroll];
+          uint4 ed[kUnroll / 2];
           float4 v[kUnroll];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) ed[u] = mine[j + u];
+          for (int u = 0; u < kUnroll / 2; ++u)
+            if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) v[u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
+          for (int u = 0; u < kUnroll / 2; ++u) {
+            if (j + 2 * u < LANES) {
+              v[2 * u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
+              v[2 * u + 1] = ld_row_f32x4(row_ptr(xf, ed[u].z, row_bytes), pol_keep);
+            }
+          }
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
             if (j + u < LANES) {
-              float ws = __uint_as_float(ed[u].y);
+              float ws = __uint_as_float((u & 1) ? ed[u / 2].w : ed[u / 2].y);
               if (WKIND == 2) {
                 ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
                 if (DIV) ws = ws / den;
@@ -212,31 +274,30 @@ aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_
     }
     __syncwarp();
   }
-  if (!active) return;
-  if (it.w < 0) {
-    st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
-  } else {
-    *reinterpret_cast<float4*>(partials + int64_t(it.w) * f + fo) = acc;
-  }
-}
-
-// rows that own several items: sum their partial rows in slot order
-__global__ void __launch_bounds__(kAggThreads)
-aggregate_combine_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, const float* __restrict__ partials,
-                         float* __restrict__ out, int64_t ldo, int f, int epilogue) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
-  if (r >= num_rows) return;
-  const int s0 = row_slots[r], s1 = row_slots[r + 1];
-  if (s1 == s0) return;
-  for (int fo = 4 * lane; fo < f; fo += 128) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = s0; s < s1; ++s) {
-      float4 p = *reinterpret_cast<const float4*>(partials + int64_t(s) * f + fo);
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  const bool chained = have && it.w >= 0;
+  for_groups_in_order<LANES>(lane, chained, [&]() {
+    bool last = true;
+    if (chained) {
+      const int s0 = __ldg(row_slots + it.x), s1 = __ldg(row_slots + it.x + 1);
+      int32_t* flags = chain_flags + int64_t(blockIdx.y) * num_slots;
+      last = it.w == s1 - 1;
+      if (it.w != s0) {
+        if (l == 0) chain_wait(flags + it.w - 1);
+        __syncwarp(group_mask<LANES>(lane));
+        if (active) {
+          const float4 p = ld_state_f32x4(partials + int64_t(it.w - 1) * f + fo);
+          acc.x = p.x + acc.x; acc.y = p.y + acc.y; acc.z = p.z + acc.z; acc.w = p.w + acc.w;
+        }
+      }
+      if (!last) {
+        if (active) *reinterpret_cast<float4*>(partials + int64_t(it.w) * f + fo) = acc;
+        __threadfence();
+        __syncwarp(group_mask<LANES>(lane));
+        if (l == 0) chain_publish(flags + it.w);
+      }
     }
-    *reinterpret_cast<float4*>(out + r * ldo + fo) = epilogue4(acc, 1.f, epilogue);
-  }
+    if (last && active) st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
+  });
 }
 
 // ----------------------------------------------------------------------------------------
@@ -272,15 +333,20 @@ __device__ __forceinline__ float pick(const float (&v)[H], int h) {
 
 template <int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? kAggMinBlocks : (kAggMinBlocks + 1) / 2)
-gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
+gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ row_slots,
+                     int64_t num_slots, const int32_t* __restrict__ indices,
                      const float* __restrict__ el, const float* __restrict__ er, int64_t lder, float slope,
-                     const float* __restrict__ z, int64_t ldz, float* __restrict__ out, int64_t ldo,
+                     const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
                      int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
-                     float* __restrict__ partials) {
-  // per warp: 32 staged edges x H heads, each entry = {source id, softmax numerator}
-  __shared__ uint2 s_e[kAggWarps][32 * H];
-  const uint64_t pol_stream = policy_evict_first();
-  const uint64_t pol_keep = policy_evict_last();
+                     float* partials, int32_t* chain_flags, const uint64_t pol_stream,
+    const uint64_t pol_keep) {
+  // per warp: H rows of 32 staged edges, entry = {source id, softmax numerator}.  Row pitch kS = 34
+  // entries: a lane's STS.64 lands beside its neighbour's (2 wavefronts per head, no conflicts) and the
+  // LDS.128 of the gather loop -- two consecutive edges of one head, the 4 heads of a warp at once --
+  // hits 4 disjoint bank quads (68 words = 4 mod 32).  Round 1 staged [edge][head]: 4-way conflicts on
+  // every store, 27 % of the L1/TEX data-pipe wavefronts of the kernel.
+  constexpr int kS = 34;
+  __shared__ __align__(16) uint2 s_e[kAggWarps][H * kS];
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int gbase = lane & ~(LANES - 1);          // first lane of my group inside the warp
@@ -294,9 +360,9 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   const int32_t* idx_base = indices + it.y;
   const int head = active ? fo / (f / H) : 0;
   const float* zf = z + (active ? fo : 0);
-  const uint32_t row_bytes = uint32_t(ldz) * 4u;
   uint2* se = s_e[threadIdx.x >> 5];
-  const uint2* mine = se + gbase * H + head;
+  const uint2* mine = se + head * kS + gbase;
+  const uint4* mine2 = reinterpret_cast<const uint4*>(mine);
 
   float elr[H], m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
   if (have) load_heads<H>(el + int64_t(it.x) * H, elr);
@@ -332,12 +398,12 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
     for (int h = 0; h < H; ++h) {
       const float mn = fmaxf(m[h], group_max<LANES>(e[h]));
       // mn stays -inf only while this group has seen no edge (another group in the warp is running)
-      const float sc = (mn == -INFINITY) ? 1.f : expf(m[h] - mn);
-      const float p = (l < n) ? expf(e[h] - mn) : 0.f;
+      const float sc = (mn == -INFINITY) ? 1.f : softmax_exp(m[h] - mn);
+      const float p = (l < n) ? softmax_exp(e[h] - mn) : 0.f;
       s[h] = fmaf(s[h], sc, p);
       m[h] = mn;
       my_scale = (h == head) ? sc : my_scale;
-      se[lane * H + h] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
+      se[h * kS + lane] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
     }
     acc.x *= my_scale; acc.y *= my_scale; acc.z *= my_scale; acc.w *= my_scale;
     __syncwarp();
@@ -346,17 +412,25 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
       if (LANES < 32 || active) {
 #pragma unroll 1
         for (int j = 0; j < LANES; j += kUnroll) {
-          uint2 ed[kUnroll];
+          uint4 ed[kUnroll / 2];
           float4 v[kUnroll];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) ed[u] = mine[(j + u) * H];
+          for (int u = 0; u < kUnroll / 2; ++u)
+            if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) v[u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
+          for (int u = 0; u < kUnroll / 2; ++u) {
+            if (j + 2 * u < LANES) {
+              v[2 * u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
+              v[2 * u + 1] = ld_row_f32x4(row_ptr(zf, ed[u].z, row_bytes), pol_keep);
+            }
+          }
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
-            if (j + u < LANES) fma4(acc, __uint_as_float(ed[u].y), v[u]);
+          for (int u = 0; u < kUnroll / 2; ++u) {
+            if (j + 2 * u < LANES) {
+              fma4(acc, __uint_as_float(ed[u].y), v[2 * u]);
+              fma4(acc, __uint_as_float(ed[u].w), v[2 * u + 1]);
+            }
+          }
         }
       }
     } else {
@@ -367,7 +441,7 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           if (j + u < LANES) {
-            const uint2 ed = mine[(j + u) * H];
+            const uint2 ed = mine[j + u];
             pv[u] = __uint_as_float(ed.y);
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, ed.x, row_bytes), pol_keep);
@@ -382,74 +456,62 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   }
 #pragma unroll
   for (int h = 0; h < H; ++h) s[h] = group_sum<LANES>(s[h]);
-  if (!have) return;
-  if (it.w < 0) {
-    if (active) {
-      const float sh = pick<H>(s, head);
-      st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue));
-    }
-    if (blockIdx.y == 0 && l < H) {
-      if (rowmax) rowmax[int64_t(it.x) * H + l] = (count > 0) ? pick<H>(m, l) : 0.f;
-      if (rowsum) rowsum[int64_t(it.x) * H + l] = pick<H>(s, l);
-    }
-  } else {
-    float* part = partials + int64_t(it.w) * gat_partial_stride(f, H);
-    if (active) *reinterpret_cast<float4*>(part + fo) = acc;
-    if (blockIdx.y == 0 && l < H) {
-      part[f + l] = pick<H>(m, l);
-      part[f + H + l] = pick<H>(s, l);
-    }
-  }
-}
-
-// merge the (max, sum, acc) triples of a row in slot order
-template <int H>
-__global__ void __launch_bounds__(kAggThreads)
-gat_combine_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, const float* __restrict__ partials,
-                   float* __restrict__ out, int64_t ldo, int f, int epilogue,
-                   float* __restrict__ rowmax, float* __restrict__ rowsum) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
-  if (r >= num_rows) return;
-  const int s0 = row_slots[r], s1 = row_slots[r + 1];
-  if (s1 == s0) return;
-  const int stride = gat_partial_stride(f, H);
-  const int d = f / H;
-  // pass 1: global max and rescaled sum per head (every lane redundantly, H is small)
-  float gm[H], gs[H];
+  const bool chained = have && it.w >= 0;
+  for_groups_in_order<LANES>(lane, chained, [&]() {
+    bool last = true;
+    if (chained) {
+      const int s0 = __ldg(row_slots + it.x), s1 = __ldg(row_slots + it.x + 1);
+      int32_t* flags = chain_flags + int64_t(blockIdx.y) * num_slots;
+      const int pstride = gat_partial_stride(f, H);
+      const int stats = f + int(blockIdx.y) * gat_stats_stride(H);
+      last = it.w == s1 - 1;
+      if (it.w != s0) {
+        // fold the state of slots [s0, it.w) in: (max, sum, acc) triples merge like the online softmax itself
+        if (l == 0) chain_wait(flags + it.w - 1);
+        __syncwarp(group_mask<LANES>(lane));
+        const float* prev = partials + int64_t(it.w - 1) * pstride;
+        float a_mine = 1.f, b_mine = 1.f;
 #pragma unroll
-  for (int h = 0; h < H; ++h) { gm[h] = -INFINITY; gs[h] = 0.f; }
-  for (int c = s0; c < s1; ++c) {
-    const float* part = partials + int64_t(c) * stride;
-#pragma unroll
-    for (int h = 0; h < H; ++h) gm[h] = fmaxf(gm[h], part[f + h]);
-  }
-  for (int c = s0; c < s1; ++c) {
-    const float* part = partials + int64_t(c) * stride;
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const float mc = part[f + h];
-      gs[h] += (mc == -INFINITY) ? 0.f : part[f + H + h] * expf(mc - gm[h]);
+        for (int h = 0; h < H; ++h) {
+          const float pm = ld_state_f32(prev + stats + h), ps = ld_state_f32(prev + stats + H + h);
+          const float mn = fmaxf(pm, m[h]);
+          const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
+          const float b = (m[h] == -INFINITY) ? 0.f : expf(m[h] - mn);
+          s[h] = fmaf(ps, a, s[h] * b);
+          m[h] = mn;
+          a_mine = (h == head) ? a : a_mine;
+          b_mine = (h == head) ? b : b_mine;
+        }
+        if (active) {
+          const float4 p = ld_state_f32x4(prev + fo);
+          acc.x = fmaf(p.x, a_mine, acc.x * b_mine); acc.y = fmaf(p.y, a_mine, acc.y * b_mine);
+          acc.z = fmaf(p.z, a_mine, acc.z * b_mine); acc.w = fmaf(p.w, a_mine, acc.w * b_mine);
+        }
+      }
+      if (!last) {
+        float* part = partials + int64_t(it.w) * pstride;
+        if (active) *reinterpret_cast<float4*>(part + fo) = acc;
+        if (l < H) {
+          part[stats + l] = pick<H>(m, l);
+          part[stats + H + l] = pick<H>(s, l);
+        }
+        __threadfence();
+        __syncwarp(group_mask<LANES>(lane));
+        if (l == 0) chain_publish(flags + it.w);
+      }
     }
-  }
-  for (int fo = 4 * lane; fo < f; fo += 128) {
-    const int head = fo / d;
-    const float mh = pick<H>(gm, head);
-    const float sh = pick<H>(gs, head);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = s0; c < s1; ++c) {
-      const float* part = partials + int64_t(c) * stride;
-      const float mc = part[f + head];
-      if (mc == -INFINITY) continue;          // an item without edges contributes nothing
-      fma4(acc, expf(mc - mh), *reinterpret_cast<const float4*>(part + fo));
+    if (last && have) {
+      if (active) {
+        const float sh = pick<H>(s, head);
+        st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue));
+      }
+      if (blockIdx.y == 0 && l < H) {
+        const float ml = pick<H>(m, l);
+        if (rowmax) rowmax[int64_t(it.x) * H + l] = (ml == -INFINITY) ? 0.f : ml;
+        if (rowsum) rowsum[int64_t(it.x) * H + l] = pick<H>(s, l);
+      }
     }
-    *reinterpret_cast<float4*>(out + r * ldo + fo) = epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue);
-  }
-  if (lane < H) {
-    const float mh = pick<H>(gm, lane);
-    if (rowmax) rowmax[r * H + lane] = (mh == -INFINITY) ? 0.f : mh;
-    if (rowsum) rowsum[r * H + lane] = pick<H>(gs, lane);
-  }
+  });
 }
 
 // ----------------------------------------------------------------------------------------
@@ -464,14 +526,14 @@ gat_combine_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, cons
 // ----------------------------------------------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
-gat_aggregate_llh_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ indices,
+gat_aggregate_llh_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ row_slots,
+                         int64_t num_slots, const int32_t* __restrict__ indices,
                          const float* __restrict__ el, const float* __restrict__ er, int64_t lder, int heads,
-                         float slope, const float* __restrict__ z, int64_t ldz, float* __restrict__ out,
+                         float slope, const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out,
                          int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
-                         float* __restrict__ rowsum, float* __restrict__ partials) {
+                         float* __restrict__ rowsum, float* partials, int32_t* chain_flags, const uint64_t pol_stream,
+    const uint64_t pol_keep) {
   __shared__ uint32_t s_id[kAggWarps][32];
-  const uint64_t pol_stream = policy_evict_first();
-  const uint64_t pol_keep = policy_evict_last();
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int64_t group = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) / LANES;
@@ -486,7 +548,6 @@ gat_aggregate_llh_kernel(const int4* __restrict__ items, int64_t num_items, cons
   const int head = active ? fo / d : 0;
   const float* zf = z + (active ? fo : 0);
   const float* erh = er + head;
-  const uint32_t row_bytes = uint32_t(ldz) * 4u;
   const uint32_t er_bytes = uint32_t(lder) * 4u;
   uint32_t* sid = s_id[threadIdx.x >> 5];
   const uint32_t* mine = sid + (lane & ~(LANES - 1));
@@ -541,56 +602,52 @@ gat_aggregate_llh_kernel(const int4* __restrict__ items, int64_t num_items, cons
     }
     __syncwarp();
   }
-  if (!active) return;
-  const bool head_leader = (fo % d) == 0;       // one lane per head publishes the statistics
-  if (it.w < 0) {
-    st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, s > 0.f ? 1.f / s : 0.f, epilogue));
-    if (head_leader) {
-      if (rowmax) rowmax[int64_t(it.x) * heads + head] = (count > 0) ? m : 0.f;
-      if (rowsum) rowsum[int64_t(it.x) * heads + head] = s;
+  const bool head_leader = active && (fo % d) == 0;       // one lane per head publishes the statistics
+  const bool chained = have && it.w >= 0;
+  for_groups_in_order<LANES>(lane, chained, [&]() {
+    bool last = true;
+    if (chained) {
+      const int s0 = __ldg(row_slots + it.x), s1 = __ldg(row_slots + it.x + 1);
+      int32_t* flags = chain_flags + int64_t(blockIdx.y) * num_slots;
+      const int pstride = gat_partial_stride(f, heads);
+      const int stats = f + int(blockIdx.y) * gat_stats_stride(heads);
+      last = it.w == s1 - 1;
+      if (it.w != s0) {
+        if (l == 0) chain_wait(flags + it.w - 1);
+        __syncwarp(group_mask<LANES>(lane));
+        if (active) {
+          const float* prev = partials + int64_t(it.w - 1) * pstride;
+          const float pm = ld_state_f32(prev + stats + head), ps = ld_state_f32(prev + stats + heads + head);
+          const float mn = fmaxf(pm, m);
+          const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
+          const float b = (m == -INFINITY) ? 0.f : expf(m - mn);
+          const float4 p = ld_state_f32x4(prev + fo);
+          s = fmaf(ps, a, s * b);
+          m = mn;
+          acc.x = fmaf(p.x, a, acc.x * b); acc.y = fmaf(p.y, a, acc.y * b);
+          acc.z = fmaf(p.z, a, acc.z * b); acc.w = fmaf(p.w, a, acc.w * b);
+        }
+      }
+      if (!last) {
+        float* part = partials + int64_t(it.w) * pstride;
+        if (active) *reinterpret_cast<float4*>(part + fo) = acc;
+        if (head_leader) {
+          part[stats + head] = m;
+          part[stats + heads + head] = s;
+        }
+        __threadfence();
+        __syncwarp(group_mask<LANES>(lane));
+        if (l == 0) chain_publish(flags + it.w);
+      }
     }
-  } else {
-    float* part = partials + int64_t(it.w) * gat_partial_stride(f, heads);
-    *reinterpret_cast<float4*>(part + fo) = acc;
-    if (head_leader) {
-      part[f + head] = m;
-      part[f + heads + head] = s;
+    if (last && active) {
+      st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, s > 0.f ? 1.f / s : 0.f, epilogue));
+      if (head_leader) {
+        if (rowmax) rowmax[int64_t(it.x) * heads + head] = (m == -INFINITY) ? 0.f : m;
+        if (rowsum) rowsum[int64_t(it.x) * heads + head] = s;
+      }
     }
-  }
-}
-
-// merge of the (max, sum, acc) triples for any H: every lane handles the head of its own columns
-__global__ void __launch_bounds__(kAggThreads)
-gat_combine_llh_kernel(const int32_t* __restrict__ row_slots, int64_t num_rows, const float* __restrict__ partials,
-                       float* __restrict__ out, int64_t ldo, int f, int heads, int epilogue,
-                       float* __restrict__ rowmax, float* __restrict__ rowsum) {
-  const int lane = threadIdx.x & 31;
-  const int64_t r = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) >> 5;
-  if (r >= num_rows) return;
-  const int s0 = row_slots[r], s1 = row_slots[r + 1];
-  if (s1 == s0) return;
-  const int stride = gat_partial_stride(f, heads);
-  const int d = f / heads;
-  for (int fo = 4 * lane; fo < f; fo += 128) {
-    const int head = fo / d;
-    float gm = -INFINITY;
-    for (int c = s0; c < s1; ++c) gm = fmaxf(gm, partials[int64_t(c) * stride + f + head]);
-    float gs = 0.f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = s0; c < s1; ++c) {
-      const float* part = partials + int64_t(c) * stride;
-      const float mc = part[f + head];
-      if (mc == -INFINITY) continue;
-      const float sc = expf(mc - gm);
-      gs = fmaf(part[f + heads + head], sc, gs);
-      fma4(acc, sc, *reinterpret_cast<const float4*>(part + fo));
-    }
-    *reinterpret_cast<float4*>(out + r * ldo + fo) = epilogue4(acc, gs > 0.f ? 1.f / gs : 0.f, epilogue);
-    if ((fo % d) == 0) {
-      if (rowmax) rowmax[r * heads + head] = (gm == -INFINITY) ? 0.f : gm;
-      if (rowsum) rowsum[r * heads + head] = gs;
-    }
-  }
+  });
 }
 
 // ----------------------------------------------------------------------------------------
@@ -637,12 +694,25 @@ static int lanes_for(int f) {
   return l < 4 ? 4 : l;
 }
 
+// the work list and the chain state every aggregation launch takes
+struct WorkList {
+  const int4* items;
+  int64_t num_items;
+  const int32_t* row_slots;
+  int64_t num_slots;
+  const int32_t* indices;
+  float* partials;
+  int32_t* chain_flags;
+};
+
 template <int LANES>
-static void dispatch_aggregate(int wkind, bool div, dim3 grid, cudaStream_t st, const int4* items, int64_t num_items,
-                               const int32_t* indices, const float* w, int wh, const float* rowden, const float* x,
-                               int64_t ldx, float* out, int64_t ldo, int f, int epi, float* partials) {
-#define GTA_AGG(K, D) \
-  aggregate_kernel<LANES, K, D><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epi, partials)
+static void dispatch_aggregate(const CachePolicies& pol, int wkind, bool div, dim3 grid, cudaStream_t st, const WorkList& wl, const float* w,
+                               int wh, const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo,
+                               int f, int epi) {
+#define GTA_AGG(K, D)                                                                                             \
+  aggregate_kernel<LANES, K, D><<<grid, kAggThreads, 0, st>>>(wl.items, wl.num_items, wl.row_slots, wl.num_slots, \
+                                                              wl.indices, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi, \
+                                                              wl.partials, wl.chain_flags, pol.stream, pol.keep)
   if (wkind == 0) GTA_AGG(0, false);
   else if (wkind == 1 && !div) GTA_AGG(1, false);
   else if (wkind == 1 && div) GTA_AGG(1, true);
@@ -652,12 +722,13 @@ static void dispatch_aggregate(int wkind, bool div, dim3 grid, cudaStream_t st, 
 }
 
 template <int H>
-static int dispatch_gat(int lanes, dim3 grid, cudaStream_t st, const int4* items, int64_t num_items,
-                        const int32_t* indices, const float* el, const float* er, int64_t lder, float slope,
-                        const float* z, int64_t ldz, float* out, int64_t ldo, int f, int epi, float* rowmax,
-                        float* rowsum, float* partials) {
-#define GTA_GAT(L) \
-  gat_aggregate_kernel<L, H><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, lder, slope, z, ldz, out, ldo, f, epi, rowmax, rowsum, partials)
+static int dispatch_gat(const CachePolicies& pol, int lanes, dim3 grid, cudaStream_t st, const WorkList& wl, const float* el, const float* er,
+                        int64_t lder, float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int f, int epi,
+                        float* rowmax, float* rowsum) {
+#define GTA_GAT(L)                                                                                                 \
+  gat_aggregate_kernel<L, H><<<grid, kAggThreads, 0, st>>>(wl.items, wl.num_items, wl.row_slots, wl.num_slots,     \
+                                                           wl.indices, el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi, \
+                                                           rowmax, rowsum, wl.partials, wl.chain_flags, pol.stream, pol.keep)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
     case 8: if (H <= 8) { GTA_GAT(8); return GTA_OK; } break;
@@ -668,6 +739,18 @@ static int dispatch_gat(int lanes, dim3 grid, cudaStream_t st, const int4* items
   return GTA_ERR_UNSUPPORTED;
 }
 
+// common argument checks + the RESET phase (clear the chain flags of every feature window)
+static int prepare_worklist(const char* who, WorkList& wl, int32_t f, int32_t phases, cudaStream_t st) {
+  GTA_REQUIRE(wl.num_slots == 0 || (wl.partials && wl.row_slots && wl.chain_flags),
+              "%s: partials, row_slots and chain_flags are required for %lld slots", who, (long long)wl.num_slots);
+  if ((phases & GTA_PHASE_RESET) && wl.num_slots > 0) {
+    const size_t windows = size_t((f + 127) / 128);
+    GTA_CUDA(cudaMemsetAsync(wl.chain_flags, 0, windows * size_t(wl.num_slots) * sizeof(int32_t), st));
+    count_launch();
+  }
+  return GTA_OK;
+}
+
 }  // namespace gta
 
 using namespace gta;
@@ -676,18 +759,20 @@ extern "C" {
 
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads) { return gat_partial_stride(f, heads); }
 
-int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_rows,
-                      int64_t num_slots, const int32_t* indices, int32_t wmode, const float* w, int32_t wh,
-                      const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
-                      int32_t epilogue, float* partials, int32_t phases, void* stream_) {
+int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+                      const int32_t* indices, int32_t wmode, const float* w, int32_t wh, const float* rowden,
+                      const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f, int32_t epilogue,
+                      float* partials, int32_t* chain_flags, int32_t phases, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (num_items == 0 && !(phases & GTA_PHASE_COMBINE)) return GTA_OK;
-  GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, chain_flags};
+  int rc = prepare_worklist("gta_aggregate_f32", wl, f, phases, st);
+  if (rc != GTA_OK) return rc;
+  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
+  GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
   GTA_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f && ldx < (int64_t(1) << 30), "gta_aggregate_f32: leading dimensions must be multiples of 4, >= f and < 2^30");
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gta_aggregate_f32: tables must be 16-byte aligned");
   GTA_REQUIRE(wmode >= GTA_W_NONE && wmode <= GTA_W_EDGE_DIV, "gta_aggregate_f32: bad wmode %d", wmode);
-  GTA_REQUIRE(num_slots == 0 || (partials && row_slots), "gta_aggregate_f32: partials and row_slots required for %lld slots", (long long)num_slots);
   int wkind = 0;
   bool div = wmode == GTA_W_EDGE_DIV;
   if (wmode != GTA_W_NONE) {
@@ -699,37 +784,34 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
       return GTA_ERR_UNSUPPORTED;
     }
   }
-  const int4* items = reinterpret_cast<const int4*>(items_);
+  CachePolicies pol;
+  rc = cache_policies(&pol);
+  if (rc != GTA_OK) return rc;
   int lanes = lanes_for(f);
   int64_t threads = num_items * lanes;
   dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
-  if ((phases & GTA_PHASE_MAIN) && num_items > 0) {
   switch (lanes) {
-    case 4: dispatch_aggregate<4>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
-    case 8: dispatch_aggregate<8>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
-    case 16: dispatch_aggregate<16>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
-    default: dispatch_aggregate<32>(wkind, div, grid, st, items, num_items, indices, w, wh, rowden, x, ldx, out, ldo, f, epilogue, partials); break;
+    case 4: dispatch_aggregate<4>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 8: dispatch_aggregate<8>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 16: dispatch_aggregate<16>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    default: dispatch_aggregate<32>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
   }
   GTA_CHECK_LAUNCH("aggregate_kernel");
-  }
-  if ((phases & GTA_PHASE_COMBINE) && num_slots > 0) {
-    int64_t cthreads = num_rows * 32;
-    aggregate_combine_kernel<<<(unsigned)((cthreads + kAggThreads - 1) / kAggThreads), kAggThreads, 0, st>>>(
-        row_slots, num_rows, partials, out, ldo, f, epilogue);
-    GTA_CHECK_LAUNCH("aggregate_combine_kernel");
-  }
   return GTA_OK;
 }
 
-int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_rows,
-                          int64_t num_slots, const int32_t* indices, const float* el, const float* er, int64_t lder,
-                          int32_t heads, float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
-                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t phases,
-                          void* stream_) {
+int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+                          const int32_t* indices, const float* el, const float* er, int64_t lder, int32_t heads,
+                          float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_flags,
+                          int32_t phases, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (num_items == 0 && !(phases & GTA_PHASE_COMBINE)) return GTA_OK;
-  GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, chain_flags};
+  int rc = prepare_worklist("gta_gat_aggregate_f32", wl, f, phases, st);
+  if (rc != GTA_OK) return rc;
+  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
+  GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
   GTA_REQUIRE(ldz % 4 == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f && ldz < (int64_t(1) << 30), "gta_gat_aggregate_f32: leading dimensions must be multiples of 4, >= f and < 2^30");
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
@@ -737,61 +819,46 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   GTA_REQUIRE(heads >= 1 && f % heads == 0, "gta_gat_aggregate_f32: heads=%d must divide f=%d", heads, f);
   GTA_REQUIRE(lder >= heads && (heads % 4 != 0 || lder % 4 == 0) && (heads % 2 != 0 || lder % 2 == 0),
               "gta_gat_aggregate_f32: er row stride %lld breaks the vector alignment of %d heads", (long long)lder, heads);
-  GTA_REQUIRE(num_slots == 0 || (partials && row_slots), "gta_gat_aggregate_f32: partials and row_slots required for %lld slots", (long long)num_slots);
   if ((f / heads) % 4 != 0) {
     set_error("gta_gat_aggregate_f32: per-head width f/heads=%d is not a multiple of 4", f / heads);
     return GTA_ERR_UNSUPPORTED;
   }
-  const int4* items = reinterpret_cast<const int4*>(items_);
+  CachePolicies pol;
+  rc = cache_policies(&pol);
+  if (rc != GTA_OK) return rc;
   int lanes = lanes_for(f);
   int64_t threads = num_items * lanes;
   dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
   // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
   // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint)
   const bool staged = heads == 1 || heads == 2 || heads == 4;
-  if ((phases & GTA_PHASE_MAIN) && num_items > 0) {
-    if (staged) {
-      int rc = GTA_ERR_UNSUPPORTED;
-#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, grid, st, items, num_items, indices, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials)
-      switch (heads) {
-        case 1: GTA_GAT_H(1); break;
-        case 2: GTA_GAT_H(2); break;
-        default: GTA_GAT_H(4); break;
-      }
+  if (staged) {
+    rc = GTA_ERR_UNSUPPORTED;
+#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(pol, lanes, grid, st, wl, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum)
+    switch (heads) {
+      case 1: GTA_GAT_H(1); break;
+      case 2: GTA_GAT_H(2); break;
+      default: GTA_GAT_H(4); break;
+    }
 #undef GTA_GAT_H
-      if (rc != GTA_OK) {
-        set_error("gta_gat_aggregate_f32: no kernel for heads=%d, f=%d", heads, f);
-        return rc;
-      }
-    } else {
-#define GTA_LLH(L) gat_aggregate_llh_kernel<L><<<grid, kAggThreads, 0, st>>>(items, num_items, indices, el, er, lder, heads, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials)
-      switch (lanes) {
-        case 4: GTA_LLH(4); break;
-        case 8: GTA_LLH(8); break;
-        case 16: GTA_LLH(16); break;
-        default: GTA_LLH(32); break;
-      }
+    if (rc != GTA_OK) {
+      set_error("gta_gat_aggregate_f32: no kernel for heads=%d, f=%d", heads, f);
+      return rc;
+    }
+  } else {
+#define GTA_LLH(L)                                                                                                   \
+  gat_aggregate_llh_kernel<L><<<grid, kAggThreads, 0, st>>>(wl.items, wl.num_items, wl.row_slots, wl.num_slots,      \
+                                                            wl.indices, el, er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, \
+                                                            f, epilogue, rowmax, rowsum, wl.partials, wl.chain_flags, pol.stream, pol.keep)
+    switch (lanes) {
+      case 4: GTA_LLH(4); break;
+      case 8: GTA_LLH(8); break;
+      case 16: GTA_LLH(16); break;
+      default: GTA_LLH(32); break;
+    }
 #undef GTA_LLH
-    }
-    GTA_CHECK_LAUNCH("gat_aggregate_kernel");
   }
-  if ((phases & GTA_PHASE_COMBINE) && num_slots > 0) {
-    int64_t cthreads = num_rows * 32;
-    unsigned cgrid = (unsigned)((cthreads + kAggThreads - 1) / kAggThreads);
-    if (staged) {
-#define GTA_COMB(HH) gat_combine_kernel<HH><<<cgrid, kAggThreads, 0, st>>>(row_slots, num_rows, partials, out, ldo, f, epilogue, rowmax, rowsum)
-      switch (heads) {
-        case 1: GTA_COMB(1); break;
-        case 2: GTA_COMB(2); break;
-        default: GTA_COMB(4); break;
-      }
-#undef GTA_COMB
-    } else {
-      gat_combine_llh_kernel<<<cgrid, kAggThreads, 0, st>>>(row_slots, num_rows, partials, out, ldo, f, heads, epilogue,
-                                                            rowmax, rowsum);
-    }
-    GTA_CHECK_LAUNCH("gat_combine_kernel");
-  }
+  GTA_CHECK_LAUNCH("gat_aggregate_kernel");
   return GTA_OK;
 }
 

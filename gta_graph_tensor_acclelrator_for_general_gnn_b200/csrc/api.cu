@@ -1,5 +1,6 @@
 // Error string, ABI version and launch counter of libgta_b200.so.
 #include <atomic>
+#include <mutex>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -17,6 +18,34 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+__global__ void cache_policy_kernel(uint64_t* out) {
+  out[0] = policy_evict_first();
+  out[1] = policy_evict_last();
+}
+
+// createpolicy's encoding is opaque, so it is asked of the device once (first aggregation call of the
+// process; synchronises, hence outside any stream capture) instead of being hard-coded.
+int cache_policies(CachePolicies* out) {
+  static std::mutex mu;
+  static bool ready = false;
+  static CachePolicies cached{};
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ready) {
+    uint64_t* d = nullptr;
+    uint64_t h[2] = {0, 0};
+    GTA_CUDA(cudaMalloc(&d, sizeof(h)));
+    cache_policy_kernel<<<1, 1>>>(d);
+    cudaError_t e = cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    GTA_CUDA(e);
+    cached.stream = h[0];
+    cached.keep = h[1];
+    ready = true;
+  }
+  *out = cached;
+  return GTA_OK;
+}
 
 }  // namespace gta
 

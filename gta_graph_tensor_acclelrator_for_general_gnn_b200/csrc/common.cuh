@@ -59,6 +59,16 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// The same 64-bit policy words, fetched once per process (a one-thread kernel runs createpolicy) and then
+// handed to the gather kernels as KERNEL PARAMETERS: a parameter lives in the constant bank, so the
+// cache-hint descriptor of every load sits in a uniform register (a per-thread createpolicy result costs
+// two R2UR per load; profiles/r01_gat_aggregate_v2: 16 of 85 instructions per 8 edges).
+struct CachePolicies {
+  uint64_t stream;   // L2 evict_first: CSR indices, edge weights
+  uint64_t keep;     // L2 evict_last: gathered source rows
+};
+int cache_policies(CachePolicies* out);
+
 // streamed once (CSR indices, edge weights): do not pollute L1, evict first from L2 so the
 // gathered feature table stays resident in the 126 MB L2.
 __device__ __forceinline__ int ld_stream_i32(const int* p, uint64_t pol) {

@@ -68,22 +68,45 @@ def _ld(t: torch.Tensor) -> int:
 
 
 class _Workspace:
-    """Grow-only scratch buffer (fp32 elements) reused across calls on one device."""
+    """Scratch buffer (fp32 elements) per (device, stream), grown by replacement.
+
+    A buffer that has been handed out is never freed: a CUDA graph captured earlier keeps the device
+    pointer it saw (the chain state of the aggregation kernels, the hi/lo split of W), so a later,
+    larger request must not return that memory to the caching allocator.  Keying by stream keeps
+    concurrent ``execute()`` calls on different streams (pipeline.HostPipeline) off each other's
+    chain state; calls on one stream are ordered and may share."""
 
     def __init__(self):
-        self.buf = None
+        self.live = {}
+        self.retired = []
 
     def get(self, n: int, device):
         if n == 0:
             return None
         device = torch.device(device)
-        if self.buf is None or self.buf.numel() < n or self.buf.device != device:
-            self.buf = torch.empty(n, dtype=torch.float32, device=device)
-        return self.buf
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        buf = self.live.get(key)
+        if buf is None or buf.numel() < n:
+            if buf is not None:
+                self.retired.append(buf)
+            buf = torch.empty(n, dtype=torch.float32, device=device)
+            self.live[key] = buf
+        return buf
 
 
 _gemm_ws = _Workspace()
-_agg_ws = _Workspace()      # partial slots of gta_aggregate_f32
+_agg_ws = _Workspace()      # chain state (partials + flags) of gta_aggregate_f32
+
+
+def _chain_state(ws: _Workspace, num_slots: int, stride: int, f: int, device):
+    """(partials, flags) pointers inside one workspace: num_slots*stride floats, then one int32 flag per
+    slot and 128-feature window."""
+    if num_slots == 0:
+        return None, None
+    windows = (f + 127) // 128
+    base = (num_slots * stride + 3) // 4 * 4
+    buf = ws.get(base + num_slots * windows, device)
+    return buf.data_ptr(), buf.data_ptr() + 4 * base
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -130,8 +153,8 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
 
 
 def _launch_blocks(launch, sched: Schedule, block_events):
-    """One launch for everything, or -- when the gathered table arrives chunk by chunk -- one launch
-    per column block gated on that chunk's event, then the merge of multi-item rows."""
+    """One launch for everything, or -- when the gathered table arrives chunk by chunk -- the first column
+    block as soon as its chunk has landed and the rest after the last event."""
     if block_events is None:
         launch(0, sched.num_items, _cabi.PHASE_ALL)
         return
@@ -140,20 +163,19 @@ def _launch_blocks(launch, sched: Schedule, block_events):
     # Two launches, not one per block: column block 0 starts as soon as its chunk has landed and
     # hides the transfer of all later chunks; the rest runs as ONE launch after the last event
     # (every extra launch boundary drains the SMs: measured 0.1 ms per boundary on the Reddit shape).
+    # Chains of multi-item rows cross the boundary: the flags are cleared once, before the first launch.
     stream = torch.cuda.current_stream()
     nb = sched.num_blocks
     if block_events[0] is not None:
         stream.wait_event(block_events[0])
     first, last = sched.block_begin[0], sched.block_begin[1]
-    if last > first:
-        launch(first, last - first, _cabi.PHASE_MAIN)
+    launch(first, last - first, _cabi.PHASE_ALL)
     if nb > 1:
         if block_events[nb - 1] is not None:
             stream.wait_event(block_events[nb - 1])      # chunks complete in order on the communication stream
         first, last = sched.block_begin[1], sched.block_begin[nb]
         if last > first:
             launch(first, last - first, _cabi.PHASE_MAIN)
-    launch(0, 0, _cabi.PHASE_COMBINE)
 
 
 @_timed("gta_aggregate_f32")
@@ -180,18 +202,18 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
         wmode = _cabi.W_EDGE_DIV if rowden is not None else _cabi.W_EDGE
         if rowden is not None:
             rowden = rowden.contiguous()
-    partials = _agg_ws.get(sched.num_slots * f, x.device)
+    partials, flags = _chain_state(_agg_ws, sched.num_slots, f, f, x.device)
 
     def launch(first, count, phases):
-        _cabi.check(lib.gta_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots), rows,
+        _cabi.check(lib.gta_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
                                           sched.num_slots, _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh,
                                           _cabi.ptr(rowden), _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
-                                          _cabi.ptr(partials), phases, _stream()), "gta_aggregate_f32")
+                                          partials, flags, phases, _stream()), "gta_aggregate_f32")
     _launch_blocks(launch, sched, block_events)
     return o
 
 
-_gat_ws = _Workspace()      # partial slots of the single-pass GAT kernel
+_gat_ws = _Workspace()      # chain state of the single-pass GAT kernel
 
 
 @_timed("gta_gat_aggregate_f32")
@@ -215,13 +237,14 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
         rowmax = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
         rowsum = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
     stride = int(lib.gta_gat_partial_stride(f, heads))
-    partials = _gat_ws.get(sched.num_slots * stride, z.device)
+    partials, flags = _chain_state(_gat_ws, sched.num_slots, stride, f, z.device)
+
     def launch(first, count, phases):
         _cabi.check(lib.gta_gat_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
-                                              rows, sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el),
+                                              sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el),
                                               _cabi.ptr(er), lder, heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o),
                                               _ld(o), f, epilogue, _cabi.ptr(rowmax), _cabi.ptr(rowsum),
-                                              _cabi.ptr(partials), phases, _stream()), "gta_gat_aggregate_f32")
+                                              partials, flags, phases, _stream()), "gta_gat_aggregate_f32")
     _launch_blocks(launch, sched, block_events)
     if want_stats:
         return o, rowmax, rowsum

@@ -43,11 +43,12 @@ extern "C" {
 #define GTA_EPI_ELU 1
 #define GTA_EPI_RELU 2
 
-/* which part of an aggregation call runs: the item kernel, the merge of multi-item rows, or both.
- * Callers that overlap a chunked all-gather launch MAIN once per column block (items of that block
- * only, see h_block_begin) and COMBINE once at the end. */
+/* which part of an aggregation call runs.  RESET clears the chain flags of multi-item rows and must run
+ * once before the first MAIN launch of a pass; MAIN launches the item kernel over the items handed in.
+ * Callers that start a column block as soon as its part of the source table has landed launch
+ * RESET|MAIN for the first block's items and MAIN alone for the rest (see h_block_begin). */
 #define GTA_PHASE_MAIN 1
-#define GTA_PHASE_COMBINE 2
+#define GTA_PHASE_RESET 2
 #define GTA_PHASE_ALL 3
 
 /* how the per-edge weight of gta_aggregate_f32 is formed */
@@ -127,7 +128,8 @@ int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm,
  * from one L2-sized slice of the source table; this is the B200 form of the reference's
  * TR x TC tile walk (interpreter.py:85-106; simulator.py:262-263,292).
  *   items     int32[4] per item = {row - row_begin, edge_begin, edge_count, partial slot | -1}
- *   row_slots int32[rows+1]: slots of row r are [row_slots[r], row_slots[r+1]) (empty if 1 item)
+ *   row_slots int32[rows+1]: slots of row r are [row_slots[r], row_slots[r+1]) (empty if 1 item);
+ *             the items of a row carry consecutive slots in work-list order (the fold order)
  * h_counts[0] = number of items, h_counts[1] = number of partial slots; h_block_begin[cb] = first
  * item of column block cb, h_block_begin[n_cb] = number of items (host arrays, after a sync;
  * n_cb = gta_schedule_col_blocks(num_sources, col_block)). */
@@ -166,14 +168,17 @@ int gta_gemm_get_mode(void);
  * interpreter.py:575-638) and plain COMP_ADD gather (interpreter.py:85-106):
  *   out[i,:] = epi( sum_{k in row i, ascending src} weight(k) (x) x[src(k),:] )
  * `w` is [E,wh] (wh = 1 scalar per edge, or wh = heads, head h covering f/wh features);
- * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Work comes from gta_schedule_build; `partials`
- * holds num_slots*f floats for rows that own several items (combined in slot order).
+ * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Work comes from gta_schedule_build.  Rows that own several
+ * items are folded in slot order INSIDE the kernel (each item waits for its predecessor's state, no
+ * merge launch): `partials` holds num_slots*f floats, `chain_flags` num_slots*ceil(f/128) int32
+ * (cleared by GTA_PHASE_RESET); both may be NULL when num_slots == 0.
  * ------------------------------------------------------------------------------------ */
 int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
-                      int64_t num_rows, int64_t num_slots, const int32_t* indices,
+                      int64_t num_slots, const int32_t* indices,
                       int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
-                      int32_t epilogue, float* partials, int32_t phases, void* stream);
+                      int32_t epilogue, float* partials, int32_t* chain_flags, int32_t phases,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * GAT edge phase in ONE pass (ops 3-13 of genGraphOP.py:52-62; ISA blocks
@@ -182,16 +187,17 @@ int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* ro
  *   out[i,:] = epi( sum_k alpha[k,h(f)] * z[j,:] )
  * el [rows,H] (dense) is indexed by LOCAL row; er (row stride `lder` elements, so it can live in
  * the same gathered table as z: [.., F | H] per source) and z by source id.
- * partials: n_slots * gta_gat_partial_stride(f,H) floats  (= f + roundup4(2*H)).
+ * partials: num_slots * gta_gat_partial_stride(f,H) floats (acc[f], then (max[H], sum[H]) padded to 4
+ * per 128-feature window); chain_flags as for gta_aggregate_f32.
  * Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip).
  * ------------------------------------------------------------------------------------ */
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads);
 int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
-                          int64_t num_rows, int64_t num_slots, const int32_t* indices,
+                          int64_t num_slots, const int32_t* indices,
                           const float* el, const float* er, int64_t lder, int32_t heads, float slope,
                           const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum,
-                          float* partials, int32_t phases, void* stream);
+                          float* partials, int32_t* chain_flags, int32_t phases, void* stream);
 
 /* GAT block [4,5,6,7,8] alone (COMP_ADD 6, COMP_SF 7, STORE_E 7, COMP_ADD 8 gather):
  *   p[k,h] = exp(leaky_relu(el[i,h] + er[j,h]) - rowmax[i,h]),  rowsum[i,h] = sum_k p[k,h].
