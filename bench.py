@@ -256,6 +256,10 @@ def main():
                     help="edges in the CPU arm's sample (whole destination rows from row 0); the layer time is "
                          "extrapolated from it.  40 M edges = about a second per step on 16 cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fp64-oracle check of the benchmarked output")
+    ap.add_argument("--parity-edges", type=int, default=200_000_000,
+                    help="edge budget of the parity check: every destination row of rank 0 when it holds at most this "
+                         "many edges, else the 512 highest-degree rows plus every k-th row")
     ap.add_argument("--no-fuse", action="store_true", help="honour every STORE_* of the program")
     ap.add_argument("--chunks", type=int, default=1,
                     help="multi-GPU: pieces the source all-gather is cut into; > 1 overlaps the transfer with the "
@@ -332,6 +336,10 @@ def main():
         sample_rows = int(min(n, max(64, np.searchsorted(np.cumsum(deg_h), args.cpu_sample_edges) + 1)))
         e_s = int(host_csr[0][sample_rows])
         host_csr = (host_csr[0][:sample_rows + 1].copy(), full.indices[:e_s].cpu().numpy(), sample_rows, deg_h)
+    parity_csr = None
+    if rank == 0 and not args.no_parity:
+        e0, e1 = int(full.indptr[r0]), int(full.indptr[r1])
+        parity_csr = ((full.indptr[r0:r1 + 1] - e0).cpu().numpy(), full.indices[e0:e1].cpu().numpy())
     if world > 1 and not args.alt:
         del full
         torch.cuda.empty_cache()
@@ -482,10 +490,43 @@ def main():
     h2d = int(xs_pin[0].numel() * 4)
     d2h = int(ys_pin[0].numel() * 4)
 
+    # bitwise run-to-run reproducibility of the timed path (every rank; the reduction shape is fixed)
+    y_first = run_step().clone()
+    bitwise = bool(torch.equal(y_first, run_step()))
+    if world > 1:
+        tb = torch.tensor([int(bitwise)], dtype=torch.int32, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MIN)
+        bitwise = bool(tb.item())
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- parity of the BENCHMARKED output against the fp64 oracle (rank 0's destination rows) ----------
+    parity = None
+    if parity_csr is not None:
+        from oracle import c_oracle, parity as P
+        c_oracle.use_all_cores()
+        t_par = time.perf_counter()
+        indptr_l, indices_l = parity_csr
+        rows_sel = P.select_rows(indptr_l, args.parity_edges)
+        ip_s, ix_s = P.sub_csr(indptr_l, indices_l, rows_sel)
+        y_h = y_first.cpu().numpy()[rows_sel]
+        if network == "GAT":
+            z64, zabs, el64, er64 = P.host_tables(x_h, w_h, al_h, ar_h)
+            parity = P.check_gat(y_h, ip_s, ix_s, el64[r0 + rows_sel], er64, z64, zabs)
+        else:
+            z64, zabs, _, _ = P.host_tables(x_h, w_h)
+            deg_l = np.diff(indptr_l)
+            pos = np.repeat(indptr_l[rows_sel] - ip_s[:-1], deg_l[rows_sel]) + np.arange(int(ip_s[-1]), dtype=np.int64)
+            parity = P.check_gcn(y_h, ip_s, ix_s, edge_w.cpu().numpy().reshape(-1)[pos], z64, zabs)
+        del z64, zabs
+        parity.update(bitwise_rerun=bitwise, rows_of=int(r1 - r0), edges_of=int(indptr_l[-1]),
+                      checked="rank 0's destination rows [%d,%d)%s" % (r0, r1, "" if rows_sel.shape[0] == r1 - r0 else
+                                                                      " (512 highest-degree rows + every k-th row)"),
+                      seconds=round(time.perf_counter() - t_par, 1))
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     dom = "gta_gat_aggregate_f32" if network == "GAT" else "gta_aggregate_f32"
@@ -552,10 +593,13 @@ def main():
                             "(pipeline.HostPipeline, depth 2; serial_ms_per_step = depth 1); the CSR (static graph "
                             "structure) and the weights stay resident"},
             "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline}
-    print(json.dumps(line))
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not (parity["max_err_over_tol"] <= 1.0 and parity["bitwise_rerun"]):
+        raise SystemExit("parity FAILED: the benchmarked output is %.2fx the tolerance away from the fp64 oracle "
+                         "(bitwise rerun: %s)" % (parity["max_err_over_tol"], parity["bitwise_rerun"]))
 
 
 if __name__ == "__main__":

@@ -60,8 +60,9 @@ SIGNATURES = {
     "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
                                     _p, _p, _i32, _p]),
     "gta_gat_partial_stride": (_i32, [_i32, _i32]),
+    "gta_er_stats": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _p]),
     "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _i64,
-                                        _i32, _i32, _p, _p, _p, _p, _i32, _p]),
+                                        _i32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p]),
     "gta_gat_logits_f32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "gta_edge_binary_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _i32, _i32, _i64, _p, _i32,
                                       _i64, _p]),

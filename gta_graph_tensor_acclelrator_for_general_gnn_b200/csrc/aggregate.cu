@@ -18,9 +18,9 @@
 // in column blocks) form a CHAIN in slot order: an item reduces its own edges first, then waits for
 // its predecessor's published state (a release/acquire flag per slot), folds it in, and either
 // publishes the folded state or -- last item of the row -- normalises and writes the output.  The
-// wait is at the END of an item and predecessors always sit earlier in the grid (CTAs are dispatched
-// in blockIdx order), so it almost never spins; there is no separate merge launch and the last
-// partial of every row is never written (round 1: a combine kernel re-read 507 MB in 0.24 ms).
+// wait is at the END of an item and whoever holds the predecessor took it from the item counter earlier
+// and is running, so it almost never spins and cannot deadlock; there is no separate merge launch and the
+// last partial of every row is never written (round 1: a combine kernel re-read 507 MB in 0.24 ms).
 //
 // Determinism.  Every item is reduced by exactly one group in ascending source order and the chain
 // is a left fold in slot order: a fixed-shape reduction, bitwise reproducible run to run, no atomics.
@@ -38,7 +38,7 @@ namespace gta {
 #define GTA_AGG_MINBLOCKS 6       // 128 threads x 6 blocks = 24 warps/SM => at most 80 registers (measured best)
 #endif
 #ifndef GTA_AGG_FASTEXP
-#define GTA_AGG_FASTEXP 0
+#define GTA_AGG_FASTEXP 1
 #endif
 constexpr int kAggThreads = GTA_AGG_THREADS;
 constexpr int kAggWarps = kAggThreads / 32;
@@ -157,151 +157,186 @@ __device__ __forceinline__ float4 epilogue4(float4 a, float scale, int epi) {
 }
 
 // ----------------------------------------------------------------------------------------
+// the work list, its chain state and the dynamic item counter every aggregation launch takes
+// ----------------------------------------------------------------------------------------
+struct WorkList {
+  const int4* items;
+  int64_t num_items;
+  const int32_t* row_slots;
+  int64_t num_slots;
+  const int32_t* indices;
+  float* partials;
+  int32_t* chain_flags;      // [windows][num_slots]
+  int32_t* work_counter;     // [windows], zeroed before every launch
+  uint64_t pol_stream;
+  uint64_t pol_keep;
+};
+
+// Persistent launch: every warp takes the next 32/LANES items from a global counter until the list is
+// empty.  (Round 1 launched one CTA per 4 items: a CTA slot stayed occupied until its longest item was
+// done and only 18 of the 24 resident warps per SM were active.)  The grab for the NEXT items is issued
+// before the current ones are processed and its result is only read afterwards, so the atomic's round
+// trip hides under the gathers.  Items are still started in work-list order, which keeps the CTAs on one
+// column block at a time and keeps the chain invariant: whoever holds a predecessor slot started earlier
+// and is running, so a wait can never deadlock, whatever the grid size.
+template <int LANES>
+__device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane) {
+  int32_t v = 0;
+  if (lane == 0) v = atomicAdd(counter, 32 / LANES);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------
 // weighted aggregate
 //   WKIND 0: no weight, 1: scalar weight per edge (wh == 1), 2: per-head weight (wh > 1,
 //   (f / wh) % 4 == 0 so a lane's 4 features share a head)
 // ----------------------------------------------------------------------------------------
 template <int LANES, int WKIND, bool DIV>
 __global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
-aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ row_slots,
-                 int64_t num_slots, const int32_t* __restrict__ indices,
-                 const float* __restrict__ w, int wh, const float* __restrict__ rowden,
+aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const float* __restrict__ rowden,
                  const float* __restrict__ x, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
-                 int f, int epilogue, float* partials, int32_t* chain_flags, const uint64_t pol_stream,
-    const uint64_t pol_keep) {
+                 int f, int epilogue) {
   __shared__ __align__(16) uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
-  const int64_t group = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) / LANES;
   const int fo = blockIdx.y * 128 + 4 * l;
-  const bool have = group < num_items;
-  const bool active = have && fo < f;
-  int4 it = have ? items[group] : make_int4(0, 0, 0, -1);
-  const int count = have ? it.z : 0;
-  const int max_count = (LANES == 32) ? count : warp_max_i32(count);
-  const int32_t* idx_base = indices + it.y;
   uint2* se = s_a[threadIdx.x >> 5];
   const uint2* mine = se + (lane & ~(LANES - 1));
   const uint4* mine2 = reinterpret_cast<const uint4*>(mine);      // two staged edges per LDS.128
-  const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
-  const float* xf = x + (active ? fo : 0);
-  int head = 0;
-  float den = 1.f;
-  if (WKIND == 2) head = active ? fo / (f / wh) : 0;
-  if (DIV && have) den = rowden[int64_t(it.x) * wh + head];
+  int32_t* counter = wl.work_counter + blockIdx.y;
+  int32_t* flags = wl.chain_flags + int64_t(blockIdx.y) * wl.num_slots;
+  const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
 
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // software pipeline: ids (and scalar weights) of batch b+1 are in flight under the gathers of batch b
-  int idx_nxt = 0;
-  float w_nxt = 0.f;
-  if (l < count) {
-    idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
-    if (WKIND == 1) w_nxt = ld_stream_f32(w_base + l, pol_stream);
-  }
-  for (int base = 0; base < max_count; base += LANES) {
-    int n = count - base;
-    n = n < 0 ? 0 : (n > LANES ? LANES : n);
-    const int my_idx = idx_nxt;
-    float my_w = (l < n) ? w_nxt : 0.f;
-    // divide only where an edge exists: a neighbouring group's empty row has den = 0 (0/0 = NaN)
-    if (WKIND == 1 && DIV && l < n) my_w = my_w / den;
-    if (base + LANES + l < count) {
-      idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
-      if (WKIND == 1) w_nxt = ld_stream_f32(w_base + base + LANES + l, pol_stream);
+  int32_t first = __shfl_sync(0xffffffffu, grab_items<LANES>(counter, lane), 0);
+  while (first < wl.num_items) {
+    const int32_t pending = grab_items<LANES>(counter, lane);
+    const int64_t group = int64_t(first) + lane / LANES;
+    const bool have = group < wl.num_items;
+    const bool active = have && fo < f;
+    const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
+    const int count = have ? it.z : 0;
+    const int max_count = (LANES == 32) ? count : warp_max_i32(count);
+    const int32_t* idx_base = wl.indices + it.y;
+    const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
+    const float* xf = x + (active ? fo : 0);
+    int head = 0;
+    float den = 1.f;
+    if (WKIND == 2) head = active ? fo / (f / wh) : 0;
+    if (DIV && have) den = rowden[int64_t(it.x) * wh + head];
+
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // software pipeline: ids (and scalar weights) of batch b+1 are in flight under the gathers of batch b
+    int idx_nxt = 0;
+    float w_nxt = 0.f;
+    if (l < count) {
+      idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+      if (WKIND == 1) w_nxt = ld_stream_f32(w_base + l, pol_stream);
     }
-    // stage {source id, weight} of the batch in shared memory: one LDS.64 per edge in the gather loop
-    se[lane] = make_uint2(uint32_t(my_idx), __float_as_uint(WKIND == 1 ? my_w : 1.f));
-    __syncwarp();
-    const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
-    if (full) {
-      // whole batch, no predicates: kUnroll loads in flight, then their FMAs (the outer loop stays
-      // rolled: unrolled, ptxas hoists every load of the batch and spills)
-      if (LANES < 32 || active) {
+    for (int base = 0; base < max_count; base += LANES) {
+      int n = count - base;
+      n = n < 0 ? 0 : (n > LANES ? LANES : n);
+      const int my_idx = idx_nxt;
+      float my_w = (l < n) ? w_nxt : 0.f;
+      // divide only where an edge exists: a neighbouring group's empty row has den = 0 (0/0 = NaN)
+      if (WKIND == 1 && DIV && l < n) my_w = my_w / den;
+      if (base + LANES + l < count) {
+        idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
+        if (WKIND == 1) w_nxt = ld_stream_f32(w_base + base + LANES + l, pol_stream);
+      }
+      // stage {source id, weight} of the batch in shared memory: one LDS.128 per two edges in the gather loop
+      se[lane] = make_uint2(uint32_t(my_idx), __float_as_uint(WKIND == 1 ? my_w : 1.f));
+      __syncwarp();
+      const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
+      if (full) {
+        // whole batch, no predicates: kUnroll loads in flight, then their FMAs (the outer loop stays
+        // rolled: unrolled, ptxas hoists every load of the batch and spills)
+        if (LANES < 32 || active) {
 #pragma unroll 1
-        for (int j = 0; j < LANES; j += kUnroll) {
-          uint4 ed[kUnroll / 2];
-          float4 v[kUnroll];
+          for (int j = 0; j < LANES; j += kUnroll) {
+            uint4 ed[kUnroll / 2];
+            float4 v[kUnroll];
 #pragma unroll
-          for (int u = 0; u < kUnroll / 2; ++u)
-            if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
+            for (int u = 0; u < kUnroll / 2; ++u)
+              if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
-          for (int u = 0; u < kUnroll / 2; ++u) {
-            if (j + 2 * u < LANES) {
-              v[2 * u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
-              v[2 * u + 1] = ld_row_f32x4(row_ptr(xf, ed[u].z, row_bytes), pol_keep);
+            for (int u = 0; u < kUnroll / 2; ++u) {
+              if (j + 2 * u < LANES) {
+                v[2 * u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
+                v[2 * u + 1] = ld_row_f32x4(row_ptr(xf, ed[u].z, row_bytes), pol_keep);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              if (j + u < LANES) {
+                float ws = __uint_as_float((u & 1) ? ed[u / 2].w : ed[u / 2].y);
+                if (WKIND == 2) {
+                  ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
+                  if (DIV) ws = ws / den;
+                }
+                fma4(acc, ws, v[u]);
+              }
             }
           }
+        }
+      } else {
+        const int nmax = (LANES == 32) ? n : LANES;
+        for (int j = 0; j < nmax; j += kUnroll) {
+          float4 v[kUnroll];
+          float wv[kUnroll];
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
             if (j + u < LANES) {
-              float ws = __uint_as_float((u & 1) ? ed[u / 2].w : ed[u / 2].y);
+              const uint2 ed = mine[j + u];
+              const bool ok = active && (j + u) < n;
+              float ws = ok ? __uint_as_float(ed.y) : 0.f;
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) v[u] = ld_row_f32x4(row_ptr(xf, ed.x, row_bytes), pol_keep);
               if (WKIND == 2) {
-                ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
-                if (DIV) ws = ws / den;
+                ws = 0.f;
+                if (ok) {
+                  ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
+                  if (DIV) ws = ws / den;
+                }
               }
-              fma4(acc, ws, v[u]);
+              wv[u] = ws;
             }
           }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) fma4(acc, wv[u], v[u]);
         }
       }
-    } else {
-      const int nmax = (LANES == 32) ? n : LANES;
-      for (int j = 0; j < nmax; j += kUnroll) {
-        float4 v[kUnroll];
-        float wv[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          if (j + u < LANES) {
-            const uint2 ed = mine[j + u];
-            const bool ok = active && (j + u) < n;
-            float ws = ok ? __uint_as_float(ed.y) : 0.f;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v[u] = ld_row_f32x4(row_ptr(xf, ed.x, row_bytes), pol_keep);
-            if (WKIND == 2) {
-              ws = 0.f;
-              if (ok) {
-                ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
-                if (DIV) ws = ws / den;
-              }
-            }
-            wv[u] = ws;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          if (j + u < LANES) fma4(acc, wv[u], v[u]);
-      }
+      __syncwarp();
     }
-    __syncwarp();
+    const bool chained = have && it.w >= 0;
+    for_groups_in_order<LANES>(lane, chained, [&]() {
+      bool last = true;
+      if (chained) {
+        const int s0 = __ldg(wl.row_slots + it.x), s1 = __ldg(wl.row_slots + it.x + 1);
+        last = it.w == s1 - 1;
+        if (it.w != s0) {
+          if (l == 0) chain_wait(flags + it.w - 1);
+          __syncwarp(group_mask<LANES>(lane));
+          if (active) {
+            const float4 p = ld_state_f32x4(wl.partials + int64_t(it.w - 1) * f + fo);
+            acc.x = p.x + acc.x; acc.y = p.y + acc.y; acc.z = p.z + acc.z; acc.w = p.w + acc.w;
+          }
+        }
+        if (!last) {
+          if (active) *reinterpret_cast<float4*>(wl.partials + int64_t(it.w) * f + fo) = acc;
+          __threadfence();
+          __syncwarp(group_mask<LANES>(lane));
+          if (l == 0) chain_publish(flags + it.w);
+        }
+      }
+      if (last && active) st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
+    });
+    first = __shfl_sync(0xffffffffu, pending, 0);
   }
-  const bool chained = have && it.w >= 0;
-  for_groups_in_order<LANES>(lane, chained, [&]() {
-    bool last = true;
-    if (chained) {
-      const int s0 = __ldg(row_slots + it.x), s1 = __ldg(row_slots + it.x + 1);
-      int32_t* flags = chain_flags + int64_t(blockIdx.y) * num_slots;
-      last = it.w == s1 - 1;
-      if (it.w != s0) {
-        if (l == 0) chain_wait(flags + it.w - 1);
-        __syncwarp(group_mask<LANES>(lane));
-        if (active) {
-          const float4 p = ld_state_f32x4(partials + int64_t(it.w - 1) * f + fo);
-          acc.x = p.x + acc.x; acc.y = p.y + acc.y; acc.z = p.z + acc.z; acc.w = p.w + acc.w;
-        }
-      }
-      if (!last) {
-        if (active) *reinterpret_cast<float4*>(partials + int64_t(it.w) * f + fo) = acc;
-        __threadfence();
-        __syncwarp(group_mask<LANES>(lane));
-        if (l == 0) chain_publish(flags + it.w);
-      }
-    }
-    if (last && active) st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
-  });
 }
 
 // ----------------------------------------------------------------------------------------
-// GAT edge phase, single pass (online softmax over batches of LANES edges)
+// GAT edge phase, single pass
 // ----------------------------------------------------------------------------------------
 template <int H>
 __device__ __forceinline__ void load_heads(const float* __restrict__ p, float (&v)[H]) {
@@ -331,15 +366,40 @@ __device__ __forceinline__ float pick(const float (&v)[H], int h) {
   return r;
 }
 
+// ---- softmax shift from a BOUND instead of the running maximum -----------------------------------
+// leaky_relu is monotonic, so for every edge of row i whose source lies in column block cb
+//     e = leaky(el[i,h] + er[j,h])  <=  leaky(el[i,h] + max_{j in cb} er[j,h])  =: bound(i, cb, h).
+// Softmax is invariant under the shift, so p = exp(e - bound) needs no running maximum: no warp
+// reductions, no rescale of the accumulator, one exp per edge and head instead of two (round 2 ncu: the 20
+// shuffles per 32-edge batch were 0.9 L1/TEX data-pipe wavefronts per edge, the exps 0.6 ms of 5.0).
+// A loose bound only costs exponent range, never precision: as long as max er - min er of the block is
+// below kBoundRange every p stays above exp(-kBoundRange) relative to the row's largest term.  er_stats
+// (gta_er_stats: ordered-int coded max er and max -er per column block and head) says so; blocks that
+// fail the test, heads counts that are no power of two and calls that want the true row maximum back
+// take the online path below.
+constexpr float kBoundRange = 60.f;
+__device__ __forceinline__ uint32_t ordered_code(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_decode(uint32_t c) {
+  return __uint_as_float((c & 0x80000000u) ? (c & 0x7fffffffu) : ~c);
+}
+// er_stats[cb][0][h] = code(max er), er_stats[cb][1][h] = code(max -er); zero = "no source seen"
+__device__ __forceinline__ bool block_bound(const uint32_t* __restrict__ er_stats, int64_t cb, int heads, int h,
+                                            float* er_max) {
+  const uint32_t cmax = __ldg(er_stats + (cb * 2) * heads + h), cneg = __ldg(er_stats + (cb * 2 + 1) * heads + h);
+  const float hi = ordered_decode(cmax), lo = -ordered_decode(cneg);
+  *er_max = hi;
+  return cmax != 0u && cneg != 0u && (hi - lo) < kBoundRange;      // NaN compares false
+}
+
 template <int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? kAggMinBlocks : (kAggMinBlocks + 1) / 2)
-gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ row_slots,
-                     int64_t num_slots, const int32_t* __restrict__ indices,
-                     const float* __restrict__ el, const float* __restrict__ er, int64_t lder, float slope,
-                     const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
-                     int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
-                     float* partials, int32_t* chain_flags, const uint64_t pol_stream,
-    const uint64_t pol_keep) {
+gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const float* __restrict__ er, int64_t lder,
+                     float slope, const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out,
+                     int64_t ldo, int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
+                     const uint32_t* __restrict__ er_stats, int64_t col_block) {
   // per warp: H rows of 32 staged edges, entry = {source id, softmax numerator}.  Row pitch kS = 34
   // entries: a lane's STS.64 lands beside its neighbour's (2 wavefronts per head, no conflicts) and the
   // LDS.128 of the gather loop -- two consecutive edges of one head, the 4 heads of a warp at once --
@@ -350,168 +410,206 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int gbase = lane & ~(LANES - 1);          // first lane of my group inside the warp
-  const int64_t group = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) / LANES;
   const int fo = blockIdx.y * 128 + 4 * l;
-  const bool have = group < num_items;
-  const bool active = have && fo < f;
-  int4 it = have ? items[group] : make_int4(0, 0, 0, -1);
-  const int count = have ? it.z : 0;
-  const int max_count = (LANES == 32) ? count : warp_max_i32(count);
-  const int32_t* idx_base = indices + it.y;
-  const int head = active ? fo / (f / H) : 0;
-  const float* zf = z + (active ? fo : 0);
+  const int head = (fo < f) ? fo / (f / H) : 0;
   uint2* se = s_e[threadIdx.x >> 5];
   const uint2* mine = se + head * kS + gbase;
   const uint4* mine2 = reinterpret_cast<const uint4*>(mine);
+  int32_t* counter = wl.work_counter + blockIdx.y;
+  int32_t* flags = wl.chain_flags + int64_t(blockIdx.y) * wl.num_slots;
+  const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
+  const int pstride = gat_partial_stride(f, H);
+  const int stats = f + int(blockIdx.y) * gat_stats_stride(H);
 
-  float elr[H], m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
-  if (have) load_heads<H>(el + int64_t(it.x) * H, elr);
-#pragma unroll
-  for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; if (!have) elr[h] = 0.f; }
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int32_t first = __shfl_sync(0xffffffffu, grab_items<LANES>(counter, lane), 0);
+  while (first < wl.num_items) {
+    const int32_t pending = grab_items<LANES>(counter, lane);
+    const int64_t group = int64_t(first) + lane / LANES;
+    const bool have = group < wl.num_items;
+    const bool active = have && fo < f;
+    const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
+    const int count = have ? it.z : 0;
+    const int max_count = (LANES == 32) ? count : warp_max_i32(count);
+    const int32_t* idx_base = wl.indices + it.y;
+    const float* zf = z + (active ? fo : 0);
 
-  // software pipeline: source ids are loaded two batches ahead and the er rows one batch ahead, so
-  // the id -> er -> softmax dependency chain of batch b+1 hides under the row gathers of batch b
-  int idx_cur = 0, idx_nxt = 0;
-  float er_cur[H];
+    float elr[H], m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
+    if (have) load_heads<H>(el + int64_t(it.x) * H, elr);
 #pragma unroll
-  for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
-  if (l < count) {
-    idx_cur = ld_stream_i32(idx_base + l, pol_stream);
-    load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
-  }
-  if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; if (!have) elr[h] = 0.f; }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int base = 0; base < max_count; base += LANES) {
-    int n = count - base;
-    n = n < 0 ? 0 : (n > LANES ? LANES : n);
-    float e[H];
-    const int my_idx = idx_cur;
+    // software pipeline: source ids are loaded two batches ahead and the er rows one batch ahead, so
+    // the id -> er -> softmax dependency chain of batch b+1 hides under the row gathers of batch b
+    int idx_cur = 0, idx_nxt = 0;
+    float er_cur[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) e[h] = (l < n) ? leaky(elr[h] + er_cur[h], slope) : -INFINITY;
-    // prefetch: er of the next batch (its ids arrived during the previous iteration), ids of the one after
-    idx_cur = idx_nxt;
-    if (base + LANES + l < count) load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
-    if (base + 2 * LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + 2 * LANES + l, pol_stream);
-    float my_scale = 1.f;
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const float mn = fmaxf(m[h], group_max<LANES>(e[h]));
-      // mn stays -inf only while this group has seen no edge (another group in the warp is running)
-      const float sc = (mn == -INFINITY) ? 1.f : softmax_exp(m[h] - mn);
-      const float p = (l < n) ? softmax_exp(e[h] - mn) : 0.f;
-      s[h] = fmaf(s[h], sc, p);
-      m[h] = mn;
-      my_scale = (h == head) ? sc : my_scale;
-      se[h * kS + lane] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
+    for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
+    if (l < count) {
+      idx_cur = ld_stream_i32(idx_base + l, pol_stream);
+      load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
     }
-    acc.x *= my_scale; acc.y *= my_scale; acc.z *= my_scale; acc.w *= my_scale;
-    __syncwarp();
-    const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
-    if (full) {
-      if (LANES < 32 || active) {
-#pragma unroll 1
-        for (int j = 0; j < LANES; j += kUnroll) {
-          uint4 ed[kUnroll / 2];
-          float4 v[kUnroll];
-#pragma unroll
-          for (int u = 0; u < kUnroll / 2; ++u)
-            if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
-#pragma unroll
-          for (int u = 0; u < kUnroll / 2; ++u) {
-            if (j + 2 * u < LANES) {
-              v[2 * u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
-              v[2 * u + 1] = ld_row_f32x4(row_ptr(zf, ed[u].z, row_bytes), pol_keep);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kUnroll / 2; ++u) {
-            if (j + 2 * u < LANES) {
-              fma4(acc, __uint_as_float(ed[u].y), v[2 * u]);
-              fma4(acc, __uint_as_float(ed[u].w), v[2 * u + 1]);
-            }
-          }
-        }
-      }
-    } else {
-      const int nmax = (LANES == 32) ? n : LANES;
-      for (int j = 0; j < nmax; j += kUnroll) {
-        float4 v[kUnroll];
-        float pv[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          if (j + u < LANES) {
-            const uint2 ed = mine[j + u];
-            pv[u] = __uint_as_float(ed.y);
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, ed.x, row_bytes), pol_keep);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-          if (j + u < LANES) fma4(acc, pv[u], v[u]);
-      }
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int h = 0; h < H; ++h) s[h] = group_sum<LANES>(s[h]);
-  const bool chained = have && it.w >= 0;
-  for_groups_in_order<LANES>(lane, chained, [&]() {
-    bool last = true;
-    if (chained) {
-      const int s0 = __ldg(row_slots + it.x), s1 = __ldg(row_slots + it.x + 1);
-      int32_t* flags = chain_flags + int64_t(blockIdx.y) * num_slots;
-      const int pstride = gat_partial_stride(f, H);
-      const int stats = f + int(blockIdx.y) * gat_stats_stride(H);
-      last = it.w == s1 - 1;
-      if (it.w != s0) {
-        // fold the state of slots [s0, it.w) in: (max, sum, acc) triples merge like the online softmax itself
-        if (l == 0) chain_wait(flags + it.w - 1);
-        __syncwarp(group_mask<LANES>(lane));
-        const float* prev = partials + int64_t(it.w - 1) * pstride;
-        float a_mine = 1.f, b_mine = 1.f;
+    if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
+
+    // bound path: the whole warp or nobody (the online path reduces with full-warp shuffles)
+    bool bounded = false;
+    if (er_stats != nullptr) {
+      bool ok = true;
+      const int first_src = __shfl_sync(0xffffffffu, idx_cur, gbase);
+      if (count > 0) {
+        const int64_t cb = col_block > 0 ? int64_t(first_src) / col_block : 0;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          const float pm = ld_state_f32(prev + stats + h), ps = ld_state_f32(prev + stats + H + h);
-          const float mn = fmaxf(pm, m[h]);
-          const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
-          const float b = (m[h] == -INFINITY) ? 0.f : expf(m[h] - mn);
-          s[h] = fmaf(ps, a, s[h] * b);
+          float hi;
+          ok = block_bound(er_stats, cb, H, h, &hi) && ok;
+          if (ok) m[h] = leaky(elr[h] + hi, slope);
+        }
+      }
+      bounded = __all_sync(0xffffffffu, ok);
+      if (!bounded) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) m[h] = -INFINITY;
+      }
+    }
+
+    for (int base = 0; base < max_count; base += LANES) {
+      int n = count - base;
+      n = n < 0 ? 0 : (n > LANES ? LANES : n);
+      float e[H];
+      const int my_idx = idx_cur;
+#pragma unroll
+      for (int h = 0; h < H; ++h) e[h] = (l < n) ? leaky(elr[h] + er_cur[h], slope) : -INFINITY;
+      // prefetch: er of the next batch (its ids arrived during the previous iteration), ids of the one after
+      idx_cur = idx_nxt;
+      if (base + LANES + l < count) load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
+      if (base + 2 * LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + 2 * LANES + l, pol_stream);
+      if (bounded) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float p = (l < n) ? softmax_exp(e[h] - m[h]) : 0.f;
+          s[h] += p;
+          se[h * kS + lane] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
+        }
+      } else {
+        float my_scale = 1.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float mn = fmaxf(m[h], group_max<LANES>(e[h]));
+          // mn stays -inf only while this group has seen no edge (another group in the warp is running)
+          const float sc = (mn == -INFINITY) ? 1.f : softmax_exp(m[h] - mn);
+          const float p = (l < n) ? softmax_exp(e[h] - mn) : 0.f;
+          s[h] = fmaf(s[h], sc, p);
           m[h] = mn;
-          a_mine = (h == head) ? a : a_mine;
-          b_mine = (h == head) ? b : b_mine;
+          my_scale = (h == head) ? sc : my_scale;
+          se[h * kS + lane] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
         }
+        acc.x *= my_scale; acc.y *= my_scale; acc.z *= my_scale; acc.w *= my_scale;
+      }
+      __syncwarp();
+      const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
+      if (full) {
+        if (LANES < 32 || active) {
+#pragma unroll 1
+          for (int j = 0; j < LANES; j += kUnroll) {
+            uint4 ed[kUnroll / 2];
+            float4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll / 2; ++u)
+              if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
+#pragma unroll
+            for (int u = 0; u < kUnroll / 2; ++u) {
+              if (j + 2 * u < LANES) {
+                v[2 * u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
+                v[2 * u + 1] = ld_row_f32x4(row_ptr(zf, ed[u].z, row_bytes), pol_keep);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll / 2; ++u) {
+              if (j + 2 * u < LANES) {
+                fma4(acc, __uint_as_float(ed[u].y), v[2 * u]);
+                fma4(acc, __uint_as_float(ed[u].w), v[2 * u + 1]);
+              }
+            }
+          }
+        }
+      } else {
+        const int nmax = (LANES == 32) ? n : LANES;
+        for (int j = 0; j < nmax; j += kUnroll) {
+          float4 v[kUnroll];
+          float pv[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            if (j + u < LANES) {
+              const uint2 ed = mine[j + u];
+              pv[u] = __uint_as_float(ed.y);
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, ed.x, row_bytes), pol_keep);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u)
+            if (j + u < LANES) fma4(acc, pv[u], v[u]);
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) s[h] = group_sum<LANES>(s[h]);
+    const bool chained = have && it.w >= 0;
+    for_groups_in_order<LANES>(lane, chained, [&]() {
+      bool last = true;
+      if (chained) {
+        const int s0 = __ldg(wl.row_slots + it.x), s1 = __ldg(wl.row_slots + it.x + 1);
+        last = it.w == s1 - 1;
+        if (it.w != s0) {
+          // fold the state of slots [s0, it.w) in: (max, sum, acc) triples merge like the online softmax itself
+          if (l == 0) chain_wait(flags + it.w - 1);
+          __syncwarp(group_mask<LANES>(lane));
+          const float* prev = wl.partials + int64_t(it.w - 1) * pstride;
+          float a_mine = 1.f, b_mine = 1.f;
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float pm = ld_state_f32(prev + stats + h), ps = ld_state_f32(prev + stats + H + h);
+            const float mn = fmaxf(pm, m[h]);
+            const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
+            const float b = (m[h] == -INFINITY) ? 0.f : expf(m[h] - mn);
+            s[h] = fmaf(ps, a, s[h] * b);
+            m[h] = mn;
+            a_mine = (h == head) ? a : a_mine;
+            b_mine = (h == head) ? b : b_mine;
+          }
+          if (active) {
+            const float4 p = ld_state_f32x4(prev + fo);
+            acc.x = fmaf(p.x, a_mine, acc.x * b_mine); acc.y = fmaf(p.y, a_mine, acc.y * b_mine);
+            acc.z = fmaf(p.z, a_mine, acc.z * b_mine); acc.w = fmaf(p.w, a_mine, acc.w * b_mine);
+          }
+        }
+        if (!last) {
+          float* part = wl.partials + int64_t(it.w) * pstride;
+          if (active) *reinterpret_cast<float4*>(part + fo) = acc;
+          if (l < H) {
+            part[stats + l] = pick<H>(m, l);
+            part[stats + H + l] = pick<H>(s, l);
+          }
+          __threadfence();
+          __syncwarp(group_mask<LANES>(lane));
+          if (l == 0) chain_publish(flags + it.w);
+        }
+      }
+      if (last && have) {
         if (active) {
-          const float4 p = ld_state_f32x4(prev + fo);
-          acc.x = fmaf(p.x, a_mine, acc.x * b_mine); acc.y = fmaf(p.y, a_mine, acc.y * b_mine);
-          acc.z = fmaf(p.z, a_mine, acc.z * b_mine); acc.w = fmaf(p.w, a_mine, acc.w * b_mine);
+          const float sh = pick<H>(s, head);
+          st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue));
+        }
+        if (blockIdx.y == 0 && l < H) {
+          const float ml = pick<H>(m, l);
+          if (rowmax) rowmax[int64_t(it.x) * H + l] = (count > 0 || it.w >= 0) && ml != -INFINITY ? ml : 0.f;
+          if (rowsum) rowsum[int64_t(it.x) * H + l] = pick<H>(s, l);
         }
       }
-      if (!last) {
-        float* part = partials + int64_t(it.w) * pstride;
-        if (active) *reinterpret_cast<float4*>(part + fo) = acc;
-        if (l < H) {
-          part[stats + l] = pick<H>(m, l);
-          part[stats + H + l] = pick<H>(s, l);
-        }
-        __threadfence();
-        __syncwarp(group_mask<LANES>(lane));
-        if (l == 0) chain_publish(flags + it.w);
-      }
-    }
-    if (last && have) {
-      if (active) {
-        const float sh = pick<H>(s, head);
-        st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue));
-      }
-      if (blockIdx.y == 0 && l < H) {
-        const float ml = pick<H>(m, l);
-        if (rowmax) rowmax[int64_t(it.x) * H + l] = (ml == -INFINITY) ? 0.f : ml;
-        if (rowsum) rowsum[int64_t(it.x) * H + l] = pick<H>(s, l);
-      }
-    }
-  });
+    });
+    first = __shfl_sync(0xffffffffu, pending, 0);
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -520,134 +618,199 @@ gat_aggregate_kernel(const int4* __restrict__ items, int64_t num_items, const in
 // The staged kernel above keeps el/max/sum/er for ALL heads in every lane (5H registers: H = 16
 // spills and runs at a quarter of the H = 4 speed).  Here a lane tracks only the head its own 4
 // features belong to: one scalar er gather per edge (the 32 lanes of a row read the H
-// consecutive floats of er[j]: one wavefront), online softmax over groups of kUnroll edges, no
+// consecutive floats of er[j]: one wavefront), softmax over groups of kUnroll edges, no
 // per-head arrays, no shuffles.  Lanes of one head see the same edges in the same order, so their
 // (max, sum) are bit-identical.
 // ----------------------------------------------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
-gat_aggregate_llh_kernel(const int4* __restrict__ items, int64_t num_items, const int32_t* __restrict__ row_slots,
-                         int64_t num_slots, const int32_t* __restrict__ indices,
-                         const float* __restrict__ el, const float* __restrict__ er, int64_t lder, int heads,
-                         float slope, const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out,
-                         int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
-                         float* __restrict__ rowsum, float* partials, int32_t* chain_flags, const uint64_t pol_stream,
-    const uint64_t pol_keep) {
+gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const float* __restrict__ er, int64_t lder,
+                         int heads, float slope, const float* __restrict__ z, const uint32_t row_bytes,
+                         float* __restrict__ out, int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
+                         float* __restrict__ rowsum, const uint32_t* __restrict__ er_stats, int64_t col_block) {
   __shared__ uint32_t s_id[kAggWarps][32];
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
-  const int64_t group = (blockIdx.x * int64_t(kAggThreads) + threadIdx.x) / LANES;
   const int fo = blockIdx.y * 128 + 4 * l;
-  const bool have = group < num_items;
-  const bool active = have && fo < f;
-  int4 it = have ? items[group] : make_int4(0, 0, 0, -1);
-  const int count = have ? it.z : 0;
-  const int max_count = (LANES == 32) ? count : warp_max_i32(count);
-  const int32_t* idx_base = indices + it.y;
   const int d = f / heads;
-  const int head = active ? fo / d : 0;
-  const float* zf = z + (active ? fo : 0);
+  const int head = (fo < f) ? fo / d : 0;
   const float* erh = er + head;
   const uint32_t er_bytes = uint32_t(lder) * 4u;
   uint32_t* sid = s_id[threadIdx.x >> 5];
   const uint32_t* mine = sid + (lane & ~(LANES - 1));
-  const float elh = have ? __ldg(el + int64_t(it.x) * heads + head) : 0.f;
+  int32_t* counter = wl.work_counter + blockIdx.y;
+  int32_t* flags = wl.chain_flags + int64_t(blockIdx.y) * wl.num_slots;
+  const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
+  const int pstride = gat_partial_stride(f, heads);
+  const int stats = f + int(blockIdx.y) * gat_stats_stride(heads);
 
-  float m = -INFINITY, s = 0.f;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int idx_nxt = 0;
-  if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
-  for (int base = 0; base < max_count; base += LANES) {
-    int n = count - base;
-    n = n < 0 ? 0 : (n > LANES ? LANES : n);
-    sid[lane] = uint32_t(idx_nxt);
-    if (base + LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
-    __syncwarp();
-    const int nmax = (LANES == 32) ? n : LANES;
+  int32_t first = __shfl_sync(0xffffffffu, grab_items<LANES>(counter, lane), 0);
+  while (first < wl.num_items) {
+    const int32_t pending = grab_items<LANES>(counter, lane);
+    const int64_t group = int64_t(first) + lane / LANES;
+    const bool have = group < wl.num_items;
+    const bool active = have && fo < f;
+    const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
+    const int count = have ? it.z : 0;
+    const int max_count = (LANES == 32) ? count : warp_max_i32(count);
+    const int32_t* idx_base = wl.indices + it.y;
+    const float* zf = z + (active ? fo : 0);
+    const float elh = have ? __ldg(el + int64_t(it.x) * heads + head) : 0.f;
+
+    float m = -INFINITY, s = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int idx_nxt = 0;
+    if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+    // bound path (see gat_aggregate_kernel): a lane only needs the bound of its own head; the choice is
+    // per lane group here, nothing below synchronises across groups on it
+    bool bounded = false;
+    int first_src = 0;
+    if (er_stats != nullptr) first_src = __shfl_sync(0xffffffffu, idx_nxt, lane & ~(LANES - 1));
+    if (er_stats != nullptr && count > 0) {
+      const int64_t cb = col_block > 0 ? int64_t(first_src) / col_block : 0;
+      bool ok = true;
+      for (int h = 0; h < heads; ++h) {          // every head of the block must pass: lanes of one item agree
+        float hi;
+        ok = block_bound(er_stats, cb, heads, h, &hi) && ok;
+        if (h == head) m = leaky(elh + hi, slope);
+      }
+      bounded = ok;
+      if (!bounded) m = -INFINITY;
+    }
+    for (int base = 0; base < max_count; base += LANES) {
+      int n = count - base;
+      n = n < 0 ? 0 : (n > LANES ? LANES : n);
+      sid[lane] = uint32_t(idx_nxt);
+      if (base + LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
+      __syncwarp();
+      const int nmax = (LANES == 32) ? n : LANES;
 #pragma unroll 1
-    for (int j = 0; j < nmax; j += kUnroll) {
-      float e[kUnroll];
-      float4 v[kUnroll];
-      uint32_t id[kUnroll];
+      for (int j = 0; j < nmax; j += kUnroll) {
+        float e[kUnroll];
+        float4 v[kUnroll];
+        uint32_t id[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const bool ok = (j + u) < n;
-        e[u] = ok ? leaky(elh + __ldg(row_ptr(erh, id[u], er_bytes)), slope) : -INFINITY;
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, id[u], row_bytes), pol_keep);
-      }
-      float bm = e[0];
-#pragma unroll
-      for (int u = 1; u < kUnroll; ++u) bm = fmaxf(bm, e[u]);
-      const float mn = fmaxf(m, bm);
-      if (mn != -INFINITY) {          // at least one edge seen so far
-        const float sc = expf(m - mn);          // m = -inf on the first group: sc = 0, acc and s are 0 anyway
-        acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
-        s *= sc;
-        m = mn;
+        for (int u = 0; u < kUnroll; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-          // e = -inf for the padding of the last group: p = 0.  ex2.approx path: the argument is <= 0 and
-          // terms that matter have small |e - mn|; relative error < 2e-6, inside the 1e-5 tolerance
-          const float p = __expf(e[u] - mn);
-          s += p;
-          fma4(acc, p, v[u]);
+          const bool ok = (j + u) < n;
+          e[u] = ok ? leaky(elh + __ldg(row_ptr(erh, id[u], er_bytes)), slope) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, id[u], row_bytes), pol_keep);
+        }
+        if (bounded) {
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const float p = __expf(e[u] - m);          // e = -inf for the padding: p = 0
+            s += p;
+            fma4(acc, p, v[u]);
+          }
+        } else {
+          float bm = e[0];
+#pragma unroll
+          for (int u = 1; u < kUnroll; ++u) bm = fmaxf(bm, e[u]);
+          const float mn = fmaxf(m, bm);
+          if (mn != -INFINITY) {          // at least one edge seen so far
+            const float sc = expf(m - mn);          // m = -inf on the first group: sc = 0, acc and s are 0 anyway
+            acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+            s *= sc;
+            m = mn;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+              // e = -inf for the padding of the last group: p = 0.  ex2.approx path: the argument is <= 0 and
+              // terms that matter have small |e - mn|; relative error < 2e-6, inside the 1e-5 tolerance
+              const float p = __expf(e[u] - mn);
+              s += p;
+              fma4(acc, p, v[u]);
+            }
+          }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
-  }
-  const bool head_leader = active && (fo % d) == 0;       // one lane per head publishes the statistics
-  const bool chained = have && it.w >= 0;
-  for_groups_in_order<LANES>(lane, chained, [&]() {
-    bool last = true;
-    if (chained) {
-      const int s0 = __ldg(row_slots + it.x), s1 = __ldg(row_slots + it.x + 1);
-      int32_t* flags = chain_flags + int64_t(blockIdx.y) * num_slots;
-      const int pstride = gat_partial_stride(f, heads);
-      const int stats = f + int(blockIdx.y) * gat_stats_stride(heads);
-      last = it.w == s1 - 1;
-      if (it.w != s0) {
-        if (l == 0) chain_wait(flags + it.w - 1);
-        __syncwarp(group_mask<LANES>(lane));
-        if (active) {
-          const float* prev = partials + int64_t(it.w - 1) * pstride;
-          const float pm = ld_state_f32(prev + stats + head), ps = ld_state_f32(prev + stats + heads + head);
-          const float mn = fmaxf(pm, m);
-          const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
-          const float b = (m == -INFINITY) ? 0.f : expf(m - mn);
-          const float4 p = ld_state_f32x4(prev + fo);
-          s = fmaf(ps, a, s * b);
-          m = mn;
-          acc.x = fmaf(p.x, a, acc.x * b); acc.y = fmaf(p.y, a, acc.y * b);
-          acc.z = fmaf(p.z, a, acc.z * b); acc.w = fmaf(p.w, a, acc.w * b);
+    const bool head_leader = active && (fo % d) == 0;       // one lane per head publishes the statistics
+    const bool chained = have && it.w >= 0;
+    for_groups_in_order<LANES>(lane, chained, [&]() {
+      bool last = true;
+      if (chained) {
+        const int s0 = __ldg(wl.row_slots + it.x), s1 = __ldg(wl.row_slots + it.x + 1);
+        last = it.w == s1 - 1;
+        if (it.w != s0) {
+          if (l == 0) chain_wait(flags + it.w - 1);
+          __syncwarp(group_mask<LANES>(lane));
+          if (active) {
+            const float* prev = wl.partials + int64_t(it.w - 1) * pstride;
+            const float pm = ld_state_f32(prev + stats + head), ps = ld_state_f32(prev + stats + heads + head);
+            const float mn = fmaxf(pm, m);
+            const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
+            const float b = (m == -INFINITY) ? 0.f : expf(m - mn);
+            const float4 p = ld_state_f32x4(prev + fo);
+            s = fmaf(ps, a, s * b);
+            m = mn;
+            acc.x = fmaf(p.x, a, acc.x * b); acc.y = fmaf(p.y, a, acc.y * b);
+            acc.z = fmaf(p.z, a, acc.z * b); acc.w = fmaf(p.w, a, acc.w * b);
+          }
+        }
+        if (!last) {
+          float* part = wl.partials + int64_t(it.w) * pstride;
+          if (active) *reinterpret_cast<float4*>(part + fo) = acc;
+          if (head_leader) {
+            part[stats + head] = m;
+            part[stats + heads + head] = s;
+          }
+          __threadfence();
+          __syncwarp(group_mask<LANES>(lane));
+          if (l == 0) chain_publish(flags + it.w);
         }
       }
-      if (!last) {
-        float* part = partials + int64_t(it.w) * pstride;
-        if (active) *reinterpret_cast<float4*>(part + fo) = acc;
+      if (last && active) {
+        st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, s > 0.f ? 1.f / s : 0.f, epilogue));
         if (head_leader) {
-          part[stats + head] = m;
-          part[stats + heads + head] = s;
+          if (rowmax) rowmax[int64_t(it.x) * heads + head] = (count > 0 || it.w >= 0) && m != -INFINITY ? m : 0.f;
+          if (rowsum) rowsum[int64_t(it.x) * heads + head] = s;
         }
-        __threadfence();
-        __syncwarp(group_mask<LANES>(lane));
-        if (l == 0) chain_publish(flags + it.w);
       }
-    }
-    if (last && active) {
-      st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, s > 0.f ? 1.f / s : 0.f, epilogue));
-      if (head_leader) {
-        if (rowmax) rowmax[int64_t(it.x) * heads + head] = (m == -INFINITY) ? 0.f : m;
-        if (rowsum) rowsum[int64_t(it.x) * heads + head] = s;
-      }
-    }
-  });
+    });
+    first = __shfl_sync(0xffffffffu, pending, 0);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// er_stats: per column block and head, max er and max -er as ordered-int codes (atomicMax on zeroed words)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+er_stats_kernel(const float* __restrict__ er, int64_t lder, int64_t num_sources, int64_t col_block, int heads,
+                uint32_t* __restrict__ stats) {
+  // lane -> head (heads is a power of two <= 32), 32/heads rows per warp step
+  const int lane = threadIdx.x & 31;
+  const int h = lane & (heads - 1);
+  const int rows_per_step = 32 / heads;
+  const int64_t cb = blockIdx.y;
+  const int64_t lo = col_block > 0 ? cb * col_block : 0;
+  const int64_t hi = col_block > 0 ? (lo + col_block < num_sources ? lo + col_block : num_sources) : num_sources;
+  const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float mx = -INFINITY, mn = INFINITY;
+  bool seen = false;
+  for (int64_t r = lo + warp * rows_per_step + lane / heads; r < hi; r += warps * rows_per_step) {
+    const float v = __ldg(er + r * lder + h);
+    mx = fmaxf(mx, v);
+    mn = fminf(mn, v);
+    seen = true;
+  }
+  // lanes with the same head: xor offsets heads, 2*heads, ...
+  for (int o = heads; o < 32; o <<= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    seen = __shfl_xor_sync(0xffffffffu, int(seen), o) || seen;
+  }
+  if (lane < heads && seen) {
+    atomicMax(stats + (cb * 2) * heads + h, ordered_code(mx));
+    atomicMax(stats + (cb * 2 + 1) * heads + h, ordered_code(-mn));
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -694,25 +857,32 @@ static int lanes_for(int f) {
   return l < 4 ? 4 : l;
 }
 
-// the work list and the chain state every aggregation launch takes
-struct WorkList {
-  const int4* items;
-  int64_t num_items;
-  const int32_t* row_slots;
-  int64_t num_slots;
-  const int32_t* indices;
-  float* partials;
-  int32_t* chain_flags;
-};
+// persistent grid: as many CTAs as fit on the device at once (or fewer when the list is short)
+template <typename K>
+static int resident_ctas(K kernel) {
+  static int cached = 0;          // one static per kernel instantiation
+  if (cached > 0) return cached;
+  int per_sm = 0, dev = 0, sms = kNumSMs;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kAggThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cached = per_sm * sms;
+  return cached;
+}
+
+template <typename K>
+static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f) {
+  const int64_t need = (num_items * lanes + kAggThreads - 1) / kAggThreads;
+  const int64_t cap = resident_ctas(kernel);
+  return dim3((unsigned)(need < cap ? need : cap), (unsigned)((f + 127) / 128));
+}
 
 template <int LANES>
-static void dispatch_aggregate(const CachePolicies& pol, int wkind, bool div, dim3 grid, cudaStream_t st, const WorkList& wl, const float* w,
-                               int wh, const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo,
-                               int f, int epi) {
-#define GTA_AGG(K, D)                                                                                             \
-  aggregate_kernel<LANES, K, D><<<grid, kAggThreads, 0, st>>>(wl.items, wl.num_items, wl.row_slots, wl.num_slots, \
-                                                              wl.indices, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi, \
-                                                              wl.partials, wl.chain_flags, pol.stream, pol.keep)
+static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkList& wl, const float* w, int wh,
+                               const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo, int f,
+                               int epi) {
+#define GTA_AGG(K, D)                                                                                          \
+  aggregate_kernel<LANES, K, D><<<persistent_grid(aggregate_kernel<LANES, K, D>, wl.num_items, LANES, f),       \
+                                  kAggThreads, 0, st>>>(wl, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi)
   if (wkind == 0) GTA_AGG(0, false);
   else if (wkind == 1 && !div) GTA_AGG(1, false);
   else if (wkind == 1 && div) GTA_AGG(1, true);
@@ -722,13 +892,13 @@ static void dispatch_aggregate(const CachePolicies& pol, int wkind, bool div, di
 }
 
 template <int H>
-static int dispatch_gat(const CachePolicies& pol, int lanes, dim3 grid, cudaStream_t st, const WorkList& wl, const float* el, const float* er,
+static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const float* el, const float* er,
                         int64_t lder, float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int f, int epi,
-                        float* rowmax, float* rowsum) {
-#define GTA_GAT(L)                                                                                                 \
-  gat_aggregate_kernel<L, H><<<grid, kAggThreads, 0, st>>>(wl.items, wl.num_items, wl.row_slots, wl.num_slots,     \
-                                                           wl.indices, el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi, \
-                                                           rowmax, rowsum, wl.partials, wl.chain_flags, pol.stream, pol.keep)
+                        float* rowmax, float* rowsum, const uint32_t* er_stats, int64_t col_block) {
+#define GTA_GAT(L)                                                                                              \
+  gat_aggregate_kernel<L, H><<<persistent_grid(gat_aggregate_kernel<L, H>, wl.num_items, L, f), kAggThreads, 0, \
+                               st>>>(wl, el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi, rowmax,  \
+                                     rowsum, er_stats, col_block)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
     case 8: if (H <= 8) { GTA_GAT(8); return GTA_OK; } break;
@@ -739,14 +909,28 @@ static int dispatch_gat(const CachePolicies& pol, int lanes, dim3 grid, cudaStre
   return GTA_ERR_UNSUPPORTED;
 }
 
-// common argument checks + the RESET phase (clear the chain flags of every feature window)
-static int prepare_worklist(const char* who, WorkList& wl, int32_t f, int32_t phases, cudaStream_t st) {
-  GTA_REQUIRE(wl.num_slots == 0 || (wl.partials && wl.row_slots && wl.chain_flags),
-              "%s: partials, row_slots and chain_flags are required for %lld slots", who, (long long)wl.num_slots);
+// common argument checks, the RESET phase (clear the chain flags of every feature window) and the item
+// counters (cleared before every launch).  chain_state = [windows][num_slots] flags, then [windows] counters.
+static int prepare_worklist(const char* who, WorkList& wl, int32_t* chain_state, int32_t f, int32_t phases,
+                            cudaStream_t st) {
+  GTA_REQUIRE(chain_state, "%s: chain_state is required (chain flags and the item counters live there)", who);
+  GTA_REQUIRE(wl.num_slots == 0 || (wl.partials && wl.row_slots),
+              "%s: partials and row_slots are required for %lld slots", who, (long long)wl.num_slots);
+  const size_t windows = size_t((f + 127) / 128);
+  wl.chain_flags = chain_state;
+  wl.work_counter = chain_state + windows * size_t(wl.num_slots);
   if ((phases & GTA_PHASE_RESET) && wl.num_slots > 0) {
-    const size_t windows = size_t((f + 127) / 128);
     GTA_CUDA(cudaMemsetAsync(wl.chain_flags, 0, windows * size_t(wl.num_slots) * sizeof(int32_t), st));
     count_launch();
+  }
+  if ((phases & GTA_PHASE_MAIN) && wl.num_items > 0) {
+    GTA_CUDA(cudaMemsetAsync(wl.work_counter, 0, windows * sizeof(int32_t), st));
+    count_launch();
+    CachePolicies pol;
+    int rc = cache_policies(&pol);
+    if (rc != GTA_OK) return rc;
+    wl.pol_stream = pol.stream;
+    wl.pol_keep = pol.keep;
   }
   return GTA_OK;
 }
@@ -762,11 +946,12 @@ int32_t gta_gat_partial_stride(int32_t f, int32_t heads) { return gat_partial_st
 int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
                       const int32_t* indices, int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f, int32_t epilogue,
-                      float* partials, int32_t* chain_flags, int32_t phases, void* stream_) {
+                      float* partials, int32_t* chain_state, int32_t phases, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
-  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, chain_flags};
-  int rc = prepare_worklist("gta_aggregate_f32", wl, f, phases, st);
+  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_aggregate_f32: bad item count");
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 0, 0};
+  int rc = prepare_worklist("gta_aggregate_f32", wl, chain_state, f, phases, st);
   if (rc != GTA_OK) return rc;
   if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
@@ -784,31 +969,49 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
       return GTA_ERR_UNSUPPORTED;
     }
   }
-  CachePolicies pol;
-  rc = cache_policies(&pol);
-  if (rc != GTA_OK) return rc;
-  int lanes = lanes_for(f);
-  int64_t threads = num_items * lanes;
-  dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
-  switch (lanes) {
-    case 4: dispatch_aggregate<4>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    case 8: dispatch_aggregate<8>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    case 16: dispatch_aggregate<16>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    default: dispatch_aggregate<32>(pol, wkind, div, grid, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+  switch (lanes_for(f)) {
+    case 4: dispatch_aggregate<4>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 8: dispatch_aggregate<8>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 16: dispatch_aggregate<16>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    default: dispatch_aggregate<32>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
   }
   GTA_CHECK_LAUNCH("aggregate_kernel");
+  return GTA_OK;
+}
+
+int gta_er_stats(const float* er, int64_t lder, int64_t num_sources, int64_t col_block, int32_t heads,
+                 uint32_t* stats, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  GTA_REQUIRE(er && stats && num_sources >= 0 && lder >= heads, "gta_er_stats: bad arguments");
+  if (heads < 1 || heads > 32 || (heads & (heads - 1)) != 0) {
+    set_error("gta_er_stats: heads=%d is not a power of two <= 32 (run the aggregation without er_stats)", heads);
+    return GTA_ERR_UNSUPPORTED;
+  }
+  const int64_t n_cb = (col_block > 0 && col_block < num_sources) ? (num_sources + col_block - 1) / col_block : 1;
+  GTA_REQUIRE(n_cb <= 65535, "gta_er_stats: %lld column blocks", (long long)n_cb);
+  GTA_CUDA(cudaMemsetAsync(stats, 0, size_t(n_cb) * 2 * heads * sizeof(uint32_t), st));
+  count_launch();
+  if (num_sources == 0) return GTA_OK;
+  const int64_t rows_per_block = n_cb > 1 ? col_block : num_sources;
+  int64_t ctas = (rows_per_block * heads + 256 * 8 - 1) / (256 * 8);        // about 8 rows per thread
+  if (ctas < 1) ctas = 1;
+  if (ctas > 4 * kNumSMs) ctas = 4 * kNumSMs;
+  er_stats_kernel<<<dim3((unsigned)ctas, (unsigned)n_cb), 256, 0, st>>>(er, lder, num_sources, n_cb > 1 ? col_block : 0,
+                                                                         heads, stats);
+  GTA_CHECK_LAUNCH("er_stats_kernel");
   return GTA_OK;
 }
 
 int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
                           const int32_t* indices, const float* el, const float* er, int64_t lder, int32_t heads,
                           float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
-                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_flags,
-                          int32_t phases, void* stream_) {
+                          int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_state,
+                          const uint32_t* er_stats, int64_t col_block, int32_t phases, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
-  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, chain_flags};
-  int rc = prepare_worklist("gta_gat_aggregate_f32", wl, f, phases, st);
+  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_gat_aggregate_f32: bad item count");
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 0, 0};
+  int rc = prepare_worklist("gta_gat_aggregate_f32", wl, chain_state, f, phases, st);
   if (rc != GTA_OK) return rc;
   if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
@@ -823,18 +1026,15 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
     set_error("gta_gat_aggregate_f32: per-head width f/heads=%d is not a multiple of 4", f / heads);
     return GTA_ERR_UNSUPPORTED;
   }
-  CachePolicies pol;
-  rc = cache_policies(&pol);
-  if (rc != GTA_OK) return rc;
-  int lanes = lanes_for(f);
-  int64_t threads = num_items * lanes;
-  dim3 grid((unsigned)((threads + kAggThreads - 1) / kAggThreads), (unsigned)((f + 127) / 128));
+  // the bound path does not track the true row maximum: callers that want it back run the online softmax
+  if (rowmax != nullptr) er_stats = nullptr;
+  const int lanes = lanes_for(f);
   // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
   // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint)
   const bool staged = heads == 1 || heads == 2 || heads == 4;
   if (staged) {
     rc = GTA_ERR_UNSUPPORTED;
-#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(pol, lanes, grid, st, wl, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum)
+#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, st, wl, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, col_block)
     switch (heads) {
       case 1: GTA_GAT_H(1); break;
       case 2: GTA_GAT_H(2); break;
@@ -846,10 +1046,10 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
       return rc;
     }
   } else {
-#define GTA_LLH(L)                                                                                                   \
-  gat_aggregate_llh_kernel<L><<<grid, kAggThreads, 0, st>>>(wl.items, wl.num_items, wl.row_slots, wl.num_slots,      \
-                                                            wl.indices, el, er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, \
-                                                            f, epilogue, rowmax, rowsum, wl.partials, wl.chain_flags, pol.stream, pol.keep)
+#define GTA_LLH(L)                                                                                                 \
+  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f), kAggThreads, 0,  \
+                                st>>>(wl, el, er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epilogue, \
+                                      rowmax, rowsum, er_stats, col_block)
     switch (lanes) {
       case 4: GTA_LLH(4); break;
       case 8: GTA_LLH(8); break;

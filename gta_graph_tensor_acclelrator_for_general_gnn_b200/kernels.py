@@ -99,14 +99,12 @@ _agg_ws = _Workspace()      # chain state (partials + flags) of gta_aggregate_f3
 
 
 def _chain_state(ws: _Workspace, num_slots: int, stride: int, f: int, device):
-    """(partials, flags) pointers inside one workspace: num_slots*stride floats, then one int32 flag per
-    slot and 128-feature window."""
-    if num_slots == 0:
-        return None, None
+    """(partials, chain_state) pointers inside one workspace: num_slots*stride floats, then per 128-feature
+    window num_slots int32 chain flags, then one int32 item counter per window (always present)."""
     windows = (f + 127) // 128
     base = (num_slots * stride + 3) // 4 * 4
-    buf = ws.get(base + num_slots * windows, device)
-    return buf.data_ptr(), buf.data_ptr() + 4 * base
+    buf = ws.get(base + (num_slots + 1) * windows, device)
+    return (buf.data_ptr() if num_slots else None), buf.data_ptr() + 4 * base
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -202,13 +200,13 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
         wmode = _cabi.W_EDGE_DIV if rowden is not None else _cabi.W_EDGE
         if rowden is not None:
             rowden = rowden.contiguous()
-    partials, flags = _chain_state(_agg_ws, sched.num_slots, f, f, x.device)
+    partials, chain = _chain_state(_agg_ws, sched.num_slots, f, f, x.device)
 
     def launch(first, count, phases):
         _cabi.check(lib.gta_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
                                           sched.num_slots, _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh,
                                           _cabi.ptr(rowden), _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
-                                          partials, flags, phases, _stream()), "gta_aggregate_f32")
+                                          partials, chain, phases, _stream()), "gta_aggregate_f32")
     _launch_blocks(launch, sched, block_events)
     return o
 
@@ -216,11 +214,28 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
 _gat_ws = _Workspace()      # chain state of the single-pass GAT kernel
 
 
+def er_stats(er: torch.Tensor, col_block: int = 0) -> torch.Tensor | None:
+    """Ordered-int codes of ``max er`` / ``max -er`` per column block and head (``gta_er_stats``), or None
+    when the head count is not a power of two (the aggregation then runs the online softmax)."""
+    lib = _cabi.load()
+    n, heads = int(er.shape[0]), int(er.shape[1])
+    if heads < 1 or heads > 32 or heads & (heads - 1):
+        return None
+    n_cb = int(lib.gta_schedule_col_blocks(n, col_block))
+    stats = torch.empty((n_cb, 2, heads), dtype=torch.int32, device=er.device)
+    lder = int(er.stride(0)) if n > 1 else max(int(er.stride(0)), heads)
+    _cabi.check(lib.gta_er_stats(_cabi.ptr(er), lder, n, col_block if n_cb > 1 else 0, heads, _cabi.ptr(stats),
+                                 _stream()), "gta_er_stats")
+    return stats
+
+
 @_timed("gta_gat_aggregate_f32")
 def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.Tensor, slope: float = LEAKY_SLOPE,
                   epilogue: int = _cabi.EPI_ELU, sched: Schedule | None = None, out: torch.Tensor | None = None,
-                  want_stats: bool = False, block_events=None):
-    """GAT ops 3-13 in one pass (online softmax): returns ``out`` or ``(out, rowmax, rowsum)``."""
+                  want_stats: bool = False, block_events=None, bounded: bool = True):
+    """GAT ops 3-13 in one pass: returns ``out`` or ``(out, rowmax, rowsum)``.  ``bounded`` shifts the softmax
+    by the per-(row, column block) bound ``leaky(el + max er)`` where the block's er range allows it (see
+    ``gta_er_stats``); ``False`` or ``want_stats`` runs the online softmax with a running maximum."""
     lib = _cabi.load()
     _require_cuda(el, er, z)
     sched = sched or g.schedule_for(_ld(z) * 4)
@@ -237,14 +252,18 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
         rowmax = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
         rowsum = torch.empty((rows, heads), dtype=torch.float32, device=z.device)
     stride = int(lib.gta_gat_partial_stride(f, heads))
-    partials, flags = _chain_state(_gat_ws, sched.num_slots, stride, f, z.device)
+    partials, chain = _chain_state(_gat_ws, sched.num_slots, stride, f, z.device)
+    col_block = sched.col_block if sched.num_blocks > 1 else 0
+    # with chunk events the table is still arriving: its er range is not known before the launch
+    stats = er_stats(er, col_block) if bounded and not want_stats and block_events is None else None
 
     def launch(first, count, phases):
         _cabi.check(lib.gta_gat_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
                                               sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el),
                                               _cabi.ptr(er), lder, heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o),
                                               _ld(o), f, epilogue, _cabi.ptr(rowmax), _cabi.ptr(rowsum),
-                                              partials, flags, phases, _stream()), "gta_gat_aggregate_f32")
+                                              partials, chain, _cabi.ptr(stats), col_block, phases, _stream()),
+                    "gta_gat_aggregate_f32")
     _launch_blocks(launch, sched, block_events)
     if want_stats:
         return o, rowmax, rowsum

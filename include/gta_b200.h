@@ -168,28 +168,41 @@ int gta_gemm_get_mode(void);
  * interpreter.py:575-638) and plain COMP_ADD gather (interpreter.py:85-106):
  *   out[i,:] = epi( sum_{k in row i, ascending src} weight(k) (x) x[src(k),:] )
  * `w` is [E,wh] (wh = 1 scalar per edge, or wh = heads, head h covering f/wh features);
- * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Work comes from gta_schedule_build.  Rows that own several
- * items are folded in slot order INSIDE the kernel (each item waits for its predecessor's state, no
- * merge launch): `partials` holds num_slots*f floats, `chain_flags` num_slots*ceil(f/128) int32
- * (cleared by GTA_PHASE_RESET); both may be NULL when num_slots == 0.
+ * `rowden` is [N,wh] for GTA_W_EDGE_DIV.  Work comes from gta_schedule_build; the launch is persistent
+ * (warps take items from a counter in work-list order).  Rows that own several items are folded in slot
+ * order INSIDE the kernel (each item waits for its predecessor's state, no merge launch): `partials`
+ * holds num_slots*f floats (NULL when num_slots == 0); `chain_state` holds, for W = ceil(f/128) feature
+ * windows, W*num_slots int32 chain flags (cleared by GTA_PHASE_RESET) followed by W int32 item counters
+ * (cleared by every MAIN launch) and is always required.
  * ------------------------------------------------------------------------------------ */
 int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
                       int64_t num_slots, const int32_t* indices,
                       int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
-                      int32_t epilogue, float* partials, int32_t* chain_flags, int32_t phases,
+                      int32_t epilogue, float* partials, int32_t* chain_state, int32_t phases,
                       void* stream);
+
+/* Range of the GAT source-side logits per column block: stats[cb][0][h] / stats[cb][1][h] = ordered-int
+ * codes of max_j er[j,h] and max_j -er[j,h] over the sources j of column block cb (col_block source ids
+ * per block, <= 0: one block; 2*H uint32 per block).  heads must be a power of two <= 32
+ * (GTA_ERR_UNSUPPORTED otherwise).  gta_gat_aggregate_f32 uses it to shift the softmax by the bound
+ * leaky_relu(el[i,h] + max er) instead of a running maximum (genGraphOP.py:56-58 ops 6-8). */
+int gta_er_stats(const float* er, int64_t lder, int64_t num_sources, int64_t col_block, int32_t heads,
+                 uint32_t* stats, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * GAT edge phase in ONE pass (ops 3-13 of genGraphOP.py:52-62; ISA blocks
- * [4,5,6,7,8] + [3,9,10,11,12,13] of SURVEY Appendix B3 collapsed, online softmax):
+ * [4,5,6,7,8] + [3,9,10,11,12,13] of SURVEY Appendix B3 collapsed):
  *   s = el[i,h] + er[j,h]; e = leaky_relu(s, slope); alpha = softmax_row(e);
  *   out[i,:] = epi( sum_k alpha[k,h(f)] * z[j,:] )
  * el [rows,H] (dense) is indexed by LOCAL row; er (row stride `lder` elements, so it can live in
  * the same gathered table as z: [.., F | H] per source) and z by source id.
  * partials: num_slots * gta_gat_partial_stride(f,H) floats (acc[f], then (max[H], sum[H]) padded to 4
- * per 128-feature window); chain_flags as for gta_aggregate_f32.
- * Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip).
+ * per 128-feature window); chain_state as for gta_aggregate_f32.
+ * er_stats (from gta_er_stats with the same col_block; NULL: online softmax with a running maximum):
+ * where a block's er range is below 60 the softmax is shifted by a per-(row, block) bound -- same result
+ * within rounding, no warp reductions.  Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip;
+ * asking for rowmax selects the online path, which tracks the true maximum).
  * ------------------------------------------------------------------------------------ */
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads);
 int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
@@ -197,7 +210,8 @@ int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t
                           const float* el, const float* er, int64_t lder, int32_t heads, float slope,
                           const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum,
-                          float* partials, int32_t* chain_flags, int32_t phases, void* stream);
+                          float* partials, int32_t* chain_state, const uint32_t* er_stats,
+                          int64_t col_block, int32_t phases, void* stream);
 
 /* GAT block [4,5,6,7,8] alone (COMP_ADD 6, COMP_SF 7, STORE_E 7, COMP_ADD 8 gather):
  *   p[k,h] = exp(leaky_relu(el[i,h] + er[j,h]) - rowmax[i,h]),  rowsum[i,h] = sum_k p[k,h].

@@ -120,6 +120,24 @@ def gat_edge_phase(indptr, indices, el, er, z, slope=0.2, dtype=np.float32, row_
     return out
 
 
+def gat_edge_phase_scaled(indptr, indices, el, er, z, zabs, slope=0.2, row_begin=0, row_end=None, activation=True):
+    """fp64 edge phase plus the per-element error scale ``sum_k alpha_k * zabs[src k]`` (``zabs = |X|.|W|``):
+    returns ``(out, scale)``.  ``el`` is indexed by (row - row_begin); er, z, zabs by source id."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    el, er, z, zabs = (np.ascontiguousarray(a, dtype=np.float64) for a in (el, er, z, zabs))
+    row_end = indptr.shape[0] - 1 if row_end is None else row_end
+    f = z.shape[1]
+    heads = er.shape[1]
+    assert f <= 1024 and heads <= 64 and f % heads == 0 and zabs.shape == z.shape
+    out = np.empty((row_end - row_begin, f), dtype=np.float64)
+    scale = np.empty_like(out)
+    load().gta_oracle_gat_scaled_f64(_p(indptr), _p(indices), _p(el), _p(er), C.c_int(heads), C.c_double(slope), _p(z),
+                                     _p(zabs), C.c_int64(f), _p(out), _p(scale), C.c_int64(f), C.c_int64(row_begin),
+                                     C.c_int64(row_end), C.c_int(f), C.c_int(int(activation)))
+    return out, scale
+
+
 def gat_layer(indptr, indices, x, w, al, ar, dtype=np.float32, row_begin=0, row_end=None):
     """Whole GAT layer (ops 0-13) on host cores: GEMM, projections, edge phase."""
     z = gemm(x, w, dtype)

@@ -122,6 +122,52 @@ DEFINE_SPMM(gta_oracle_spmm_f64, double, double)
 DEFINE_GAT(gta_oracle_gat_f32, float, float, expf, expm1f)
 DEFINE_GAT(gta_oracle_gat_f64, double, double, exp, expm1)
 
+/* The same edge phase in double precision, returning beside out[i,c] the error scale of that element:
+ *   scale[i,c] = sum_k alpha[k,h(c)] * zabs[j,c],   zabs = |X|.|W|  (what bounds the rounding error of Z[j,c]).
+ * This is the `rowscale` of the stated fp32 tolerance |y - y64| <= 1e-5 |y64| + 1e-5 rowscale
+ *  for a whole GAT layer; the at-scale parity checks (bench.py, tests/) use it. */
+void gta_oracle_gat_scaled_f64(const int64_t* indptr, const int32_t* indices, const double* el, const double* er,
+                               int heads, double slope, const double* z, const double* zabs, int64_t ldz,
+                               double* out, double* scale, int64_t ldo, int64_t row_begin, int64_t row_end,
+                               int f, int activation) {
+  const int d = f / heads;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t i = row_begin; i < row_end; ++i) {
+    double acc[1024], sc[1024], mx[64], sm[64];
+    const double* eli = el + (i - row_begin) * heads;
+    for (int h = 0; h < heads; ++h) { mx[h] = -INFINITY; sm[h] = 0; }
+    for (int c = 0; c < f; ++c) { acc[c] = 0; sc[c] = 0; }
+    for (int64_t e = indptr[i]; e < indptr[i + 1]; ++e) {
+      const double* erj = er + (int64_t)indices[e] * heads;
+      for (int h = 0; h < heads; ++h) {
+        double s = eli[h] + erj[h];
+        s = s > 0 ? s : s * slope;
+        if (s > mx[h]) mx[h] = s;
+      }
+    }
+    for (int64_t e = indptr[i]; e < indptr[i + 1]; ++e) {
+      const int32_t j = indices[e];
+      const double* erj = er + (int64_t)j * heads;
+      const double* zj = z + (int64_t)j * ldz;
+      const double* aj = zabs + (int64_t)j * ldz;
+      for (int h = 0; h < heads; ++h) {
+        double s = eli[h] + erj[h];
+        s = s > 0 ? s : s * slope;
+        const double p = exp(s - mx[h]);
+        sm[h] += p;
+        for (int c = h * d; c < (h + 1) * d; ++c) { acc[c] += p * zj[c]; sc[c] += p * aj[c]; }
+      }
+    }
+    for (int c = 0; c < f; ++c) {
+      const double s = sm[c / d];
+      double o = s > 0 ? acc[c] / s : 0;
+      if (activation) o = o > 0 ? o : expm1(o);
+      out[(i - row_begin) * ldo + c] = o;
+      scale[(i - row_begin) * ldo + c] = s > 0 ? sc[c] / s : 0;
+    }
+  }
+}
+
 /* GAT ops 1,2: el = Z.Al, er = Z.Ar with [f,heads] weights */
 #define DEFINE_PROJ(NAME, T_IN, T_ACC)                                                        \
   void NAME(const T_IN* z, int64_t ldz, const T_IN* a, T_IN* out, int64_t n, int f, int heads) { \

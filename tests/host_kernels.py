@@ -106,7 +106,7 @@ def gat_logits(g, el, er, slope=LEAKY_SLOPE, stabilize=True):
 
 
 def gat_aggregate(g, el, er, z, slope=LEAKY_SLOPE, epilogue=_cabi.EPI_ELU, sched=None, out=None,
-                  want_stats=False, block_events=None):
+                  want_stats=False, block_events=None, bounded=True):
     p, rowmax, rowsum = gat_logits(g, el, er, slope, True)
     alpha = p / rowsum[_rows(g)]
     res = _epilogue(_segment_sum(z[g.indices.long()] * _spread(alpha, z.shape[1]), g), epilogue)

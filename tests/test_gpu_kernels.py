@@ -211,14 +211,58 @@ def test_gat_single_pass(T, name, n, e, seed, i0, f, heads, chunk, col_block):
     er32 = ref["er"].astype(np.float32)
     # oracle on the SAME fp32 inputs the kernel sees
     r2 = _gat_from_z(indptr, indices, z32, el32, er32)
-    out, rowmax, rowsum = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)),
-                                            sched=dg.schedule(chunk, col_block), want_stats=True)
-    out2 = T.k.gat_aggregate(dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)), sched=dg.schedule(chunk, col_block))
-    assert T.torch.equal(out, out2), "not bitwise reproducible"
+    sched = dg.schedule(chunk, col_block)
+    args = (dg, _dev(T, el32), _dev(T, er32), T.k.to_table(_dev(T, z32)))
+    # want_stats tracks the true row maximum: the online-softmax path
+    out, rowmax, rowsum = T.k.gat_aggregate(*args, sched=sched, want_stats=True)
+    assert T.torch.equal(out, T.k.gat_aggregate(*args, sched=sched, bounded=False)), "online path not reproducible"
+    # default: softmax shifted by the per-(row, column block) bound leaky(el + max er)
+    out_b = T.k.gat_aggregate(*args, sched=sched)
+    assert T.torch.equal(out_b, T.k.gat_aggregate(*args, sched=sched)), "bound path not bitwise reproducible"
     scale = O.gat_rowscale(indptr, indices, z32.astype(np.float64), r2["alpha"])
-    assert_close_rowscale(out.cpu().numpy(), r2["Y"], scale, what=f"GAT f={f} H={heads} chunk={chunk}")
+    assert_close_rowscale(out.cpu().numpy(), r2["Y"], scale, what=f"GAT online f={f} H={heads} chunk={chunk}")
+    assert_close_rowscale(out_b.cpu().numpy(), r2["Y"], scale, what=f"GAT bound f={f} H={heads} chunk={chunk}")
     np.testing.assert_allclose(rowmax.cpu().numpy(), r2["rowmax"], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(rowsum.cpu().numpy(), r2["S"], rtol=2e-5)
+
+
+def test_er_stats_codes(T):
+    """gta_er_stats: per column block and head, max er and max -er (ordered-int codes decode to the exact floats)."""
+    rng = np.random.default_rng(5)
+    er = (rng.standard_normal((1000, 4)) * 3).astype(np.float32)
+    er[10, 2] = -0.0
+    for col_block in (0, 256, 999):
+        st = T.k.er_stats(_dev(T, er), col_block).cpu().numpy().view(np.uint32)
+        blocks = 1 if col_block == 0 else -(-1000 // col_block)
+        assert st.shape == (blocks, 2, 4)
+        dec = np.where(st & 0x80000000, st & 0x7FFFFFFF, ~st).astype(np.uint32).view(np.float32)
+        for b in range(blocks):
+            lo, hi = (0, 1000) if col_block == 0 else (b * col_block, min((b + 1) * col_block, 1000))
+            np.testing.assert_array_equal(dec[b, 0], er[lo:hi].max(axis=0))
+            np.testing.assert_array_equal(-dec[b, 1], er[lo:hi].min(axis=0))
+    assert T.k.er_stats(_dev(T, np.zeros((8, 3), np.float32))) is None          # 3 heads: no power of two
+
+
+@pytest.mark.parametrize("heads,f", [(4, 128), (8, 128), (2, 16)])
+@pytest.mark.parametrize("col_block", [0, 700])
+def test_gat_bound_falls_back_when_the_er_range_is_wide(T, heads, f, col_block):
+    """Source logits spanning far more than the bound path's exponent budget (60): those column blocks must take the
+    online softmax; a narrow block beside a wide one keeps the bound.  Either way the result is the oracle's."""
+    g = _graph("skew", 3000, 90000, 2, 3.0)
+    n = g.num_nodes
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    rng = np.random.default_rng(7)
+    z = rng.standard_normal((n, f), dtype=np.float32)
+    el = rng.standard_normal((n, heads), dtype=np.float32)
+    er = rng.standard_normal((n, heads), dtype=np.float32)
+    er[:700] *= 80.0          # the first column block (or the whole table) spans about +-300
+    r = _gat_from_z(indptr, indices, z, el, er)
+    sched = dg.schedule(1024, col_block)
+    out = T.k.gat_aggregate(dg, _dev(T, el), _dev(T, er), T.k.to_table(_dev(T, z)), sched=sched)
+    assert T.torch.equal(out, T.k.gat_aggregate(dg, _dev(T, el), _dev(T, er), T.k.to_table(_dev(T, z)), sched=sched))
+    scale = O.gat_rowscale(indptr, indices, z.astype(np.float64), r["alpha"])
+    assert_close_rowscale(out.cpu().numpy(), r["Y"], scale, what=f"wide er range H={heads} col_block={col_block}")
 
 
 def _gat_from_z(indptr, indices, z, el, er):

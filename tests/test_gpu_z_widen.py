@@ -6,6 +6,7 @@ import pytest
 
 import test_cpu_executor as C
 import test_gpu_executor as shared
+from conftest import assert_close_rowscale
 from oracle import gta_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -26,13 +27,13 @@ def test_dgn_pna_match_oracle(network, reorder, plan_kind, fuse):
     g, indptr, indices, dg = shared._graph(rt, "cora")
     node_inputs, weights, edge_inputs = shared._inputs(op_info, g.num_nodes, g.num_edges)
     sem = O.NETWORK_SEMANTICS.get((network, reorder), {})
-    ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, semantics=sem, stabilize=True)
+    ref, ref_scale = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, semantics=sem, stabilize=True, return_scale=True)
     dev = lambda d: {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     out, log = executor.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs), network=network,
                                 is_reorder=reorder, fuse_across_blocks=fuse, return_log=True)
     (p, y), = out.items()
     y64 = ref[p]
-    np.testing.assert_allclose(y.cpu().numpy(), y64, rtol=1e-4, atol=2e-5 * np.abs(y64).max(), err_msg=str(log))
+    assert_close_rowscale(y.cpu().numpy(), y64, ref_scale[p], what=str(log))
     assert any(k == "gta_gemm_f32:edges" for k, _ in log)
 
 
@@ -86,11 +87,11 @@ def test_order_c_gather_on_device(fuse):
         op["INPUT"]["feature_number"] = [e if op["TYPE"] in ("applyedge", "gather") else n] * len(op["INPUT"]["feature_number"])
     records = lowering.lower(op_info, [[0], [1, 2, 3]], [[64, 1], [64, 1]], n)
     node_inputs, weights, edge_inputs = shared._inputs(op_info, n, e)
-    ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs)
+    ref, ref_scale = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, return_scale=True)
     dev = lambda d: {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     out, log = executor.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs),
                                 fuse_across_blocks=fuse, return_log=True)
-    np.testing.assert_allclose(out[3].cpu().numpy(), ref[3], rtol=1e-4, atol=2e-5 * np.abs(ref[3]).max())
+    assert_close_rowscale(out[3].cpu().numpy(), ref[3], ref_scale[3])
     assert any(k == "gta_aggregate_f32:by_source" for k, _ in log)
     again = executor.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs), fuse_across_blocks=fuse)
     assert torch.equal(out[3], again[3])       # deterministic
@@ -112,11 +113,11 @@ def test_edge_mm_feeding_a_gather_on_device(plan, fuse):
     op_info = C.mm_then_gather_case(n, e)
     records = lowering.lower(op_info, plan, [[64, 1]] * len(plan), n)
     node_inputs, weights, edge_inputs = shared._inputs(op_info, n, e)
-    ref = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs)
+    ref, ref_scale = O.run_opgraph(op_info, indptr, indices, node_inputs, weights, edge_inputs, return_scale=True)
     dev = lambda d: {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     out, log = executor.execute(records, op_info, dg, dev(node_inputs), dev(weights), dev(edge_inputs),
                                 fuse_across_blocks=fuse, return_log=True)
-    np.testing.assert_allclose(out[5].cpu().numpy(), ref[5], rtol=1e-4, atol=2e-5 * np.abs(ref[5]).max(), err_msg=str(log))
+    assert_close_rowscale(out[5].cpu().numpy(), ref[5], ref_scale[5], what=str(log))
     names = [k for k, _ in log]
     stored_between = len(plan) == 2 and not fuse
     assert ("gta_gemm_f32:edges" in names) == stored_between and ("gta_gemm_f32:after_gather" in names) != stored_between

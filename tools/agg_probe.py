@@ -50,7 +50,9 @@ def main():
         for kind, ncb in [(k, c) for k in args.kinds for c in args.col_blocks]:
             sched = g.schedule(args.chunk, 0 if ncb <= 1 else -(-n // ncb))
             ev = [None] * sched.num_blocks if args.split_launch else None
+            # "gat": softmax shifted by the per-block bound (default); "gato": online softmax with a running maximum
             fn = (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched, block_events=ev)) if kind == "gat" else \
+                 (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched, block_events=ev, bounded=False)) if kind == "gato" else \
                  (lambda: kernels.aggregate(g, z, w, sched=sched, block_events=ev))
             for _ in range(3):
                 fn()
@@ -62,7 +64,7 @@ def main():
             t1.record()
             torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / args.iters
-            byt = e * (4 + f * 4 + (h * 4 if kind == "gat" else 4)) + n * (f * 4 + 8)
+            byt = e * (4 + f * 4 + (h * 4 if kind.startswith("gat") else 4)) + n * (f * 4 + 8)
             print(f"{name:8s} {kind:5s} cb={ncb} chunk={args.chunk} N={n} E={e} F={f} H={h} items={sched.num_items} slots={sched.num_slots} "
                   f"{ms:8.3f} ms  {e / ms / 1e6:7.2f} GTEPS  {byt / ms / 1e6:8.1f} GB/s algorithmic", flush=True)
         del g, z, el, er, w
