@@ -31,19 +31,37 @@ namespace gta {
 #ifndef GTA_AGG_THREADS
 #define GTA_AGG_THREADS 128
 #endif
-#ifndef GTA_AGG_UNROLL
-#define GTA_AGG_UNROLL 8
-#endif
+// Resident CTAs per SM (caps the registers) and row loads in flight per lane, per kernel family.  Measured on
+// B200, Reddit shape, persistent launch (tools/agg_probe.py, gpurun_out/p2_probe.log):
+//   weighted aggregate   6x8: 3.36 ms   8x8: 3.29   8x4: 3.29   10x4: 3.13   (48 registers, no spills)
+//   GAT staged (H <= 4)  6x8: 3.89 ms   7x8: 3.88   8x8: 3.75   8x4: 3.49   10x4: 4.11 (spills)
+// More resident warps beat a deeper unroll: the kernels wait on L2 latency (long scoreboard), not on issue.
 #ifndef GTA_AGG_MINBLOCKS
-#define GTA_AGG_MINBLOCKS 6       // 128 threads x 6 blocks = 24 warps/SM => at most 80 registers (measured best)
+#define GTA_AGG_MINBLOCKS 10
+#endif
+#ifndef GTA_AGG_UNROLL
+#define GTA_AGG_UNROLL 4
+#endif
+#ifndef GTA_GAT_MINBLOCKS
+#define GTA_GAT_MINBLOCKS 8
+#endif
+#ifndef GTA_GAT_UNROLL
+#define GTA_GAT_UNROLL 4
+#endif
+#ifndef GTA_LLH_MINBLOCKS
+#define GTA_LLH_MINBLOCKS 6
+#endif
+#ifndef GTA_LLH_UNROLL
+#define GTA_LLH_UNROLL 8
 #endif
 #ifndef GTA_AGG_FASTEXP
 #define GTA_AGG_FASTEXP 1
 #endif
+#ifndef GTA_GAT_FORCE_LLH
+#define GTA_GAT_FORCE_LLH 0       // experiment: run the lane-local-head kernel for every head count
+#endif
 constexpr int kAggThreads = GTA_AGG_THREADS;
 constexpr int kAggWarps = kAggThreads / 32;
-constexpr int kUnroll = GTA_AGG_UNROLL;
-constexpr int kAggMinBlocks = GTA_AGG_MINBLOCKS;
 
 // floats per partial slot of the GAT kernel: acc[f] | per 128-feature window: max[H] | sum[H], padded to 16 bytes
 __host__ __device__ inline int gat_stats_stride(int heads) { return (2 * heads + 3) & ~3; }
@@ -191,8 +209,12 @@ __device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane) {
 //   WKIND 0: no weight, 1: scalar weight per edge (wh == 1), 2: per-head weight (wh > 1,
 //   (f / wh) % 4 == 0 so a lane's 4 features share a head)
 // ----------------------------------------------------------------------------------------
+constexpr int kAggUnroll = GTA_AGG_UNROLL;
+constexpr int kGatUnroll = GTA_GAT_UNROLL;
+constexpr int kLlhUnroll = GTA_LLH_UNROLL;
+
 template <int LANES, int WKIND, bool DIV>
-__global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
+__global__ void __launch_bounds__(kAggThreads, GTA_AGG_MINBLOCKS)
 aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const float* __restrict__ rowden,
                  const float* __restrict__ x, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
                  int f, int epilogue) {
@@ -248,25 +270,25 @@ aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const f
       __syncwarp();
       const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
       if (full) {
-        // whole batch, no predicates: kUnroll loads in flight, then their FMAs (the outer loop stays
+        // whole batch, no predicates: kAggUnroll loads in flight, then their FMAs (the outer loop stays
         // rolled: unrolled, ptxas hoists every load of the batch and spills)
         if (LANES < 32 || active) {
 #pragma unroll 1
-          for (int j = 0; j < LANES; j += kUnroll) {
-            uint4 ed[kUnroll / 2];
-            float4 v[kUnroll];
+          for (int j = 0; j < LANES; j += kAggUnroll) {
+            uint4 ed[kAggUnroll / 2];
+            float4 v[kAggUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll / 2; ++u)
+            for (int u = 0; u < kAggUnroll / 2; ++u)
               if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
-            for (int u = 0; u < kUnroll / 2; ++u) {
+            for (int u = 0; u < kAggUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
                 v[2 * u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
                 v[2 * u + 1] = ld_row_f32x4(row_ptr(xf, ed[u].z, row_bytes), pol_keep);
               }
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+            for (int u = 0; u < kAggUnroll; ++u) {
               if (j + u < LANES) {
                 float ws = __uint_as_float((u & 1) ? ed[u / 2].w : ed[u / 2].y);
                 if (WKIND == 2) {
@@ -280,11 +302,11 @@ aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const f
         }
       } else {
         const int nmax = (LANES == 32) ? n : LANES;
-        for (int j = 0; j < nmax; j += kUnroll) {
-          float4 v[kUnroll];
-          float wv[kUnroll];
+        for (int j = 0; j < nmax; j += kAggUnroll) {
+          float4 v[kAggUnroll];
+          float wv[kAggUnroll];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
+          for (int u = 0; u < kAggUnroll; ++u) {
             if (j + u < LANES) {
               const uint2 ed = mine[j + u];
               const bool ok = active && (j + u) < n;
@@ -302,7 +324,7 @@ aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const f
             }
           }
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
+          for (int u = 0; u < kAggUnroll; ++u)
             if (j + u < LANES) fma4(acc, wv[u], v[u]);
         }
       }
@@ -395,7 +417,7 @@ __device__ __forceinline__ bool block_bound(const uint32_t* __restrict__ er_stat
 }
 
 template <int LANES, int H>
-__global__ void __launch_bounds__(kAggThreads, (H <= 4) ? kAggMinBlocks : (kAggMinBlocks + 1) / 2)
+__global__ void __launch_bounds__(kAggThreads, (H <= 4) ? GTA_GAT_MINBLOCKS : (GTA_GAT_MINBLOCKS + 1) / 2)
 gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const float* __restrict__ er, int64_t lder,
                      float slope, const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out,
                      int64_t ldo, int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
@@ -510,21 +532,21 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
       if (full) {
         if (LANES < 32 || active) {
 #pragma unroll 1
-          for (int j = 0; j < LANES; j += kUnroll) {
-            uint4 ed[kUnroll / 2];
-            float4 v[kUnroll];
+          for (int j = 0; j < LANES; j += kGatUnroll) {
+            uint4 ed[kGatUnroll / 2];
+            float4 v[kGatUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll / 2; ++u)
+            for (int u = 0; u < kGatUnroll / 2; ++u)
               if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
-            for (int u = 0; u < kUnroll / 2; ++u) {
+            for (int u = 0; u < kGatUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
                 v[2 * u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
                 v[2 * u + 1] = ld_row_f32x4(row_ptr(zf, ed[u].z, row_bytes), pol_keep);
               }
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll / 2; ++u) {
+            for (int u = 0; u < kGatUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
                 fma4(acc, __uint_as_float(ed[u].y), v[2 * u]);
                 fma4(acc, __uint_as_float(ed[u].w), v[2 * u + 1]);
@@ -534,11 +556,11 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
         }
       } else {
         const int nmax = (LANES == 32) ? n : LANES;
-        for (int j = 0; j < nmax; j += kUnroll) {
-          float4 v[kUnroll];
-          float pv[kUnroll];
+        for (int j = 0; j < nmax; j += kGatUnroll) {
+          float4 v[kGatUnroll];
+          float pv[kGatUnroll];
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
+          for (int u = 0; u < kGatUnroll; ++u) {
             if (j + u < LANES) {
               const uint2 ed = mine[j + u];
               pv[u] = __uint_as_float(ed.y);
@@ -547,7 +569,7 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
             }
           }
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u)
+          for (int u = 0; u < kGatUnroll; ++u)
             if (j + u < LANES) fma4(acc, pv[u], v[u]);
         }
       }
@@ -618,12 +640,12 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
 // The staged kernel above keeps el/max/sum/er for ALL heads in every lane (5H registers: H = 16
 // spills and runs at a quarter of the H = 4 speed).  Here a lane tracks only the head its own 4
 // features belong to: one scalar er gather per edge (the 32 lanes of a row read the H
-// consecutive floats of er[j]: one wavefront), softmax over groups of kUnroll edges, no
+// consecutive floats of er[j]: one wavefront), softmax over groups of kLlhUnroll edges, no
 // per-head arrays, no shuffles.  Lanes of one head see the same edges in the same order, so their
 // (max, sum) are bit-identical.
 // ----------------------------------------------------------------------------------------
 template <int LANES>
-__global__ void __launch_bounds__(kAggThreads, kAggMinBlocks)
+__global__ void __launch_bounds__(kAggThreads, GTA_LLH_MINBLOCKS)
 gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const float* __restrict__ er, int64_t lder,
                          int heads, float slope, const float* __restrict__ z, const uint32_t row_bytes,
                          float* __restrict__ out, int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
@@ -685,25 +707,25 @@ gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const 
       __syncwarp();
       const int nmax = (LANES == 32) ? n : LANES;
 #pragma unroll 1
-      for (int j = 0; j < nmax; j += kUnroll) {
-        float e[kUnroll];
-        float4 v[kUnroll];
-        uint32_t id[kUnroll];
+      for (int j = 0; j < nmax; j += kLlhUnroll) {
+        float e[kLlhUnroll];
+        float4 v[kLlhUnroll];
+        uint32_t id[kLlhUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
+        for (int u = 0; u < kLlhUnroll; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < kLlhUnroll; ++u) {
           const bool ok = (j + u) < n;
           e[u] = ok ? leaky(elh + __ldg(row_ptr(erh, id[u], er_bytes)), slope) : -INFINITY;
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
+        for (int u = 0; u < kLlhUnroll; ++u) {
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, id[u], row_bytes), pol_keep);
         }
         if (bounded) {
 #pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
+          for (int u = 0; u < kLlhUnroll; ++u) {
             const float p = __expf(e[u] - m);          // e = -inf for the padding: p = 0
             s += p;
             fma4(acc, p, v[u]);
@@ -711,7 +733,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const 
         } else {
           float bm = e[0];
 #pragma unroll
-          for (int u = 1; u < kUnroll; ++u) bm = fmaxf(bm, e[u]);
+          for (int u = 1; u < kLlhUnroll; ++u) bm = fmaxf(bm, e[u]);
           const float mn = fmaxf(m, bm);
           if (mn != -INFINITY) {          // at least one edge seen so far
             const float sc = expf(m - mn);          // m = -inf on the first group: sc = 0, acc and s are 0 anyway
@@ -719,7 +741,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const 
             s *= sc;
             m = mn;
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
+            for (int u = 0; u < kLlhUnroll; ++u) {
               // e = -inf for the padding of the last group: p = 0.  ex2.approx path: the argument is <= 0 and
               // terms that matter have small |e - mn|; relative error < 2e-6, inside the 1e-5 tolerance
               const float p = __expf(e[u] - mn);
@@ -1031,7 +1053,7 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   const int lanes = lanes_for(f);
   // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
   // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint)
-  const bool staged = heads == 1 || heads == 2 || heads == 4;
+  const bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
   if (staged) {
     rc = GTA_ERR_UNSUPPORTED;
 #define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, st, wl, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, col_block)

@@ -47,7 +47,7 @@ import yaml
 
 from . import _cabi, kernels
 from .graph import DeviceGraph, csr_from_coo
-from .isa import IsaError, Program, validate_op_graph
+from .isa import IsaError, Program, stamp_comp_types, validate_op_graph
 
 #: COMP_TYPE -> arithmetic where the YAML alone is ambiguous (the reference only names ops)
 DEFAULT_SEMANTICS = {
@@ -367,7 +367,7 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
             network: str | None = None, is_reorder: bool = False, semantics: dict | None = None,
             fuse_across_blocks: bool = True, stabilize: bool = True, slope: float = kernels.LEAKY_SLOPE,
             max_edge_bytes: int = 8 << 30, outputs=None, source_table=None, return_log: bool = False,
-            check_shapes: bool = True):
+            check_shapes: bool = True, legacy_comp_types=None):
     """Run an ISA program functionally.
 
     program      : isa.Program, a path to ``Results/Insts/*.yaml`` or the raw list interpret() built
@@ -377,6 +377,8 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
     weights      : {op position: [Fin, Fout] tensor} for COMP_MM ops
     edge_inputs  : {op position: [E] or [E, w] tensor} for '-1' entries of input_g_list
     outputs      : op positions to return (default: ops with an empty output_list)
+    legacy_comp_types : COMP_TYPE per op position for V1/V2-era op graphs that lack the field
+                   (V2/simpletest.yaml: ``isa.LEGACY_SIMPLETEST_COMP_TYPES``)
     Returns {op position: tensor} (and the kernel log with ``return_log``).
     """
     if isinstance(op_info, (str, os.PathLike)):
@@ -385,6 +387,8 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
         program = Program.load(program)
     elif isinstance(program, list):
         program = Program.from_records(program)
+    if legacy_comp_types is not None:
+        op_info = stamp_comp_types(op_info, legacy_comp_types)
     edge_inputs = edge_inputs or {}
     sem = dict(NETWORK_SEMANTICS.get((network, bool(is_reorder)), {}))
     sem.update(semantics or {})

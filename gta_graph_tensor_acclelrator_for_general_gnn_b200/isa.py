@@ -35,6 +35,31 @@ def _int_list(v, what, pos):
     return v
 
 
+#: COMP_TYPE by list position for the reference's V1/V2-era fixture ``V2/simpletest.yaml:14-209`` (the GAT
+#: attention half: XW, el, er, two scatters, +, exp(leaky_relu), row sum, activation), which predates the
+#: COMP_TYPE field; the V3+ interpreter raises KeyError on it (vTCAD/code/interpreter.py:135).  SURVEY App. A.
+LEGACY_SIMPLETEST_COMP_TYPES = ("MM", "MM", "MM", "NONE", "NONE", "ADD", "SF", "ADD", "SF")
+
+
+def stamp_comp_types(op_info, comp_types):
+    """Copy of a V1/V2-era op graph with ``COMP_TYPE`` supplied by list position (records that already carry
+    one keep it).  This is what ``changeyaml.modify_yaml`` does for the 14-op GAT (changeyaml.py:18-114),
+    generalised: the caller names the arithmetic, nothing is guessed."""
+    import copy
+    if not isinstance(op_info, list):
+        raise IsaError("an op graph is a non-empty list of op records")
+    comp_types = list(comp_types)
+    if len(comp_types) != len(op_info):
+        raise IsaError(f"legacy_comp_types has {len(comp_types)} entries, the op graph has {len(op_info)} ops")
+    out = copy.deepcopy(op_info)
+    for pos, (op, ct) in enumerate(zip(out, comp_types)):
+        if ct not in COMP_TYPES:
+            raise IsaError(f"legacy_comp_types[{pos}] = {ct!r} is not one of {COMP_TYPES}")
+        if isinstance(op, dict):
+            op.setdefault("COMP_TYPE", ct)
+    return out
+
+
 def validate_op_graph(op_info) -> None:
     """Schema check of an op-graph list (template/op_template.yaml:1-19 plus ``COMP_TYPE``): the fields the
     executor reads exist and have the types it assumes.  Raises :class:`IsaError` naming the op."""
@@ -45,7 +70,8 @@ def validate_op_graph(op_info) -> None:
         if not isinstance(op, dict):
             raise IsaError(f"op {pos}: an op record is a mapping, got {type(op).__name__}")
         if "COMP_TYPE" not in op:
-            raise IsaError(f"op {pos} has no COMP_TYPE (V1/V2-era YAML; re-stamp it, changeyaml.py:18-114)")
+            raise IsaError(f"op {pos} has no COMP_TYPE (V1/V2-era YAML; re-stamp it, changeyaml.py:18-114, or pass "
+                           f"legacy_comp_types= to execute(), e.g. isa.LEGACY_SIMPLETEST_COMP_TYPES)")
         if op.get("TYPE") not in OP_TYPES:
             raise IsaError(f"op {pos}: unknown TYPE {op.get('TYPE')!r}")
         if op["COMP_TYPE"] not in COMP_TYPES:

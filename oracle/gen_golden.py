@@ -113,6 +113,10 @@ def main():
         chg.modify_yaml(p, n, e, f, [])
         shutil.copy(p, os.path.join(out, "opgraph", f"GAT-{ds}-restamped-h4.yaml"))
 
+    # BASELINE config 1: the reference's own V1/V2-era fixture, verbatim (9 ops, Cora shape, no COMP_TYPE;
+    # V2/simpletest.yaml:14-209).  The executor takes it with the by-position COMP_TYPE list of SURVEY App. A.
+    shutil.copy(os.path.join(args.ref, "V2", "simpletest.yaml"), os.path.join(out, "opgraph", "simpletest.yaml"))
+
     # ---- 2. ISA programs (interpret, unmodified) --------------------------------------
     programs = [
         # (network, ds, layer, reorder, op_array, tile_size_list)
