@@ -39,6 +39,11 @@ WORKLOADS = {
                    "isa/GCN-flickr-layer1-trans__0_1-2-3.yaml", 0),
     "reddit-gcn": ("reddit", "GCN", 1, True, "opgraph/GCN-reddit-layer1-trans.yaml",
                    "isa/GCN-reddit-layer1-trans__0_1-2-3.yaml", 0),
+    # the Reddit shape with the heavier-tailed degree sequence (synthetic.HEAVY_TAIL: max degree 47x the mean)
+    "reddit-heavy-gat": ("reddit-heavy", "GAT", 1, False, "opgraph/GAT-reddit-restamped-h4.yaml",
+                         "isa/GAT-reddit-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml", 4),
+    "reddit-heavy-gcn": ("reddit-heavy", "GCN", 1, True, "opgraph/GCN-reddit-layer1-trans.yaml",
+                         "isa/GCN-reddit-layer1-trans__0_1-2-3.yaml", 0),
 }
 F_OUT = 128
 
@@ -59,7 +64,12 @@ def shape_of(shape):
     if shape.startswith("rmat"):
         scale = int(shape[4:])
         return (1 << scale), 16 << scale, 256
-    return synthetic.SHAPES[shape]
+    return synthetic.SHAPES[shape[:-6] if shape.endswith("-heavy") else shape]
+
+
+def f_out_of(shape):
+    """Output width of the layer: 128 (genGraphOP.py:31-32 layer 1), 256 -> 256 for the RMAT config."""
+    return 256 if shape.startswith("rmat") else F_OUT
 
 
 def graph_of(shape):
@@ -192,9 +202,14 @@ def run_reference_arm(args, wl):
     from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
     from oracle import c_oracle
     shape, network, layer, reorder, _, _, heads = wl
+    note = ""
+    if shape.startswith("rmat") and int(shape[4:]) > 20:
+        # the host cannot hold the scale-24 inputs of this arm in bounded time: same generator at scale 20
+        note = f" [sampled on RMAT-20 (same generator parameters, 1/{1 << (int(shape[4:]) - 20)} of the nodes and edges of {shape})]"
+        shape = "rmat20"
     n, e, fin = shape_of(shape)
     coo = graph_of(shape)
-    x, w, al, ar = synthetic.gat_tensors(n, fin, F_OUT, max(heads, 1), seed=0)
+    x, w, al, ar = synthetic.gat_tensors(n, fin, f_out_of(shape), max(heads, 1), seed=0)
     # sample = first rows holding about sample_edges edges
     deg = np.bincount(coo.dst, minlength=n)
     cum = np.cumsum(deg)
@@ -217,9 +232,9 @@ def run_reference_arm(args, wl):
     full = tg + te * e / max(e_s, 1)
     value = e / full / 1e9
     cores = os.cpu_count()
-    sample = (f"full GEMM {n}x{fin}x{F_OUT} (numpy BLAS) + edge phase of dst rows [0,{sample_rows}) = {e_s} of {e} "
+    sample = (f"full GEMM {n}x{fin}x{f_out_of(shape)} (numpy BLAS) + edge phase of dst rows [0,{sample_rows}) = {e_s} of {e} "
               f"edges (C oracle, OpenMP {c_oracle.threads()} threads); layer time extrapolated as "
-              f"t_gemm + t_edge*E/E_sample")
+              f"t_gemm + t_edge*E/E_sample" + note)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tg + te) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -231,12 +246,76 @@ def run_reference_arm(args, wl):
 
 
 def workload_name(args, wl):
-    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
     shape, network, layer, reorder, _, isa_rel, heads = wl
     n, e, fin = shape_of(shape)
     h = f" H={args.heads or heads}" if network == "GAT" else ""
+    if shape.startswith("rmat"):
+        kind = "RMAT (a,b,c,d)=(0.57,0.19,0.19,0.05) edge factor 16, duplicates kept"
+    elif shape.endswith("-heavy"):
+        kind = "Chung-Lu P(rank)~(rank+600)^-0.9 (max degree ~47x mean, median ~0.41x)"
+    else:
+        kind = "Chung-Lu P(rank)~(rank+100)^-0.5 (max degree ~25x mean, median ~0.72x: milder than real Reddit, see DESIGN.md)"
     return (f"{network} layer{layer} ({'trans' if reorder else 'original'}) on {shape}-shape synthetic graph "
-            f"N={n} E={e} Fin={fin} F={F_OUT}{h} fp32, program {os.path.basename(isa_rel)}")
+            f"N={n} E={e} Fin={fin} F={f_out_of(shape)}{h} fp32, {kind}, program {os.path.basename(isa_rel)}")
+
+
+def measured_traffic(workload, kernel, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from an `ncu --set full` capture
+    of THIS workload on one GPU (profiles/traffic.json names the capture); None when no capture exists for the shape
+    being run (any N > 1: the per-rank launch has another shape)."""
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if world != 1 or not os.path.exists(tp):
+        return None, "no ncu capture of this launch shape"
+    with open(tp) as f:
+        entry = json.load(f).get(f"{workload}:{kernel}")
+    if not entry:
+        return None, "no ncu capture of this launch shape"
+    return int(entry["bytes"]), entry["source"]
+
+
+def reference_pipeline_timing(shape):
+    """Wall-clock of the reference's own pipeline (compile -> interpret -> simulate, vTCAD/code/test.py:10-15) on the
+    Cora-shape config, timed here on the box's host (one Python thread: the reference cannot use more).  Needs the
+    reference files under baseline/_ref (git-ignored, copied by tools/install_reference.py); None when absent."""
+    if shape != "cora":
+        return None
+    try:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import reference_pipeline
+        return reference_pipeline.time_pipeline(os.path.join(REPO, "baseline", "_ref"))
+    except Exception as exc:      # a reported baseline, never a requirement
+        return {"unavailable": str(exc).splitlines()[0][:160] if str(exc) else type(exc).__name__}
+
+
+def parity_big(P, torch, y_h, ip_s, ix_s, rows_sel, edge_w_rows, x_d, w_d, z_local, table, part):
+    """Parity for shapes whose whole-output oracle does not fit the host (RMAT-24): (1) the aggregation of the sampled
+    rows against the fp64 oracle applied to the SOURCE ROWS THE KERNEL GATHERED (fetched from the device table), (2) the
+    GEMM on sampled rows against fp64 X.W.  Both under the stated tolerance; the worse of the two is reported."""
+    uniq, inv = np.unique(ix_s, return_inverse=True)
+    if part is not None:
+        b = np.asarray(part.bounds, dtype=np.int64)
+        owner = np.searchsorted(b, uniq, side="right") - 1
+        slot = (owner - part.rank) % part.world if part.rotate else owner
+        table_rows = slot * part.stride + (uniq - b[owner])
+    else:
+        table_rows = uniq
+    z_rows = table[torch.from_numpy(table_rows).to(table.device)].cpu().numpy().astype(np.float64)
+    rep = P.check_gcn(y_h, ip_s, inv.astype(np.int32), edge_w_rows, z_rows, np.abs(z_rows))
+    # GEMM rows
+    k = min(4096, int(z_local.shape[0]))
+    pick = torch.linspace(0, z_local.shape[0] - 1, k, device=z_local.device).long()
+    x64 = x_d[pick].cpu().numpy().astype(np.float64)
+    w64 = w_d.cpu().numpy().astype(np.float64)
+    z64 = x64 @ w64
+    zs = np.abs(x64) @ np.abs(w64)
+    zerr = np.abs(z_local[pick].cpu().numpy().astype(np.float64) - z64) / (P.RTOL * np.abs(z64) + P.RTOL * zs + 1e-30)
+    rep["gemm_rows_checked"] = k
+    rep["gemm_max_err_over_tol"] = float(zerr.max())
+    rep["aggregate_max_err_over_tol"] = rep["max_err_over_tol"]
+    rep["max_err_over_tol"] = max(rep["max_err_over_tol"], float(zerr.max()))
+    rep["mode"] = ("aggregation of the sampled rows vs fp64 oracle on the source rows fetched from the device table + GEMM "
+                   "on %d sampled rows vs fp64 X.W (whole-output oracle does not fit the host at this shape)" % k)
+    return rep
 
 
 # ------------------------------------------------------------------------------------------
@@ -252,6 +331,7 @@ def main():
     ap.add_argument("--workload", default="reddit-gat", help="one of %s or rmat<scale>-gcn" % sorted(WORKLOADS))
     ap.add_argument("--heads", type=int, default=0, help="override the attention width H")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-edges", type=int, default=40_000_000,
                     help="edges in the CPU arm's sample (whole destination rows from row 0); the layer time is "
                          "extrapolated from it.  40 M edges = about a second per step on 16 cores")
@@ -261,13 +341,10 @@ def main():
                     help="edge budget of the parity check: every destination row of rank 0 when it holds at most this "
                          "many edges, else the 512 highest-degree rows plus every k-th row")
     ap.add_argument("--no-fuse", action="store_true", help="honour every STORE_* of the program")
-    ap.add_argument("--chunks", type=int, default=1,
-                    help="multi-GPU: pieces the source all-gather is cut into; > 1 overlaps the transfer with the "
-                         "aggregation (measured slower on 8 B200: NCCL's CTAs compete with the gather kernel)")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
-                    help="multi-GPU source exchange: NCCL all-gather, or peer-to-peer copies on the copy engines")
-    ap.add_argument("--alt", default="", help="multi-GPU: also time these exchanges in the same process, "
-                                               "e.g. 'p2p:1,p2p:4,nccl:4' (exchange:chunks), reported in config.alt")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU source exchange: pulled over NVLink inside the aggregation launch (default), or one "
+                         "NCCL all-gather per layer (the round-1 path, kept as the baseline)")
+    ap.add_argument("--copy-ctas", type=int, default=0, help="fused exchange: CTAs that pull (0 = library default)")
     ap.add_argument("--no-graph", action="store_true", help="issue kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -298,56 +375,77 @@ def main():
     shape, network, layer, reorder, op_rel, isa_rel, heads = wl
     heads = args.heads or heads
     n, e, fin = shape_of(shape)
+    f_out = f_out_of(shape)
+    big = shape.startswith("rmat") and n > (1 << 21)      # too big for host-side inputs and a whole-output oracle
     op_info = load_yaml(op_rel)
     program = isa.Program.from_records(load_yaml(isa_rel))
 
     # ---- inputs (synthetic, deterministic) ---------------------------------------------------
     t_setup = time.perf_counter()
-    coo = graph_of(shape)
-    x_h, w_h, al_h, ar_h = synthetic.gat_tensors(n, fin, F_OUT, max(heads, 1), seed=0)
-    full = graph.csr_from_coo(coo.dst, coo.src, n)
-    torch.cuda.synchronize()
-    if world > 1:
-        part = gdist.make_partition(full, rank, world, chunks=args.chunks)
-        g, r0, r1 = part.local, part.row_begin, part.row_end
-        exchange = gdist.SourceExchange(part)
-        if args.exchange == "p2p":
-            try:
-                probe = gdist.PeerExchange(part)
-                probe._setup(F_OUT + 4 if network == "GAT" else F_OUT, dev)      # all ranks agree or all raise
-                exchange = probe
-            except RuntimeError as exc:
-                if rank == 0:
-                    print("p2p exchange unavailable, using the NCCL all-gather: %s" % exc, file=sys.stderr)
-                args.exchange = "nccl"
+    if shape.startswith("rmat"):
+        dst_d, src_d, _ = synthetic.rmat_graph_device(int(shape[4:]), device=dev)
+        graph_checksum = "device-generated RMAT, seed 0: sum(dst)=%d sum(src)=%d" % (int(dst_d.sum(dtype=torch.int64)),
+                                                                                     int(src_d.sum(dtype=torch.int64)))
+        degree_stats = None
     else:
-        g, r0, r1, exchange = full, 0, n, None
+        coo = graph_of(shape)
+        graph_checksum = coo.checksum()
+        degree_stats = synthetic.degree_stats(coo.dst, n) if rank == 0 else None
+        dst_d, src_d = torch.from_numpy(coo.dst).to(dev), torch.from_numpy(coo.src).to(dev)
+        del coo
+    deg_d = torch.bincount(dst_d, minlength=n)          # global in-degrees (GCN edge norm)
+    if world > 1:
+        part = gdist.partition_from_coo(dst_d, src_d, n, rank, world, rotate=(args.exchange == "fused"))
+        g, r0, r1 = part.local, part.row_begin, part.row_end
+        exchange = gdist.FusedExchange(part, copy_ctas=args.copy_ctas) if args.exchange == "fused" else gdist.SourceExchange(part)
+        # global source id of every local edge (the remap inverted): slot -> owner, offset inside the owner's rows
+        slot = torch.div(g.indices, part.stride, rounding_mode="floor")
+        owner = (slot + (rank if part.rotate else 0)) % world
+        bounds_t = torch.tensor(part.bounds, dtype=torch.int64, device=dev)
+        src_glob = bounds_t[owner.long()] + (g.indices - slot * part.stride).long()
+        del slot, owner
+    else:
+        part = None
+        g = graph.csr_from_coo(dst_d, src_d, n)
+        r0, r1, exchange = 0, n, None
+        src_glob = g.indices.long()
+    del dst_d, src_d
+    torch.cuda.empty_cache()
+    e_local = g.num_edges
     edge_w = None
-    if network == "GCN":
-        deg = (full.indptr[1:] - full.indptr[:-1]).clamp(min=1).to(torch.float64)
-        rows = torch.repeat_interleave(torch.arange(r0, r1, device=dev), (full.indptr[r0 + 1:r1 + 1] - full.indptr[r0:r1]))
-        src_glob = full.indices[int(full.indptr[r0]):int(full.indptr[r1])].long()
-        edge_w = (1.0 / torch.sqrt(deg[rows] * deg[src_glob])).to(torch.float32)[:, None].contiguous()
-        del rows, src_glob
-    host_csr = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU leg is an N = 1 item (rank 0's host cores)
-        host_csr = (full.indptr.cpu().numpy(), None)
-        deg_h = np.diff(host_csr[0])
-        sample_rows = int(min(n, max(64, np.searchsorted(np.cumsum(deg_h), args.cpu_sample_edges) + 1)))
-        e_s = int(host_csr[0][sample_rows])
-        host_csr = (host_csr[0][:sample_rows + 1].copy(), full.indices[:e_s].cpu().numpy(), sample_rows, deg_h)
+    if network == "GCN":      # 1/sqrt(deg_i deg_j) in the local graph's edge order
+        deg = deg_d.clamp(min=1).to(torch.float64)
+        rows_of_edge = torch.repeat_interleave(torch.arange(r0, r1, device=dev), g.indptr[1:] - g.indptr[:-1])
+        edge_w = (1.0 / torch.sqrt(deg[rows_of_edge] * deg[src_glob])).to(torch.float32)[:, None].contiguous()
+        del rows_of_edge, deg
     parity_csr = None
-    if rank == 0 and not args.no_parity:
-        e0, e1 = int(full.indptr[r0]), int(full.indptr[r1])
-        parity_csr = ((full.indptr[r0:r1 + 1] - e0).cpu().numpy(), full.indices[e0:e1].cpu().numpy())
-    if world > 1 and not args.alt:
-        del full
-        torch.cuda.empty_cache()
-    g.schedule()
-    x_pin = torch.from_numpy(x_h[r0:r1]).pin_memory()
-    x_d = kernels.to_table(x_pin.to(dev))
-    w_d, al_d, ar_d = (torch.from_numpy(a).to(dev) for a in (w_h, al_h, ar_h))
-    weights = {0: w_d, 1: al_d, 2: ar_d} if network == "GAT" else {0: w_d}
+    if rank == 0 and not args.no_parity:      # rank 0's rows with GLOBAL source ids, on the host
+        parity_csr = (g.indptr.cpu().numpy(), src_glob.to(torch.int32).cpu().numpy())
+    host_csr = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not big:      # the CPU leg is an N = 1 item
+        ip_h = g.indptr.cpu().numpy()
+        deg_h = np.diff(ip_h)
+        sample_rows = int(min(n, max(64, np.searchsorted(np.cumsum(deg_h), args.cpu_sample_edges) + 1)))
+        e_s = int(ip_h[sample_rows])
+        host_csr = (ip_h[:sample_rows + 1].copy(), g.indices[:e_s].cpu().numpy(), sample_rows, deg_h)
+    del src_glob
+    torch.cuda.empty_cache()
+    if big:      # features and weights drawn on the device: rank p's rows from generator seed 1000 + p
+        gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+        x_d = kernels.alloc_table(r1 - r0, fin, dev)
+        x_d.normal_(generator=gen)
+        gen_w = torch.Generator(device=dev).manual_seed(7)
+        lim = float(np.sqrt(6.0 / (fin + f_out)))
+        w_d = (torch.rand((fin, f_out), device=dev, generator=gen_w) * 2 - 1) * lim
+        x_h = w_h = al_h = ar_h = None
+        x_pin = None
+        weights = {0: w_d}
+    else:
+        x_h, w_h, al_h, ar_h = synthetic.gat_tensors(n, fin, f_out, max(heads, 1), seed=0)
+        x_pin = torch.from_numpy(x_h[r0:r1]).pin_memory()
+        x_d = kernels.to_table(x_pin.to(dev))
+        w_d, al_d, ar_d = (torch.from_numpy(a).to(dev) for a in (w_h, al_h, ar_h))
+        weights = {0: w_d, 1: al_d, 2: ar_d} if network == "GAT" else {0: w_d}
     final_op = len(op_info) - 1
     edge_inputs = {2: edge_w} if network == "GCN" else None
     torch.cuda.synchronize()
@@ -371,9 +469,9 @@ def main():
     graphed = None
     graph_note = "eager"
     if world > 1:
-        # capturing the NCCL all-gathers of torch.distributed into the graph hung on the B200 box
-        # (round 1, 2 ranks); multi-rank steps are issued eagerly
-        graph_note = "eager (multi-rank: NCCL all-gather not graph-captured)"
+        # the fused exchange carries a step number and alternates two tables; steps are issued eagerly
+        # (host enqueue time is reported; it hides under the previous step's kernels)
+        graph_note = "eager (multi-rank: per-step exchange state lives on the host)"
     elif not args.no_graph:
         try:
             graphed = executor.GraphedExecution(lambda: step(x_d))
@@ -423,72 +521,64 @@ def main():
     for name, a, b in log:
         per_kernel.setdefault(name, []).append(a.elapsed_time(b))
 
-    # ---- optional: other exchange strategies on the same graph, same process --------------------
-    alt_results = {}
-    if world > 1 and args.alt:
-        for spec in args.alt.split(","):
-            kind, ch = spec.split(":")
-            part_a = gdist.make_partition(full, rank, world, chunks=int(ch))
-            if edge_inputs is not None and int(ch) > 1:
-                continue          # the GCN edge weights would need the re-sorted edge order
-            try:
-                ex_a = gdist.PeerExchange(part_a) if kind == "p2p" else gdist.SourceExchange(part_a)
-                if kind == "p2p":
-                    ex_a._setup(F_OUT + 4 if network == "GAT" else F_OUT, dev)
-            except RuntimeError:
-                alt_results[spec] = None
-                continue
-            g_a = part_a.local
-
-            def step_a(x_dev, g_a=g_a, ex_a=ex_a):
-                return executor.execute(program, op_info, g_a, {0: x_dev}, weights, edge_inputs, network=network,
-                                        is_reorder=reorder, fuse_across_blocks=not args.no_fuse, source_table=ex_a,
-                                        check_shapes=False)[final_op]
-            for _ in range(args.warmup):
-                step_a(x_d)
-            barrier()
-            ev0.record()
-            for _ in range(args.steps):
-                step_a(x_d)
-            ev1.record()
-            barrier()
-            ta = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-            alt_results[spec] = round(float(ta.item()) / args.steps, 4)
-
     # ---- e2e: host features in, result out, through execute() -------------------------------
     # Every step copies ITS features from pinned host memory and ITS result back; the copies of
     # neighbouring steps overlap this step's kernels (pipeline.HostPipeline: 3 streams, 2 buffers).
-    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import pipeline
-    xs_pin = []
-    for _ in range(2):
-        t_pin = pipeline.pinned_table(r1 - r0, fin)
-        t_pin.copy_(x_pin)
-        xs_pin.append(t_pin)
-    ys_pin = [torch.empty((r1 - r0, F_OUT), dtype=torch.float32).pin_memory() for _ in range(2)]
+    e2e = None
+    if not args.no_e2e and x_pin is not None:
+        from gta_graph_tensor_acclelrator_for_general_gnn_b200 import pipeline
+        xs_pin = []
+        for _ in range(2):
+            t_pin = pipeline.pinned_table(r1 - r0, fin)
+            t_pin.copy_(x_pin)
+            xs_pin.append(t_pin)
+        ys_pin = [torch.empty((r1 - r0, f_out), dtype=torch.float32).pin_memory() for _ in range(2)]
 
-    def e2e_run(pipe, steps):
+        def e2e_run(pipe, steps):
+            barrier()
+            for i in range(steps):
+                pipe.submit(xs_pin[i % 2], ys_pin[i % 2])
+            ms = pipe.finish()
+            barrier()
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()) / steps
+
+        # one pipeline object per mode, warmed first: the caching allocator keeps per-stream pools, so the
+        # first steps on fresh streams pay cudaMalloc (device-synchronising) for Z / el / er / out
+        pipe2 = pipeline.HostPipeline(step, r1 - r0, fin, dev, depth=2)
+        pipe1 = pipeline.HostPipeline(step, r1 - r0, fin, dev, depth=1)
+        e2e_run(pipe2, 3)
+        e2e_run(pipe1, 2)
+        e2e_serial_ms = e2e_run(pipe1, max(args.e2e_steps // 2, 2))
+        e2e_ms = e2e_run(pipe2, args.e2e_steps)
+        assert torch.equal(ys_pin[0], y.cpu()), "e2e result differs from the resident-input result"
+        h2d = int(xs_pin[0].numel() * 4)
+        d2h = int(ys_pin[0].numel() * 4)
+        # the ceiling of this box: every rank uploads its features at the same time, nothing else running
+        stage = pipe2.stage[0]
+        flat_src = torch.as_strided(xs_pin[0], (xs_pin[0].shape[0] * xs_pin[0].stride(0),), (1,))
+        flat_dst = torch.as_strided(stage, (stage.shape[0] * stage.stride(0),), (1,))
         barrier()
-        for i in range(steps):
-            pipe.submit(xs_pin[i % 2], ys_pin[i % 2])
-        ms = pipe.finish()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            flat_dst.copy_(flat_src, non_blocking=True)
+        c1.record()
         barrier()
-        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        tc = torch.tensor([c0.elapsed_time(c1) / 3], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()) / steps
-
-    # one pipeline object per mode, warmed first: the caching allocator keeps per-stream pools, so the
-    # first steps on fresh streams pay cudaMalloc (device-synchronising) for Z / el / er / out
-    pipe2 = pipeline.HostPipeline(step, r1 - r0, fin, dev, depth=2)
-    pipe1 = pipeline.HostPipeline(step, r1 - r0, fin, dev, depth=1)
-    e2e_run(pipe2, 3)
-    e2e_run(pipe1, 2)
-    e2e_serial_ms = e2e_run(pipe1, max(args.e2e_steps // 2, 2))
-    e2e_ms = e2e_run(pipe2, args.e2e_steps)
-    assert torch.equal(ys_pin[0], y.cpu()), "e2e result differs from the resident-input result"
-    h2d = int(xs_pin[0].numel() * 4)
-    d2h = int(ys_pin[0].numel() * 4)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        h2d_ms = float(tc.item())
+        e2e = {"value": e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "serial_ms_per_step": e2e_serial_ms,
+               "h2d_alone_ms": h2d_ms, "h2d_alone_gbs_per_rank": h2d / (h2d_ms * 1e-3) / 1e9,
+               "note": "per rank and per step: features X (pinned host) -> device, execute(), result -> pinned "
+                       "host, all inside the timed region; copies of neighbouring steps overlap the kernels "
+                       "(pipeline.HostPipeline, depth 2; serial_ms_per_step = depth 1); the CSR (static graph "
+                       "structure) and the weights stay resident.  h2d_alone_ms = the same upload on every rank at "
+                       "once with nothing else running (max over ranks): the host-side floor of a step"}
 
     # bitwise run-to-run reproducibility of the timed path (every rank; the reduction shape is fixed)
     y_first = run_step().clone()
@@ -497,6 +587,14 @@ def main():
         tb = torch.tensor([int(bitwise)], dtype=torch.int32, device=dev)
         dist.all_reduce(tb, op=dist.ReduceOp.MIN)
         bitwise = bool(tb.item())
+    barrier()
+    z_dev = big_table = None
+    if big and not args.no_parity:
+        # one more step (every rank, so the exchange stays in step) that also returns Z, and the table it gathered from
+        z_dev = executor.execute(program, op_info, g, {0: x_d}, weights, edge_inputs, network=network, is_reorder=reorder,
+                                 source_table=exchange, check_shapes=False, outputs=[0, final_op])
+        torch.cuda.synchronize()
+        big_table = exchange.last_table(f_out) if exchange is not None else z_dev[0]
     barrier()
 
     if rank != 0:
@@ -511,10 +609,16 @@ def main():
         c_oracle.use_all_cores()
         t_par = time.perf_counter()
         indptr_l, indices_l = parity_csr
-        rows_sel = P.select_rows(indptr_l, args.parity_edges)
+        budget = min(args.parity_edges, 4_000_000) if big else args.parity_edges
+        rows_sel = P.select_rows(indptr_l, budget)
         ip_s, ix_s = P.sub_csr(indptr_l, indices_l, rows_sel)
         y_h = y_first.cpu().numpy()[rows_sel]
-        if network == "GAT":
+        if big:
+            deg_l = np.diff(indptr_l)
+            pos = np.repeat(indptr_l[rows_sel] - ip_s[:-1], deg_l[rows_sel]) + np.arange(int(ip_s[-1]), dtype=np.int64)
+            ew_rows = edge_w.reshape(-1)[torch.from_numpy(pos).to(dev)].cpu().numpy()
+            parity = parity_big(P, torch, y_h, ip_s, ix_s, rows_sel, ew_rows, x_d, w_d, z_dev[0], big_table, part)
+        elif network == "GAT":
             z64, zabs, el64, er64 = P.host_tables(x_h, w_h, al_h, ar_h)
             parity = P.check_gat(y_h, ip_s, ix_s, el64[r0 + rows_sel], er64, z64, zabs)
         else:
@@ -522,7 +626,6 @@ def main():
             deg_l = np.diff(indptr_l)
             pos = np.repeat(indptr_l[rows_sel] - ip_s[:-1], deg_l[rows_sel]) + np.arange(int(ip_s[-1]), dtype=np.int64)
             parity = P.check_gcn(y_h, ip_s, ix_s, edge_w.cpu().numpy().reshape(-1)[pos], z64, zabs)
-        del z64, zabs
         parity.update(bitwise_rerun=bitwise, rows_of=int(r1 - r0), edges_of=int(indptr_l[-1]),
                       checked="rank 0's destination rows [%d,%d)%s" % (r0, r1, "" if rows_sel.shape[0] == r1 - r0 else
                                                                       " (512 highest-degree rows + every k-th row)"),
@@ -531,23 +634,29 @@ def main():
     # ---- roofline of the dominant kernel ------------------------------------------------------
     dom = "gta_gat_aggregate_f32" if network == "GAT" else "gta_aggregate_f32"
     dom_ms = float(np.mean(per_kernel[dom])) if dom in per_kernel else None
-    e_local = g.num_edges
-    _, dom_bytes = algorithmic_bytes(network, r1 - r0, e_local, fin, F_OUT, max(heads, 1))
-    layer_bytes, _ = algorithmic_bytes(network, n, e, fin, F_OUT, max(heads, 1))
+    _, dom_bytes = algorithmic_bytes(network, r1 - r0, e_local, fin, f_out, max(heads, 1))
+    layer_bytes, _ = algorithmic_bytes(network, n, e, fin, f_out, max(heads, 1))
     peak, peak_src = measured_peak()
-    traffic = None
-    tp = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get(f"{args.workload}:{dom}")
+    traffic, traffic_src = measured_traffic(args.workload, dom, world)
     roofline = None
     if dom_ms:
         ach = dom_bytes / (dom_ms * 1e-3) / 1e9
+        # the gather term alone against the MEASURED gather ceiling of this device (L2-resident random rows, the
+        # kernel's own load instruction): what the kernel is actually bound by when the table (or its column block)
+        # fits L2.  Not meaningful when the table is far larger than L2 (RMAT-24: HBM-bound, use frac).
+        gp = kernels.gather_peak(f=min(f_out, 128))
+        gather_bytes = e_local * f_out * 4
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                    "kernel_ms": dom_ms,
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                    "l2_gather_peak_gbs": gp["gbs"], "l2_gather_peak_how": "%s, %d-byte rows of a %.0f MB table" % (
+                        gp["how"], gp["row_bytes"], gp["table_mb"]),
+                    "l2_frac": gather_bytes / (dom_ms * 1e-3) / 1e9 / gp["gbs"],
                     "layer_frac": layer_bytes / (ms_per_step * 1e-3) / 1e9 / peak / max(world, 1),
-                    "kernel_ms_by_name": {k: float(np.mean(v)) for k, v in per_kernel.items()}}
+                    "kernel_ms_by_name": {k: float(np.mean(v)) for k, v in per_kernel.items()},
+                    "note": "frac = algorithmic bytes (no-reuse gather model, SURVEY 8d) / kernel time / measured HBM peak: "
+                            "above 1 because L2 serves the re-reads; l2_frac = gathered row bytes / kernel time / measured "
+                            "L2 gather peak is the fraction of the unit that actually bounds the kernel"}
 
     cpu_baseline = None
     if host_csr is not None:
@@ -573,26 +682,27 @@ def main():
                         "sample": (f"full GEMM (numpy BLAS, {tg:.2f} s) + edge phase of dst rows [0,{sample_rows}) = "
                                    f"{e_s} of {e} edges (C oracle fp32, {te:.2f} s); mean of {len(reps)} passes; layer "
                                    f"time extrapolated as t_gemm + t_edge*E/E_sample")}
+        ref_pipe = reference_pipeline_timing(shape)
+        if ref_pipe is not None:
+            cpu_baseline["reference_pipeline"] = ref_pipe
 
+    if world > 1:
+        par = f"dst-range partition x{world} (partition on build), " + (
+            "[Z|er] pulled from the peers over NVLink inside the aggregation launch (no NCCL in the step)"
+            if args.exchange == "fused" else "one NCCL all-gather of [Z|er] per layer")
+    else:
+        par = "single GPU"
     line = {"metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args, wl), "baseline_metric": baseline_metric(),
-                       "parallelism": f"dst-range partition x{world}" + ((", one NCCL all-gather of [Z|er] per layer" if args.exchange == "nccl" else ", [Z|er] pulled from the peers' IPC-mapped slots by copy engines")
-                                        + (" in %d overlapped chunks" % args.chunks if args.chunks > 1 else "") if world > 1 else ""),
+            "config": {"workload": workload_name(args, wl), "baseline_metric": baseline_metric(), "parallelism": par,
+                       "degrees": degree_stats,
                        "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
-                           e * 4 / 1e6, n * fin * 4 / 1e6, n * F_OUT * 4 / 1e6),
-                       "fuse_across_blocks": not args.no_fuse, "alt_ms_per_step": alt_results or None, "launch": graph_note, "host_enqueue_ms_per_step": round(host_ms, 3), "graph_checksum": coo.checksum(),
+                           e * 4 / 1e6, n * fin * 4 / 1e6, n * f_out * 4 / 1e6),
+                       "fuse_across_blocks": not args.no_fuse, "launch": graph_note,
+                       "host_enqueue_ms_per_step": round(host_ms, 3), "graph_checksum": graph_checksum,
                        "setup_s": round(t_setup, 1)},
-            "clocks": clocks,
-            "e2e": {"value": e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "serial_ms_per_step": e2e_serial_ms,
-                    "note": "per rank and per step: features X (pinned host) -> device, execute(), result -> pinned "
-                            "host, all inside the timed region; copies of neighbouring steps overlap the kernels "
-                            "(pipeline.HostPipeline, depth 2; serial_ms_per_step = depth 1); the CSR (static graph "
-                            "structure) and the weights stay resident"},
-            "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     print(json.dumps(line), flush=True)
     if world > 1:

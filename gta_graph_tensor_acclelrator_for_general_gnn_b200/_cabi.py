@@ -27,6 +27,16 @@ _i64 = C.c_int64
 _f32 = C.c_float
 _sz = C.c_size_t
 
+MAX_RANKS = 16
+
+
+class Exchange(C.Structure):
+    """gta_exchange_t (include/gta_b200.h)."""
+    _fields_ = [("world", _i32), ("rank", _i32), ("step", _i32), ("copy_ctas", _i32), ("slot_rows", _i64),
+                ("row_bytes", _i64), ("table", _p), ("signals", _p), ("peer_table", _p * MAX_RANKS),
+                ("slot_valid_rows", _i64 * MAX_RANKS)]
+
+
 #: every symbol include/gta_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gta_last_error": (C.c_char_p, []),
@@ -44,7 +54,8 @@ SIGNATURES = {
     "gta_ipc_export": (C.c_int, [_p, C.c_char_p]),
     "gta_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_p)]),
     "gta_ipc_close": (C.c_int, [_p]),
-    "gta_copy_many": (C.c_int, [C.POINTER(_p), C.POINTER(_p), C.POINTER(_i64), _i32, _p]),
+    "gta_exchange_signal_bytes": (_sz, []),
+    "gta_exchange_publish": (C.c_int, [_p, _i64, _i64, _i32, _i32, _i32, _i32, C.POINTER(_p), _p]),
     "gta_reorder_workspace": (_sz, [_i64]),
     "gta_reorder": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "gta_schedule_workspace": (_sz, [_i64, _i64, _i64]),
@@ -58,11 +69,12 @@ SIGNATURES = {
     "gta_gemm_set_mode": (C.c_int, [C.c_int]),
     "gta_gemm_get_mode": (C.c_int, []),
     "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
-                                    _p, _p, _i32, _p]),
+                                    _p, _p, _p, _i32, _p]),
     "gta_gat_partial_stride": (_i32, [_i32, _i32]),
+    "gta_gather_peak_probe": (C.c_int, [_p, _i64, _i64, _i32, _i64, _p, _p]),
     "gta_er_stats": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _p]),
     "gta_gat_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _i64,
-                                        _i32, _i32, _p, _p, _p, _p, _p, _i64, _i32, _p]),
+                                        _i32, _i32, _p, _p, _p, _p, _p, _i64, _p, _i32, _p]),
     "gta_gat_logits_f32": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _i32, _f32, _i32, _p, _p, _p, _p]),
     "gta_edge_binary_f32": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _i32, _i32, _i64, _p, _i32, _i32, _i64, _p, _i32,
                                       _i64, _p]),

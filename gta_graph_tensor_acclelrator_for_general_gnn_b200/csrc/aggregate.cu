@@ -24,7 +24,10 @@
 //
 // Determinism.  Every item is reduced by exactly one group in ascending source order and the chain
 // is a left fold in slot order: a fixed-shape reduction, bitwise reproducible run to run, no atomics.
+#include <string.h>
+
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace gta {
 
@@ -124,7 +127,8 @@ __device__ __forceinline__ int warp_max_i32(int v) {
   return v;
 }
 // gathered feature row, 128 bits per lane.  GTA_AGG_GATHER picks the cache policy (measured on B200,
-// see DESIGN.md): 0 = L1 no-allocate, 1 = default, 2 = L1 no-allocate + L2 evict_last, 3 = L2 evict_last
+// see DESIGN.md): 0 = L1 no-allocate, 1 = default, 2 = L1 no-allocate + L2 evict_last, 3 = L2 evict_last,
+// 4 = as 2 without .nc (coherent path)
 #ifndef GTA_AGG_GATHER
 #define GTA_AGG_GATHER 2
 #endif
@@ -139,8 +143,11 @@ __device__ __forceinline__ float4 ld_row_f32x4(const float* p, uint64_t pol_keep
 #elif GTA_AGG_GATHER == 2
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_keep));
-#else
+#elif GTA_AGG_GATHER == 3
   asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_keep));
+#else      // 4: as 2 but through the coherent path (no .nc)
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol_keep));
 #endif
   return v;
@@ -215,10 +222,14 @@ constexpr int kLlhUnroll = GTA_LLH_UNROLL;
 
 template <int LANES, int WKIND, bool DIV>
 __global__ void __launch_bounds__(kAggThreads, GTA_AGG_MINBLOCKS)
-aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const float* __restrict__ rowden,
-                 const float* __restrict__ x, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
-                 int f, int epilogue) {
+aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ w, int wh,
+                 const float* __restrict__ rowden, const float* __restrict__ x, const uint32_t row_bytes,
+                 float* __restrict__ out, int64_t ldo, int f, int epilogue) {
   __shared__ __align__(16) uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
+  if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
+    exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int fo = blockIdx.y * 128 + 4 * l;
@@ -253,6 +264,10 @@ aggregate_kernel(const WorkList wl, const float* __restrict__ w, int wh, const f
     if (l < count) {
       idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
       if (WKIND == 1) w_nxt = ld_stream_f32(w_base + l, pol_stream);
+    }
+    if (ex.world > 1) {          // the item's slot may still be on its way from a peer
+      if (l == 0 && count > 0) exchange_gate(ex, idx_nxt);
+      __syncwarp();
     }
     for (int base = 0; base < max_count; base += LANES) {
       int n = count - base;
@@ -400,17 +415,11 @@ __device__ __forceinline__ float pick(const float (&v)[H], int h) {
 // fail the test, heads counts that are no power of two and calls that want the true row maximum back
 // take the online path below.
 constexpr float kBoundRange = 60.f;
-__device__ __forceinline__ uint32_t ordered_code(float f) {
-  const uint32_t b = __float_as_uint(f);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float ordered_decode(uint32_t c) {
-  return __uint_as_float((c & 0x80000000u) ? (c & 0x7fffffffu) : ~c);
-}
-// er_stats[cb][0][h] = code(max er), er_stats[cb][1][h] = code(max -er); zero = "no source seen"
-__device__ __forceinline__ bool block_bound(const uint32_t* __restrict__ er_stats, int64_t cb, int heads, int h,
+// er_stats[cb*pitch + h] = code(max er), er_stats[cb*pitch + heads + h] = code(max -er); 0 = "no source seen".
+// pitch = 2*heads for a gta_er_stats buffer, 64 for the statistics of a signal block (exchange.cuh).
+__device__ __forceinline__ bool block_bound(const uint32_t* er_stats, int64_t cb, int pitch, int heads, int h,
                                             float* er_max) {
-  const uint32_t cmax = __ldg(er_stats + (cb * 2) * heads + h), cneg = __ldg(er_stats + (cb * 2 + 1) * heads + h);
+  const uint32_t cmax = __ldcg(er_stats + cb * pitch + h), cneg = __ldcg(er_stats + cb * pitch + heads + h);
   const float hi = ordered_decode(cmax), lo = -ordered_decode(cneg);
   *er_max = hi;
   return cmax != 0u && cneg != 0u && (hi - lo) < kBoundRange;      // NaN compares false
@@ -418,10 +427,10 @@ __device__ __forceinline__ bool block_bound(const uint32_t* __restrict__ er_stat
 
 template <int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? GTA_GAT_MINBLOCKS : (GTA_GAT_MINBLOCKS + 1) / 2)
-gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const float* __restrict__ er, int64_t lder,
-                     float slope, const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out,
-                     int64_t ldo, int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
-                     const uint32_t* __restrict__ er_stats, int64_t col_block) {
+gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ el, const float* __restrict__ er,
+                     int64_t lder, float slope, const float* __restrict__ z, const uint32_t row_bytes,
+                     float* __restrict__ out, int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
+                     float* __restrict__ rowsum, const uint32_t* er_stats, int stats_pitch, int64_t col_block) {
   // per warp: H rows of 32 staged edges, entry = {source id, softmax numerator}.  Row pitch kS = 34
   // entries: a lane's STS.64 lands beside its neighbour's (2 wavefronts per head, no conflicts) and the
   // LDS.128 of the gather loop -- two consecutive edges of one head, the 4 heads of a warp at once --
@@ -429,6 +438,10 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
   // every store, 27 % of the L1/TEX data-pipe wavefronts of the kernel.
   constexpr int kS = 34;
   __shared__ __align__(16) uint2 s_e[kAggWarps][H * kS];
+  if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
+    exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int gbase = lane & ~(LANES - 1);          // first lane of my group inside the warp
@@ -467,11 +480,13 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
     float er_cur[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
-    if (l < count) {
-      idx_cur = ld_stream_i32(idx_base + l, pol_stream);
-      load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
-    }
+    if (l < count) idx_cur = ld_stream_i32(idx_base + l, pol_stream);
     if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
+    if (ex.world > 1) {          // the item's slot (z, er and its er range) may still be on its way from a peer
+      if (l == 0 && count > 0) exchange_gate(ex, idx_cur);
+      __syncwarp();
+    }
+    if (l < count) load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
 
     // bound path: the whole warp or nobody (the online path reduces with full-warp shuffles)
     bool bounded = false;
@@ -483,7 +498,7 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           float hi;
-          ok = block_bound(er_stats, cb, H, h, &hi) && ok;
+          ok = block_bound(er_stats, cb, stats_pitch, H, h, &hi) && ok;
           if (ok) m[h] = leaky(elr[h] + hi, slope);
         }
       }
@@ -646,11 +661,16 @@ gat_aggregate_kernel(const WorkList wl, const float* __restrict__ el, const floa
 // ----------------------------------------------------------------------------------------
 template <int LANES>
 __global__ void __launch_bounds__(kAggThreads, GTA_LLH_MINBLOCKS)
-gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const float* __restrict__ er, int64_t lder,
-                         int heads, float slope, const float* __restrict__ z, const uint32_t row_bytes,
-                         float* __restrict__ out, int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
-                         float* __restrict__ rowsum, const uint32_t* __restrict__ er_stats, int64_t col_block) {
+gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ el,
+                         const float* __restrict__ er, int64_t lder, int heads, float slope,
+                         const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
+                         int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
+                         const uint32_t* er_stats, int stats_pitch, int64_t col_block) {
   __shared__ uint32_t s_id[kAggWarps][32];
+  if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
+    exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int fo = blockIdx.y * 128 + 4 * l;
@@ -683,6 +703,10 @@ gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const 
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int idx_nxt = 0;
     if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+    if (ex.world > 1) {
+      if (l == 0 && count > 0) exchange_gate(ex, idx_nxt);
+      __syncwarp();
+    }
     // bound path (see gat_aggregate_kernel): a lane only needs the bound of its own head; the choice is
     // per lane group here, nothing below synchronises across groups on it
     bool bounded = false;
@@ -693,7 +717,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const 
       bool ok = true;
       for (int h = 0; h < heads; ++h) {          // every head of the block must pass: lanes of one item agree
         float hi;
-        ok = block_bound(er_stats, cb, heads, h, &hi) && ok;
+        ok = block_bound(er_stats, cb, stats_pitch, heads, h, &hi) && ok;
         if (h == head) m = leaky(elh + hi, slope);
       }
       bounded = ok;
@@ -801,6 +825,36 @@ gat_aggregate_llh_kernel(const WorkList wl, const float* __restrict__ el, const 
 }
 
 // ----------------------------------------------------------------------------------------
+// Roofline denominator of the gather kernels: random whole-row gathers from a table that fits L2, with the
+// kernels' own load instruction (one 128-bit load per lane, L1 no-allocate, L2 evict_last), 8 in flight per
+// lane, ids from a hash so nothing else touches memory.  bench.py reports gather bytes / time of the real
+// kernel against this measured peak (roofline.l2_frac): the HBM roofline says little about a kernel whose
+// 96 % of the traffic is L2 hits.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAggThreads, 8)
+gather_peak_kernel(const float* __restrict__ table, uint32_t rows, uint32_t row_bytes, int lanes_per_row,
+                   int64_t gathers_per_group, float4* __restrict__ sink, const uint64_t pol_keep) {
+  const int lane = threadIdx.x & 31;
+  const int l = lane % lanes_per_row;
+  const uint64_t group = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) / lanes_per_row;
+  const float* base = table + 4 * l;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t state = uint32_t(group * 2654435761u) | 1u;
+  for (int64_t i = 0; i < gathers_per_group; i += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      state = state * 1664525u + 1013904223u;            // LCG: the lanes of a group draw the same ids
+      const uint32_t id = uint32_t((uint64_t(state) * rows) >> 32);
+      v[u] = ld_row_f32x4(row_ptr(base, id, row_bytes), pol_keep);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  if (acc.x == 1.2345e38f) sink[group] = acc;          // keeps the loads alive, never true in practice
+}
+
+// ----------------------------------------------------------------------------------------
 // er_stats: per column block and head, max er and max -er as ordered-int codes (atomicMax on zeroed words)
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -892,19 +946,52 @@ static int resident_ctas(K kernel) {
 }
 
 template <typename K>
-static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f) {
+static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f, const Exchange& ex) {
   const int64_t need = (num_items * lanes + kAggThreads - 1) / kAggThreads;
   const int64_t cap = resident_ctas(kernel);
-  return dim3((unsigned)(need < cap ? need : cap), (unsigned)((f + 127) / 128));
+  // the copy CTAs of an exchange come first in the grid, so they are resident before any CTA can wait on them
+  const int64_t copy = ex.world > 1 ? ex.copy_ctas : 0;
+  return dim3((unsigned)((need < cap ? need : cap) + copy), (unsigned)((f + 127) / 128));
+}
+
+// gta_exchange_t (host) -> Exchange (kernel parameter); arrived[] lives behind the item counters
+static int make_exchange(const char* who, const gta_exchange_t* h, int32_t* arrived, int64_t ld_elems, Exchange* ex) {
+  memset(ex, 0, sizeof(*ex));
+  if (h == nullptr || h->world <= 1) return GTA_OK;
+  GTA_REQUIRE(h->world <= GTA_MAX_RANKS && h->rank >= 0 && h->rank < h->world && h->step >= 1,
+              "%s: exchange world %d rank %d step %d", who, h->world, h->rank, h->step);
+  GTA_REQUIRE(h->table && h->signals && h->slot_rows > 0, "%s: exchange table / signals / slot_rows missing", who);
+  GTA_REQUIRE(h->row_bytes == ld_elems * 4 && h->row_bytes % 16 == 0,
+              "%s: exchange row_bytes %lld does not match the table's row pitch %lld", who, (long long)h->row_bytes,
+              (long long)(ld_elems * 4));
+  GTA_REQUIRE((h->slot_rows * h->row_bytes) % 128 == 0,
+              "%s: a slot (%lld rows of %lld bytes) must be a whole number of 128-byte lines", who,
+              (long long)h->slot_rows, (long long)h->row_bytes);
+  ex->world = h->world;
+  ex->copy_ctas = h->copy_ctas > 0 ? h->copy_ctas : 64;
+  ex->step = h->step;
+  ex->row_bytes = uint32_t(h->row_bytes);
+  ex->slot_rows = h->slot_rows;
+  ex->table = static_cast<char*>(h->table);
+  ex->signals = static_cast<const ExchangeSignals*>(h->signals);
+  ex->arrived = arrived;
+  for (int k = 0; k < h->world; ++k) {
+    GTA_REQUIRE(k == 0 || h->peer_table[k], "%s: table of slot %d's owner is not mapped", who, k);
+    GTA_REQUIRE(h->slot_valid_rows[k] >= 0 && h->slot_valid_rows[k] <= h->slot_rows, "%s: slot %d has %lld rows", who, k,
+                (long long)h->slot_valid_rows[k]);
+    ex->peer[k] = static_cast<const char*>(h->peer_table[k]);
+    ex->valid_rows[k] = int32_t(h->slot_valid_rows[k]);
+  }
+  return GTA_OK;
 }
 
 template <int LANES>
-static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkList& wl, const float* w, int wh,
-                               const float* rowden, const float* x, int64_t ldx, float* out, int64_t ldo, int f,
-                               int epi) {
+static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkList& wl, const Exchange& ex,
+                               const float* w, int wh, const float* rowden, const float* x, int64_t ldx, float* out,
+                               int64_t ldo, int f, int epi) {
 #define GTA_AGG(K, D)                                                                                          \
-  aggregate_kernel<LANES, K, D><<<persistent_grid(aggregate_kernel<LANES, K, D>, wl.num_items, LANES, f),       \
-                                  kAggThreads, 0, st>>>(wl, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi)
+  aggregate_kernel<LANES, K, D><<<persistent_grid(aggregate_kernel<LANES, K, D>, wl.num_items, LANES, f, ex),   \
+                                  kAggThreads, 0, st>>>(wl, ex, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi)
   if (wkind == 0) GTA_AGG(0, false);
   else if (wkind == 1 && !div) GTA_AGG(1, false);
   else if (wkind == 1 && div) GTA_AGG(1, true);
@@ -914,13 +1001,14 @@ static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkL
 }
 
 template <int H>
-static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const float* el, const float* er,
-                        int64_t lder, float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int f, int epi,
-                        float* rowmax, float* rowsum, const uint32_t* er_stats, int64_t col_block) {
+static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const Exchange& ex, const float* el,
+                        const float* er, int64_t lder, float slope, const float* z, int64_t ldz, float* out, int64_t ldo,
+                        int f, int epi, float* rowmax, float* rowsum, const uint32_t* er_stats, int stats_pitch,
+                        int64_t col_block) {
 #define GTA_GAT(L)                                                                                              \
-  gat_aggregate_kernel<L, H><<<persistent_grid(gat_aggregate_kernel<L, H>, wl.num_items, L, f), kAggThreads, 0, \
-                               st>>>(wl, el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi, rowmax,  \
-                                     rowsum, er_stats, col_block)
+  gat_aggregate_kernel<L, H><<<persistent_grid(gat_aggregate_kernel<L, H>, wl.num_items, L, f, ex), kAggThreads, \
+                               0, st>>>(wl, ex, el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi,     \
+                                        rowmax, rowsum, er_stats, stats_pitch, col_block)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
     case 8: if (H <= 8) { GTA_GAT(8); return GTA_OK; } break;
@@ -932,7 +1020,8 @@ static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const fl
 }
 
 // common argument checks, the RESET phase (clear the chain flags of every feature window) and the item
-// counters (cleared before every launch).  chain_state = [windows][num_slots] flags, then [windows] counters.
+// counters (cleared before every launch).  chain_state = [windows][num_slots] flags, then [windows] item
+// counters, then GTA_MAX_RANKS slot-arrival counters of an exchange.
 static int prepare_worklist(const char* who, WorkList& wl, int32_t* chain_state, int32_t f, int32_t phases,
                             cudaStream_t st) {
   GTA_REQUIRE(chain_state, "%s: chain_state is required (chain flags and the item counters live there)", who);
@@ -946,7 +1035,7 @@ static int prepare_worklist(const char* who, WorkList& wl, int32_t* chain_state,
     count_launch();
   }
   if ((phases & GTA_PHASE_MAIN) && wl.num_items > 0) {
-    GTA_CUDA(cudaMemsetAsync(wl.work_counter, 0, windows * sizeof(int32_t), st));
+    GTA_CUDA(cudaMemsetAsync(wl.work_counter, 0, (windows + GTA_MAX_RANKS) * sizeof(int32_t), st));
     count_launch();
     CachePolicies pol;
     int rc = cache_policies(&pol);
@@ -968,7 +1057,8 @@ int32_t gta_gat_partial_stride(int32_t f, int32_t heads) { return gat_partial_st
 int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
                       const int32_t* indices, int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f, int32_t epilogue,
-                      float* partials, int32_t* chain_state, int32_t phases, void* stream_) {
+                      float* partials, int32_t* chain_state, const gta_exchange_t* exchange, int32_t phases,
+                      void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
   GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_aggregate_f32: bad item count");
@@ -991,14 +1081,37 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
       return GTA_ERR_UNSUPPORTED;
     }
   }
+  Exchange ex;
+  rc = make_exchange("gta_aggregate_f32", exchange, wl.work_counter + (f + 127) / 128, ldx, &ex);
+  if (rc != GTA_OK) return rc;
+  GTA_REQUIRE(ex.world <= 1 || ex.table == reinterpret_cast<const char*>(x), "gta_aggregate_f32: x is not the exchange table");
   switch (lanes_for(f)) {
-    case 4: dispatch_aggregate<4>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    case 8: dispatch_aggregate<8>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    case 16: dispatch_aggregate<16>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    default: dispatch_aggregate<32>(wkind, div, st, wl, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 4: dispatch_aggregate<4>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 8: dispatch_aggregate<8>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    case 16: dispatch_aggregate<16>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    default: dispatch_aggregate<32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
   }
   GTA_CHECK_LAUNCH("aggregate_kernel");
   return GTA_OK;
+}
+
+int gta_gather_peak_probe(const float* table, int64_t rows, int64_t ld, int32_t f, int64_t gathers_per_group,
+                          float* sink, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (!(table && sink && rows > 0 && rows < (int64_t(1) << 32) && f >= 4 && f <= 128 && f % 4 == 0 && ld >= f &&
+        ld % 4 == 0 && gathers_per_group > 0)) {
+    set_error("gta_gather_peak_probe: bad arguments");
+    return -GTA_ERR_INVALID;
+  }
+  CachePolicies pol;
+  if (cache_policies(&pol) != GTA_OK) return -GTA_ERR_CUDA;
+  const int lanes = lanes_for(f);
+  const int ctas = resident_ctas(gather_peak_kernel);
+  gather_peak_kernel<<<ctas, kAggThreads, 0, st>>>(table, uint32_t(rows), uint32_t(ld) * 4u, lanes, gathers_per_group,
+                                                  reinterpret_cast<float4*>(sink), pol.keep);
+  count_launch();
+  if (check_cuda(cudaGetLastError(), "gather_peak_kernel") != GTA_OK) return -GTA_ERR_CUDA;
+  return ctas * kAggThreads / lanes;          // > 0: the number of groups that ran (each did gathers_per_group gathers)
 }
 
 int gta_er_stats(const float* er, int64_t lder, int64_t num_sources, int64_t col_block, int32_t heads,
@@ -1028,7 +1141,8 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
                           const int32_t* indices, const float* el, const float* er, int64_t lder, int32_t heads,
                           float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_state,
-                          const uint32_t* er_stats, int64_t col_block, int32_t phases, void* stream_) {
+                          const uint32_t* er_stats, int64_t col_block, const gta_exchange_t* exchange,
+                          int32_t phases, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
   GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_gat_aggregate_f32: bad item count");
@@ -1048,6 +1162,18 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
     set_error("gta_gat_aggregate_f32: per-head width f/heads=%d is not a multiple of 4", f / heads);
     return GTA_ERR_UNSUPPORTED;
   }
+  Exchange ex;
+  rc = make_exchange("gta_gat_aggregate_f32", exchange, wl.work_counter + (f + 127) / 128, ldz, &ex);
+  if (rc != GTA_OK) return rc;
+  int stats_pitch = 2 * heads;
+  if (ex.world > 1) {
+    GTA_REQUIRE(ex.table == reinterpret_cast<const char*>(z), "gta_gat_aggregate_f32: z is not the exchange table");
+    // the slot owners published their er range with the step; a slot's statistics are valid once it has landed
+    er_stats = &ex.signals->stats[ex.step & 1][0][0];
+    stats_pitch = 64;
+    col_block = ex.slot_rows;
+    if ((heads & (heads - 1)) != 0 || heads > 32) er_stats = nullptr;
+  }
   // the bound path does not track the true row maximum: callers that want it back run the online softmax
   if (rowmax != nullptr) er_stats = nullptr;
   const int lanes = lanes_for(f);
@@ -1056,7 +1182,7 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   const bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
   if (staged) {
     rc = GTA_ERR_UNSUPPORTED;
-#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, st, wl, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, col_block)
+#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
     switch (heads) {
       case 1: GTA_GAT_H(1); break;
       case 2: GTA_GAT_H(2); break;
@@ -1068,10 +1194,10 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
       return rc;
     }
   } else {
-#define GTA_LLH(L)                                                                                                 \
-  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f), kAggThreads, 0,  \
-                                st>>>(wl, el, er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epilogue, \
-                                      rowmax, rowsum, er_stats, col_block)
+#define GTA_LLH(L)                                                                                                  \
+  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f, ex), kAggThreads, 0, \
+                                st>>>(wl, ex, el, er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,         \
+                                      epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
     switch (lanes) {
       case 4: GTA_LLH(4); break;
       case 8: GTA_LLH(8); break;

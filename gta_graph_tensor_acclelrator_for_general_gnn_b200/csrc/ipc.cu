@@ -1,18 +1,63 @@
-// Peer-to-peer exchange of the source-side tables over NVLink WITHOUT streaming multiprocessors.
+// Peer-to-peer plumbing of the in-kernel source exchange (see gta_exchange_t in include/gta_b200.h).
 //
-// The per-layer exchange of a destination-partitioned run is an all-gather of [Z | er].  As an NCCL
-// collective it occupies SMs, so it cannot hide under the aggregation kernel (measured on 8 B200:
-// chunked NCCL all-gathers overlapped with the gather kernel made the step SLOWER, 1.01 -> 1.18 ms).
-// Here every rank publishes its slot buffer through CUDA IPC once at setup; each step it PULLS its
-// peers' slots with plain device-to-device copies on a copy stream -- copy engines, NVLink, no SMs --
-// chunk by chunk, so column block q of the work list can start while chunk q+1 is in flight.
+// The per-layer exchange of a destination-partitioned run is an all-gather of [Z | er] (SURVEY.md
+// section 8e).  As an NCCL collective it is a launch of its own between the GEMM and the aggregation
+// and it occupies SMs: on 8 B200 it was 0.21 ms of a 1.0 ms layer, un-overlapped, and the round-1
+// attempts to overlap it (chunked NCCL all-gathers; copy-engine pulls gated by events) both lost to
+// launch boundaries and SM contention.  Here the transfer happens INSIDE the aggregation launch
+// (aggregate.cu: a few CTAs pull the peers' slots with NVLink loads while the others already reduce the
+// rank's own column block); this file holds what is left outside it:
 //
-//   gta_ipc_alloc / gta_ipc_free     slot buffers (cudaMalloc'ed so the IPC handle names a base pointer)
+//   gta_ipc_alloc / gta_ipc_free     tables and signal blocks (cudaMalloc'ed so the IPC handle names a base pointer)
 //   gta_ipc_export / gta_ipc_open    64-byte handle out / peer mapping in (lazy peer access)
-//   gta_copy_many                    n asynchronous copies on one stream
+//   gta_exchange_publish             "my slot is written": er range + step number into every peer's signal block
 #include <string.h>
 
 #include "common.cuh"
+#include "exchange.cuh"
+
+namespace gta {
+
+// One CTA.  Range of this rank's er rows per head (ordered-int codes, as gta_er_stats), written with the
+// step number to the signal block of every rank q at the slot index q uses for this rank.
+__global__ void __launch_bounds__(1024)
+exchange_publish_kernel(const float* __restrict__ er, int64_t lder, int64_t rows, int heads, int rank, int world,
+                        int step, SignalPointers peers) {
+  __shared__ uint32_t s_code[2 * 32];
+  const int t = threadIdx.x;
+  if (t < 64) s_code[t] = 0u;
+  __syncthreads();
+  if (heads > 0) {
+    const int h = t & (heads - 1);
+    float mx = -INFINITY, mn = INFINITY;
+    bool seen = false;
+    for (int64_t r = t / heads; r < rows; r += blockDim.x / heads) {
+      const float v = er[r * lder + h];
+      mx = fmaxf(mx, v);
+      mn = fminf(mn, v);
+      seen = true;
+    }
+    if (seen) {
+      atomicMax(&s_code[h], ordered_code(mx));
+      atomicMax(&s_code[32 + h], ordered_code(-mn));
+    }
+  }
+  __syncthreads();
+  const int parity = step & 1;
+  for (int i = t; i < world * 2 * heads; i += blockDim.x) {
+    const int q = i / (2 * heads), j = i % (2 * heads);          // peer q, word j of [max codes | -min codes]
+    const int slot = rank >= q ? rank - q : rank - q + world;    // where q keeps this rank
+    peers.sig[q]->stats[parity][slot][j] = s_code[(j / heads) * 32 + (j % heads)];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < world) {
+    const int slot = rank >= t ? rank - t : rank - t + world;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(&peers.sig[t]->ready[slot]), "r"(step) : "memory");
+  }
+}
+
+}  // namespace gta
 
 using namespace gta;
 
@@ -52,14 +97,22 @@ int gta_ipc_close(void* mapped) {
   return GTA_OK;
 }
 
-// dst[i] <- src[i] (bytes[i]) for i < n, all on `stream`; pointers may be peer mappings
-int gta_copy_many(void* const* dst, const void* const* src, const int64_t* bytes, int32_t n, void* stream_) {
+size_t gta_exchange_signal_bytes(void) { return sizeof(ExchangeSignals); }
+
+int gta_exchange_publish(const float* er, int64_t lder, int64_t rows, int32_t heads, int32_t rank, int32_t world,
+                         int32_t step, void* const* h_peer_signals, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(n >= 0 && (n == 0 || (dst && src && bytes)), "gta_copy_many: bad arguments");
-  for (int32_t i = 0; i < n; ++i) {
-    if (bytes[i] <= 0) continue;
-    GTA_CUDA(cudaMemcpyAsync(dst[i], src[i], size_t(bytes[i]), cudaMemcpyDefault, st));
+  GTA_REQUIRE(h_peer_signals && world >= 1 && world <= GTA_MAX_RANKS && rank >= 0 && rank < world && step >= 1 && rows >= 0,
+              "gta_exchange_publish: bad arguments (world %d, rank %d, step %d)", world, rank, step);
+  GTA_REQUIRE(heads == 0 || (er && lder >= heads), "gta_exchange_publish: er is required for %d heads", heads);
+  if (heads < 0 || heads > 32 || (heads & (heads - 1)) != 0) heads = 0;      // no statistics: the consumers run the online softmax
+  SignalPointers peers{};
+  for (int q = 0; q < world; ++q) {
+    GTA_REQUIRE(h_peer_signals[q], "gta_exchange_publish: signal block of rank %d is not mapped", q);
+    peers.sig[q] = static_cast<ExchangeSignals*>(h_peer_signals[q]);
   }
+  exchange_publish_kernel<<<1, 1024, 0, st>>>(er, lder, rows, heads, rank, world, step, peers);
+  GTA_CHECK_LAUNCH("exchange_publish_kernel");
   return GTA_OK;
 }
 

@@ -143,16 +143,16 @@ __global__ void low_word_kernel(const uint64_t* __restrict__ keys, int64_t n, in
 }
 
 // ---- source-id remap for destination-partitioned execution ---------------------------------
-// The all-gathered source table is [parts, stride, F] (every rank's rows padded to `stride`),
-// so global source id j owned by rank p becomes p*stride + (j - bounds[p]).  Monotonic in j:
-// the ascending-source reduction order of every row is preserved.
-// With chunks = G > 1 the table is [G, parts, stride/G, F]: chunk q of EVERY rank is contiguous,
-// so chunk q can be all-gathered (and aggregated, as column block q) while chunk q+1 is still in
-// flight.  id = q*(parts*cs) + p*cs + (o - q*cs), cs = stride/G, o = j - bounds[p].  Not monotonic
-// in j: the caller re-sorts every row by the new ids (still a fixed, deterministic order).
+// The gathered source table of a rank is [parts, stride, F]: `parts` slots of `stride` rows (every
+// rank's rows padded to `stride`).  Slot k of rank r holds the rows of rank (r + k) mod parts, so the
+// rank's OWN rows are slot 0 and the work list -- ordered by column block = slot -- starts on data that
+// needs no transfer, then walks the peers in ring order while their slots arrive (ipc.cu, aggregate.cu).
+// Global source id j owned by rank p becomes ((p - rotate) mod parts)*stride + (j - bounds[p]).
+// rotate = 0: p*stride + offset, monotonic in j (the layout of an NCCL all-gather).  rotate > 0 is a
+// cyclic shift of every row's ascending source list: the caller re-sorts the rows by the new ids
+// (a fixed, deterministic reduction order, but not the single-GPU one).
 __global__ void remap_sources_kernel(const int32_t* __restrict__ in, int64_t n, const int64_t* __restrict__ bounds,
-                                     int parts, int64_t stride, int chunks, int32_t* __restrict__ out) {
-  const int64_t cs = stride / chunks;
+                                     int parts, int64_t stride, int rotate, int32_t* __restrict__ out) {
   int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   int64_t step = int64_t(gridDim.x) * blockDim.x;
   for (; i < n; i += step) {
@@ -162,9 +162,8 @@ __global__ void remap_sources_kernel(const int32_t* __restrict__ in, int64_t n, 
       int mid = (lo + hi) >> 1;
       if (bounds[mid] <= j) lo = mid; else hi = mid;
     }
-    const int64_t o = j - bounds[lo];
-    const int64_t q = o / cs;
-    out[i] = int32_t(q * (parts * cs) + int64_t(lo) * cs + (o - q * cs));
+    const int slot = lo >= rotate ? lo - rotate : lo - rotate + parts;
+    out[i] = int32_t(int64_t(slot) * stride + (j - bounds[lo]));
   }
 }
 
@@ -297,15 +296,14 @@ int gta_reorder(const int64_t* indptr, int64_t num_nodes, int64_t* perm, void* w
 }
 
 int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* bounds, int32_t parts,
-                      int64_t stride, int32_t chunks, int32_t* out, void* stream_) {
+                      int64_t stride, int32_t rotate, int32_t* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (num_edges == 0) return GTA_OK;
   GTA_REQUIRE(indices && bounds && out, "gta_remap_sources: null pointer");
   GTA_REQUIRE(parts >= 1 && stride >= 1 && int64_t(parts) * stride < (int64_t(1) << 31),
               "gta_remap_sources: parts*stride must fit int32");
-  GTA_REQUIRE(chunks >= 1 && stride % chunks == 0, "gta_remap_sources: stride %lld is not a multiple of %d chunks",
-              (long long)stride, chunks);
-  remap_sources_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(indices, num_edges, bounds, parts, stride, chunks, out);
+  GTA_REQUIRE(rotate >= 0 && rotate < parts, "gta_remap_sources: rotate=%d outside [0, %d)", rotate, parts);
+  remap_sources_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(indices, num_edges, bounds, parts, stride, rotate, out);
   GTA_CHECK_LAUNCH("remap_sources_kernel");
   return GTA_OK;
 }

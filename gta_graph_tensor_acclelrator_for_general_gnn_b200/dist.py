@@ -1,21 +1,27 @@
 """Destination-range partitioning over the GPUs of one box.
 
-One process per GPU (torchrun).  Rank p owns CSR rows ``[bounds[p], bounds[p+1])`` -- bounds
-balanced by edge count (gta_partition) -- and the matching rows of every node tensor.  The only
-exchange per layer is an all-gather of the source-side tables (``[Z | er]`` for GAT, ``Z`` for GCN)
-over NVLink (NCCL); destination rows are disjoint, so there is no reduction.
+One process per GPU (torchrun).  Rank p owns CSR rows ``[bounds[p], bounds[p+1])`` -- bounds balanced
+by edge count (gta_partition) -- and the matching rows of every node tensor.  The only exchange per
+layer is a replication of the source-side tables (``[Z | er]`` for GAT, ``Z`` for GCN); destination rows
+are disjoint, so there is no reduction.
 
-Overlap.  Every rank's rows are padded to ``stride`` and cut into ``chunks`` equal pieces; the
-gathered table is laid out ``[chunks, world, stride/chunks, F]`` so that chunk q of EVERY rank is
-one contiguous NCCL all-gather and one COLUMN BLOCK of the aggregation work list.  The all-gathers
-run on a communication stream, chunk after chunk; the aggregation kernel of column block q waits
-only for chunk q's event, so the transfer of chunk q+1 hides under the gathers of chunk q
-(measured on 8 B200: one 119 MB all-gather is 0.2 ms of a 1.0 ms layer).  Source ids are remapped
-once at setup (gta_remap_sources) and every row is re-sorted by the new ids: a fixed reduction
-order, deterministic, but not the single-GPU order when chunks > 1.
+Two exchanges implement it:
+
+* :class:`FusedExchange` (default): the transfer happens INSIDE the aggregation launch.  Every rank keeps
+  a gathered table ``[world, stride, ld]`` whose slot k holds the rows of rank ``(rank + k) % world`` (its own
+  rows first), published to the peers through CUDA IPC.  The GEMM writes slot 0, ``gta_exchange_publish``
+  tells the peers, and the aggregation kernel's first CTAs pull the peers' slots over NVLink in ring order
+  while the other CTAs already reduce the column block of the rank's own sources and wait, slot by slot, for
+  the rest (csrc/exchange.cuh).  No NCCL call, no communication kernel, no launch boundary in the step.
+* :class:`SourceExchange`: one NCCL all-gather per layer between the GEMM and the aggregation (the
+  round-1 path; kept as the baseline the fused exchange is measured against, ``bench.py --exchange nccl``).
+
+Source ids are remapped once at setup (gta_remap_sources).  With the rotated layout of the fused exchange
+every row is re-sorted by the new ids: a fixed reduction order, deterministic, but not the single-GPU one.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 
 import torch
@@ -24,16 +30,21 @@ import torch.distributed as dist
 from . import _cabi, kernels
 from .graph import DeviceGraph, _stream, csr_from_coo, partition_bounds, slice_rows
 
+#: a slot must be a whole number of 128-byte lines (a cached line never straddles two slots, one of which
+#: may not have landed yet): row pitches are multiples of 16 bytes, so 8 rows always are
+SLOT_ROW_MULTIPLE = 8
+
 
 @dataclass
 class Partition:
     rank: int
     world: int
     bounds: list          # python ints, len world+1
-    stride: int           # padded rows per rank in gathered tables (multiple of 4*chunks)
-    local: DeviceGraph    # zero-based local CSR, sources remapped into the gathered table
+    stride: int           # padded rows per rank in gathered tables (multiple of SLOT_ROW_MULTIPLE)
+    local: DeviceGraph    # zero-based local CSR, sources remapped into the gathered table; .perm maps its
+                          # edges to positions in the rank's slice of the global CSR edge order
     num_nodes: int
-    chunks: int = 1
+    rotate: bool = True   # slot k = rank (rank + k) % world (fused exchange); False: slot k = rank k (all-gather)
 
     @property
     def row_begin(self) -> int:
@@ -47,138 +58,124 @@ class Partition:
     def rows(self) -> int:
         return self.row_end - self.row_begin
 
-    @property
-    def chunk_rows(self) -> int:
-        return self.stride // self.chunks
+    def slot_of(self, owner: int) -> int:
+        return (owner - self.rank) % self.world if self.rotate else owner
 
-    @property
-    def col_block(self) -> int:
-        """Source ids per column block of the work list = one gathered chunk (0: no chunking)."""
-        return self.world * self.chunk_rows if self.chunks > 1 else 0
+    def owner_of(self, slot: int) -> int:
+        return (self.rank + slot) % self.world if self.rotate else slot
+
+    def permute_edges(self, t: torch.Tensor) -> torch.Tensor:
+        """Edge tensor given in the global CSR order of this rank's rows -> the local graph's edge order."""
+        return t if self.local.perm is None else t[self.local.perm]
 
 
-def make_partition(full: DeviceGraph, rank: int, world: int, chunks: int = 1) -> Partition:
-    """Cut a (replicated) full graph into this rank's destination range."""
+def _stride_for(bounds, world: int) -> int:
+    stride = max(bounds[p + 1] - bounds[p] for p in range(world))
+    return max((stride + SLOT_ROW_MULTIPLE - 1) // SLOT_ROW_MULTIPLE * SLOT_ROW_MULTIPLE, SLOT_ROW_MULTIPLE)
+
+
+def _localise(rows_of_edge: torch.Tensor, src: torch.Tensor, b: torch.Tensor, bounds, rank: int, world: int,
+              num_nodes: int, rotate: bool) -> Partition:
+    """Local CSR of one rank from its edges (local destination row, GLOBAL source id)."""
     lib = _cabi.load()
+    stride = _stride_for(bounds, world)
+    rows = bounds[rank + 1] - bounds[rank]
+    remapped = torch.empty_like(src)
+    _cabi.check(lib.gta_remap_sources(_cabi.ptr(src), int(src.shape[0]), _cabi.ptr(b), world, stride,
+                                      rank if rotate else 0, _cabi.ptr(remapped), _stream()), "gta_remap_sources")
+    local = csr_from_coo(rows_of_edge, remapped, rows, want_perm=True)
+    local.num_nodes = num_nodes
+    local.num_sources = world * stride
+    return Partition(rank, world, bounds, stride, local, num_nodes, rotate)
+
+
+def make_partition(full: DeviceGraph, rank: int, world: int, rotate: bool = True) -> Partition:
+    """Cut a (replicated) full graph into this rank's destination range."""
     b = partition_bounds(full, world)
     bounds = [int(v) for v in b.cpu().tolist()]
-    stride = max(bounds[p + 1] - bounds[p] for p in range(world))
-    unit = 4 * chunks
-    stride = (stride + unit - 1) // unit * unit
     local = slice_rows(full, bounds[rank], bounds[rank + 1])
-    remapped = torch.empty_like(local.indices)
-    _cabi.check(lib.gta_remap_sources(_cabi.ptr(local.indices), local.num_edges, _cabi.ptr(b), world, stride, chunks,
-                                      _cabi.ptr(remapped), _stream()), "gta_remap_sources")
-    if chunks > 1:
-        # the chunked layout is not monotonic in the source id: re-sort every row by the new ids
-        rows = local.num_rows
-        deg = (local.indptr[1:] - local.indptr[:-1])
-        row_of_edge = torch.repeat_interleave(torch.arange(rows, dtype=torch.int32, device=deg.device), deg)
-        local = csr_from_coo(row_of_edge, remapped, rows)
-        local.num_nodes = full.num_nodes
-    else:
-        local.indices = remapped
-    local.num_sources = world * stride
-    return Partition(rank, world, bounds, stride, local, full.num_nodes, chunks)
+    deg = local.indptr[1:] - local.indptr[:-1]
+    rows_of_edge = torch.repeat_interleave(torch.arange(local.num_rows, dtype=torch.int32, device=deg.device), deg)
+    return _localise(rows_of_edge, local.indices, b, bounds, rank, world, full.num_nodes, rotate)
+
+
+def partition_from_coo(dst: torch.Tensor, src: torch.Tensor, num_nodes: int, rank: int, world: int,
+                       rotate: bool = True) -> Partition:
+    """Partition ON BUILD: from the (replicated, device-resident) edge list straight to this rank's local CSR.
+    Only a degree histogram of the whole graph is formed, never its CSR (RMAT-24: 1 GB of indices per rank
+    saved, and one sort of E/world edges instead of E).  Same bounds as :func:`make_partition`."""
+    lib = _cabi.load()
+    deg = torch.bincount(dst, minlength=num_nodes)
+    indptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=dst.device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    b = torch.empty(world + 1, dtype=torch.int64, device=dst.device)
+    _cabi.check(lib.gta_partition(_cabi.ptr(indptr), num_nodes, world, _cabi.ptr(b), _stream()), "gta_partition")
+    bounds = [int(v) for v in b.cpu().tolist()]
+    mine = (dst >= bounds[rank]) & (dst < bounds[rank + 1])
+    rows_of_edge = (dst[mine] - bounds[rank]).to(torch.int32)
+    return _localise(rows_of_edge, src[mine].contiguous(), b, bounds, rank, world, num_nodes, rotate)
 
 
 class SourceExchange:
-    """All-gather of a local ``[rows, F]`` table into the gathered ``[chunks, world, stride/chunks, F]``
-    table.  Buffers are cached per width, so the steady state allocates nothing."""
+    """NCCL all-gather of a local ``[rows, F]`` table into the gathered ``[world, stride, F]`` table (slot k =
+    rank k: needs a partition built with ``rotate=False``).  Buffers are cached per width, so the steady state
+    allocates nothing."""
+
+    fused = False
 
     def __init__(self, part: Partition, group=None):
+        if part.rotate and part.world > 1:
+            raise ValueError("the NCCL all-gather lays slots out in rank order: build the partition with rotate=False")
         self.part = part
         self.group = group
         self._buf = {}
-        self._comm = None
-        self._events = None
 
     # -- layout ---------------------------------------------------------------------------------
     def buffer(self, width: int, device) -> torch.Tensor:
         key = (width, torch.device(device))
         if key not in self._buf:
             p = self.part
-            ld = (width + 3) // 4 * 4
-            self._buf[key] = torch.zeros((p.chunks, p.world, p.chunk_rows, ld), dtype=torch.float32, device=device)
+            self._buf[key] = torch.zeros((p.world, p.stride, kernels.pad4(width)), dtype=torch.float32, device=device)
         return self._buf[key]
 
-    def table(self, width: int, device) -> torch.Tensor:
-        """The gathered table as a flat ``[chunks*world*chunk_rows, width]`` view (what kernels index)."""
-        buf = self.buffer(width, device)
-        return buf.view(-1, buf.shape[-1])[:, :width]
-
-    def store_local(self, t: torch.Tensor, width: int, col: int = 0) -> None:
-        """Copy this rank's ``[rows, w]`` table into columns ``[col, col+w)`` of its chunk slots."""
-        p = self.part
-        buf = self.buffer(width, t.device)
-        cs = p.chunk_rows
-        w = int(t.shape[1])
-        for q in range(p.chunks):
-            lo, hi = q * cs, min((q + 1) * cs, p.rows)
-            if hi > lo:
-                buf[q, p.rank, :hi - lo, col:col + w].copy_(t[lo:hi])
-
     def local_views(self, f: int, h: int, device):
-        """``(z [rows, f], er [rows, h])`` views of this rank's slot of the gathered ``[F | H]`` table,
-        for producers (the GEMM) that write there directly.  Only when the slot is one contiguous
-        piece (chunks == 1); otherwise None."""
+        """``(z [rows, f], er [rows, h])`` views of this rank's slot of the gathered ``[F | H]`` table, for
+        producers (the GEMM) that write there directly."""
         p = self.part
-        if p.chunks != 1:
-            return None
-        width = f + (h + 3) // 4 * 4
-        slot = self.buffer(width, device)[0, p.rank, :p.rows]
+        slot = self.buffer(f + kernels.pad4(h), device)[p.slot_of(p.rank), :p.rows]
         return slot[:, :f], slot[:, f:f + h]
 
+    def _store(self, t: torch.Tensor, width: int, col: int) -> None:
+        p = self.part
+        self.buffer(width, t.device)[p.slot_of(p.rank), :p.rows, col:col + int(t.shape[1])].copy_(t)
+
     # -- collective -------------------------------------------------------------------------------
-    def gather(self, width: int, device, overlap: bool = False):
-        """All-gather every chunk in place.  ``overlap=False``: the current stream waits for all of
-        them, returns the table.  ``overlap=True``: the transfers run on the communication stream
-        and ``(table, [event per chunk])`` is returned; consumers wait per chunk."""
+    def _gather(self, width: int, device) -> torch.Tensor:
         p = self.part
         buf = self.buffer(width, device)
-        table = buf.view(-1, buf.shape[-1])[:, :width]
-        if p.world == 1:
-            return (table, [None] * p.chunks) if overlap else table
-        if not overlap:
-            for q in range(p.chunks):
-                dist.all_gather_into_tensor(buf[q].view(-1, buf.shape[-1]), buf[q, p.rank], group=self.group)
-            return table
-        cur = torch.cuda.current_stream()
-        if self._comm is None:
-            self._comm = torch.cuda.Stream()
-            self._events = [torch.cuda.Event() for _ in range(p.chunks)]
-        self._comm.wait_stream(cur)                 # the local slots were written on the compute stream
-        with torch.cuda.stream(self._comm):
-            for q in range(p.chunks):
-                dist.all_gather_into_tensor(buf[q].view(-1, buf.shape[-1]), buf[q, p.rank], group=self.group)
-                self._events[q].record(self._comm)
-        return table, list(self._events)
+        if p.world > 1:
+            dist.all_gather_into_tensor(buf.view(-1, buf.shape[-1]), buf[p.rank], group=self.group)
+        return buf.view(-1, buf.shape[-1])[:, :width]
 
     @kernels._timed("nccl_all_gather")
-    def gather_pair(self, z: torch.Tensor, er: torch.Tensor, overlap: bool = False):
+    def gather_pair(self, z: torch.Tensor, er: torch.Tensor):
         """One gathered table for the two source-side tensors of a GAT layer: every source row is
-        ``[z (F) | er (H)]``.  Returns ``(z_view, er_view, events | None)`` (strided views)."""
+        ``[z (F) | er (H)]``.  Returns ``(z_view, er_view, gate)`` (strided views; gate is None: complete)."""
         f, h = int(z.shape[1]), int(er.shape[1])
-        width = f + (h + 3) // 4 * 4
+        width = f + kernels.pad4(h)
         views = self.local_views(f, h, z.device)
-        in_place = views is not None and views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()
-        if not in_place:             # the producer did not write into the slot: copy
-            self.store_local(z, width, 0)
-            self.store_local(er, width, f)
-        if overlap and self.part.chunks > 1:
-            full, events = self.gather(width, z.device, overlap=True)
-        else:
-            full, events = self.gather(width, z.device), None
-        return full[:, :f], full[:, f:f + h], events
+        if not (views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()):
+            self._store(z, width, 0)          # the producer did not write into the slot: copy
+            self._store(er, width, f)
+        full = self._gather(width, z.device)
+        return full[:, :f], full[:, f:f + h], None
 
     @kernels._timed("nccl_all_gather")
-    def gather_one(self, t: torch.Tensor, overlap: bool = False):
-        """``(table, events | None)`` for a single source-side tensor (GCN: Z)."""
+    def gather_one(self, t: torch.Tensor):
+        """``(table, gate)`` for a single source-side tensor (GCN: Z)."""
         width = int(t.shape[1])
-        self.store_local(t, width, 0)
-        if overlap and self.part.chunks > 1:
-            return self.gather(width, t.device, overlap=True)
-        return self.gather(width, t.device), None
+        self._store(t, width, 0)
+        return self._gather(width, t.device), None
 
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         """Executor ``source_table`` hook for consumers that need the whole table at once."""
@@ -186,15 +183,17 @@ class SourceExchange:
             return t            # already a gathered table
         return self.gather_one(t)[0]
 
+    def last_table(self, width: int) -> torch.Tensor:
+        """The gathered ``[world*stride, width]`` table of the last gather_* call of that width."""
+        buf = self._buf[next(k for k in self._buf if k[0] == width)]
+        return buf.view(-1, buf.shape[-1])[:, :width]
 
-# ---- peer-to-peer exchange on the copy engines --------------------------------------------------
 
 class _IpcBuffer:
-    """fp32 buffer cudaMalloc'ed by the library (so its CUDA IPC handle names a base pointer), exposed
-    to torch through ``__cuda_array_interface__``."""
+    """Buffer cudaMalloc'ed by the library (so its CUDA IPC handle names a base pointer), exposed to torch
+    through ``__cuda_array_interface__`` as fp32."""
 
     def __init__(self, shape):
-        import ctypes as C
         self.lib = _cabi.load()
         self.shape = tuple(int(v) for v in shape)
         n = 4
@@ -211,7 +210,6 @@ class _IpcBuffer:
         return torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
 
     def handle(self) -> bytes:
-        import ctypes as C
         buf = C.create_string_buffer(64)
         _cabi.check(self.lib.gta_ipc_export(self.ptr, buf), "gta_ipc_export")
         return buf.raw
@@ -222,133 +220,175 @@ class _IpcBuffer:
             self.ptr = 0
 
 
-class PeerExchange(SourceExchange):
-    """Same contract as :class:`SourceExchange`, but the transfer is a set of device-to-device copies
-    from the peers' IPC-mapped slot buffers on a copy stream (copy engines over NVLink, no SMs), so it
-    really overlaps the aggregation kernel.  Per step: a one-element NCCL all-reduce on the compute
-    stream (every rank's slot is written), then ``chunks`` groups of ``world`` copies, one event per
-    chunk.  The slot buffers are double-buffered: a peer may still be pulling step i while this rank
-    already writes step i+1.  Raises ``RuntimeError`` on every rank if any rank cannot map its peers
-    (the caller falls back to the NCCL all-gather)."""
+class Gate:
+    """What an aggregation launch needs to pull the peers' slots itself: the ``gta_exchange_t`` of one step."""
 
-    def __init__(self, part: Partition, group=None):
-        super().__init__(part, group)
+    def __init__(self, struct: _cabi.Exchange, keep=()):
+        self.struct = struct
+        self._keep = keep
+
+    @property
+    def slot_rows(self) -> int:
+        return int(self.struct.slot_rows)
+
+    def byref(self):
+        return C.byref(self.struct)
+
+
+class FusedExchange:
+    """In-kernel exchange (module docstring).  ``peers`` (tests, single-GPU emulation of every rank): the other
+    ranks' FusedExchange objects of this process; otherwise the peers are the ranks of ``group`` and the tables
+    and signal blocks are mapped through CUDA IPC.  Raises ``RuntimeError`` on every rank if any rank cannot map
+    its peers (the caller falls back to the NCCL all-gather)."""
+
+    fused = True
+
+    def __init__(self, part: Partition, group=None, copy_ctas: int = 0):
+        if not part.rotate and part.world > 1:
+            raise ValueError("the fused exchange keeps the rank's own rows in slot 0: build the partition with rotate=True")
+        if part.world > _cabi.MAX_RANKS:
+            raise ValueError(f"at most {_cabi.MAX_RANKS} ranks")
+        self.part = part
+        self.group = group
+        self.copy_ctas = copy_ctas
+        self.step = 0
         self._state = {}
+        self._emulated = None
+
+    def emulate_with(self, peers) -> None:
+        """Single-process emulation: ``peers[q]`` is rank q's FusedExchange (this object at [rank])."""
+        self._emulated = list(peers)
+
+    # -- setup: tables (two step parities) + signal block, published to / mapped from the peers ------------
+    def _alloc(self, width: int, device):
+        p = self.part
+        lib = _cabi.load()
+        ld = kernels.pad4(width)
+        st = {"ld": ld, "tables": [_IpcBuffer((p.world, p.stride, ld)) for _ in range(2)],
+              "signals": _IpcBuffer(((int(lib.gta_exchange_signal_bytes()) + 3) // 4,))}
+        st["tables_t"] = [t.tensor() for t in st["tables"]]
+        return st
 
     def _setup(self, width: int, device):
-        import ctypes as C
         key = (width, torch.device(device))
         if key in self._state:
             return self._state[key]
         p = self.part
         lib = _cabi.load()
-        ld = (width + 3) // 4 * 4
-        cs = p.chunk_rows
-        st = {"step": 0, "ld": ld}
-        ok = 1
-        err = ""
+        if self._emulated is not None or p.world == 1:
+            st = self._alloc(width, device)
+            st["own"] = True
+            self._state[key] = st
+            return st
+        ok, err, st = 1, "", None
         try:
-            st["mine"] = [_IpcBuffer((p.chunks, cs, ld)) for _ in range(2)]
-            st["mine_t"] = [m.tensor() for m in st["mine"]]
-            handles = [m.handle() for m in st["mine"]]
+            st = self._alloc(width, device)
+            handles = [t.handle() for t in st["tables"]] + [st["signals"].handle()]
         except Exception as exc:          # keep going to the collective below so every rank agrees
-            ok, err, handles = 0, str(exc), [b"", b""]
+            ok, err, handles = 0, str(exc), [b"", b"", b""]
         gathered = [None] * p.world
         dist.all_gather_object(gathered, handles, group=self.group)
-        peer = [[0, 0] for _ in range(p.world)]
+        peer = [[0, 0, 0] for _ in range(p.world)]
         if ok:
             try:
-                for r in range(p.world):
-                    for b in range(2):
-                        if r == p.rank:
-                            peer[r][b] = st["mine"][b].ptr
+                for q in range(p.world):
+                    for i in range(3):
+                        if q == p.rank:
+                            peer[q][i] = (st["tables"] + [st["signals"]])[i].ptr
                         else:
                             mapped = C.c_void_p()
-                            _cabi.check(lib.gta_ipc_open(gathered[r][b], C.byref(mapped)), "gta_ipc_open")
-                            peer[r][b] = int(mapped.value)
+                            _cabi.check(lib.gta_ipc_open(gathered[q][i], C.byref(mapped)), "gta_ipc_open")
+                            peer[q][i] = int(mapped.value)
             except Exception as exc:
                 ok, err = 0, str(exc)
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
-            raise RuntimeError("peer-to-peer exchange unavailable on at least one rank" + (": " + err if err else ""))
-        table = self.buffer(width, device)
-        chunk_bytes = cs * ld * 4
-        plans = []
-        for b in range(2):
-            per_chunk = []
-            for q in range(p.chunks):
-                dsts, srcs, sizes = [], [], []
-                for k in range(p.world):
-                    r = (p.rank + k) % p.world            # own slot first, then round the ring
-                    rows_r = p.bounds[r + 1] - p.bounds[r]
-                    valid = max(0, min(cs, rows_r - q * cs))
-                    if valid == 0:
-                        continue
-                    dsts.append(table.data_ptr() + (q * p.world + r) * chunk_bytes)
-                    srcs.append(peer[r][b] + q * chunk_bytes)
-                    sizes.append(valid * ld * 4)
-                n = len(dsts)
-                per_chunk.append(((C.c_void_p * n)(*dsts), (C.c_void_p * n)(*srcs), (C.c_int64 * n)(*sizes), n))
-            plans.append(per_chunk)
-        st.update(peer=peer, plans=plans, sync=torch.zeros(1, dtype=torch.float32, device=device),
-                  stream=torch.cuda.Stream(), events=[torch.cuda.Event() for _ in range(p.chunks)])
+            raise RuntimeError("fused exchange unavailable on at least one rank" + (": " + err if err else ""))
+        st["peer"] = peer
         self._state[key] = st
         return st
 
-    def local_views(self, f: int, h: int, device):
+    def _peer_ptrs(self, width: int, device, parity: int):
+        """(table pointer of every rank for this parity, signal pointer of every rank)."""
         p = self.part
-        if p.chunks != 1:
-            return None
-        st = self._setup(f + (h + 3) // 4 * 4, device)
-        slot = st["mine_t"][st["step"] % 2][0, :p.rows]
+        st = self._setup(width, device)
+        if self._emulated is not None:
+            others = [pe._setup(width, device) for pe in self._emulated]
+            return [o["tables"][parity].ptr for o in others], [o["signals"].ptr for o in others]
+        if p.world == 1:
+            return [st["tables"][parity].ptr], [st["signals"].ptr]
+        return [st["peer"][q][parity] for q in range(p.world)], [st["peer"][q][2] for q in range(p.world)]
+
+    # -- per step -----------------------------------------------------------------------------------
+    def local_views(self, f: int, h: int, device):
+        """Views of slot 0 (this rank's rows) of the table the NEXT gather_* call will publish."""
+        st = self._setup(f + kernels.pad4(h), device)
+        slot = st["tables_t"][(self.step + 1) & 1][0, :self.part.rows]
         return slot[:, :f], slot[:, f:f + h]
 
-    def _store(self, st, t: torch.Tensor, col: int):
+    def _publish(self, width: int, device, er: torch.Tensor | None) -> Gate:
         p = self.part
-        mine = st["mine_t"][st["step"] % 2]
-        cs, w = p.chunk_rows, int(t.shape[1])
-        for q in range(p.chunks):
-            lo, hi = q * cs, min((q + 1) * cs, p.rows)
-            if hi > lo:
-                mine[q, :hi - lo, col:col + w].copy_(t[lo:hi])
-
-    def _pull(self, st, width: int, device, overlap: bool):
         lib = _cabi.load()
-        p = self.part
-        cur = torch.cuda.current_stream()
-        dist.all_reduce(st["sync"], group=self.group)       # on the compute stream: every slot is written
-        copy = st["stream"]
-        copy.wait_stream(cur)
-        b = st["step"] % 2
-        for q in range(p.chunks):
-            dsts, srcs, sizes, n = st["plans"][b][q]
-            _cabi.check(lib.gta_copy_many(dsts, srcs, sizes, n, copy.cuda_stream), "gta_copy_many")
-            st["events"][q].record(copy)
-        st["step"] += 1
-        buf = self.buffer(width, device)
-        table = buf.view(-1, buf.shape[-1])[:, :width]
-        if overlap and p.chunks > 1:
-            return table, list(st["events"])
-        cur.wait_event(st["events"][-1])
-        return table, None
+        st = self._setup(width, device)
+        self.step += 1
+        parity = self.step & 1
+        tables, signals = self._peer_ptrs(width, device, parity)
+        sig_arr = (C.c_void_p * p.world)(*signals)
+        heads = int(er.shape[1]) if er is not None else 0
+        lder = (int(er.stride(0)) if er.shape[0] > 1 else max(int(er.stride(0)), heads)) if er is not None else 0
+        _cabi.check(lib.gta_exchange_publish(_cabi.ptr(er), lder, p.rows, heads, p.rank, p.world, self.step, sig_arr,
+                                             _stream()), "gta_exchange_publish")
+        ex = _cabi.Exchange()
+        ex.world, ex.rank, ex.step, ex.copy_ctas = p.world, p.rank, self.step, self.copy_ctas
+        ex.slot_rows, ex.row_bytes = p.stride, st["ld"] * 4
+        ex.table, ex.signals = st["tables"][parity].ptr, st["signals"].ptr
+        for k in range(p.world):
+            q = p.owner_of(k)
+            ex.peer_table[k] = tables[q]
+            ex.slot_valid_rows[k] = p.bounds[q + 1] - p.bounds[q]
+        return Gate(ex, keep=(st,))
 
-    @kernels._timed("p2p_gather")
-    def gather_pair(self, z: torch.Tensor, er: torch.Tensor, overlap: bool = False):
+    @kernels._timed("exchange_publish")
+    def gather_pair(self, z: torch.Tensor, er: torch.Tensor):
+        """``(z_table, er_table, gate)``: views of this step's gathered table -- only slot 0 is valid until the
+        aggregation launch that is handed ``gate`` has pulled the rest."""
         f, h = int(z.shape[1]), int(er.shape[1])
-        width = f + (h + 3) // 4 * 4
-        st = self._setup(width, z.device)
+        width = f + kernels.pad4(h)
         views = self.local_views(f, h, z.device)
-        in_place = views is not None and views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()
-        if not in_place:
-            self._store(st, z, 0)
-            self._store(st, er, f)
-        full, events = self._pull(st, width, z.device, overlap)
-        return full[:, :f], full[:, f:f + h], events
+        if not (views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()):
+            views[0].copy_(z)          # the producer did not write into the slot: copy
+            views[1].copy_(er)
+        st = self._setup(width, z.device)
+        gate = self._publish(width, z.device, views[1])
+        table = st["tables_t"][self.step & 1].view(-1, st["ld"])
+        return table[:, :f], table[:, f:f + h], gate
 
-    @kernels._timed("p2p_gather")
-    def gather_one(self, t: torch.Tensor, overlap: bool = False):
+    @kernels._timed("exchange_publish")
+    def gather_one(self, t: torch.Tensor):
         width = int(t.shape[1])
         st = self._setup(width, t.device)
-        self._store(st, t, 0)
-        return self._pull(st, width, t.device, overlap)
+        st["tables_t"][(self.step + 1) & 1][0, :self.part.rows, :width].copy_(t)
+        gate = self._publish(width, t.device, None)
+        return st["tables_t"][self.step & 1].view(-1, st["ld"])[:, :width], gate
+
+    def last_table(self, width: int) -> torch.Tensor:
+        """The gathered ``[world*stride, width]`` table of the last step of that width (complete once the aggregation
+        launch that pulled it has finished)."""
+        st = self._state[next(k for k in self._state if k[0] == width)]
+        return st["tables_t"][self.step & 1].view(-1, st["ld"])[:, :width]
+
+    def __call__(self, t: torch.Tensor) -> torch.Tensor:
+        """Whole table at once for the generic kernels (any legal plan runs): an NCCL all-gather in rank order,
+        rolled into this rank's slot order.  Not the fast path."""
+        p = self.part
+        if t.shape[0] != p.rows:
+            return t
+        width = int(t.shape[1])
+        buf = torch.zeros((p.world, p.stride, kernels.pad4(width)), dtype=torch.float32, device=t.device)
+        buf[p.rank, :p.rows, :width].copy_(t)
+        if p.world > 1:
+            if self._emulated is not None:
+                raise RuntimeError("the emulated fused exchange has no whole-table gather")
+            dist.all_gather_into_tensor(buf.view(-1, buf.shape[-1]), buf[p.rank].clone(), group=self.group)
+        return torch.roll(buf, -p.rank, 0).view(-1, buf.shape[-1])[:, :width]

@@ -223,23 +223,20 @@ class _Run:
         ex = self.o["source_table"]
         self.kernel_log.append(("gta_gat_aggregate_f32", pos))
         if hasattr(ex, "gather_pair"):
-            # partitioned run: [z | er] travel in one gathered table, chunk by chunk on the communication
-            # stream; column block q of the work list starts as soon as chunk q has landed
-            z, er, events = ex.gather_pair(kernels.to_table(self.force(z_value)), self.force(sm[1]), overlap=True)
-            sched = self.g.schedule(col_block=ex.part.col_block) if events is not None else None
-            return kernels.gat_aggregate(self.g, el, er, z, self.o["slope"], epilogue, sched=sched, block_events=events)
+            # partitioned run: [z | er] travel in one gathered table.  NCCL exchange: complete on return (gate is
+            # None).  Fused exchange: only this rank's slot is there yet; the aggregation launch pulls the rest
+            z, er, gate = ex.gather_pair(kernels.to_table(self.force(z_value)), self.force(sm[1]))
+            return kernels.gat_aggregate(self.g, el, er, z, self.o["slope"], epilogue, exchange=gate)
         er = ex(self.force(sm[1]))
         z = ex(kernels.to_table(self.force(z_value)))
         return kernels.gat_aggregate(self.g, el, er, z, self.o["slope"], epilogue)
 
     def _gather_sources(self, x: torch.Tensor):
-        """(table, schedule, chunk events) of a source-side table for the fused aggregate kernels."""
+        """(table, gate) of a source-side table for the fused aggregate kernels (gate: see dist.Gate)."""
         ex = self.o["source_table"]
         if hasattr(ex, "gather_one") and x.shape[0] == ex.part.rows:
-            table, events = ex.gather_one(x, overlap=True)
-            sched = self.g.schedule(col_block=ex.part.col_block) if events is not None else None
-            return table, sched, events
-        return ex(x), None, None
+            return ex.gather_one(x)
+        return ex(x), None
 
     def _by_source(self) -> DeviceGraph:
         """The CSC walk as a graph over EDGE ids: row j lists the CSR positions of the edges whose
@@ -263,9 +260,9 @@ class _Run:
         if src.forced and "rowsum" in src.extra and epilogue == _cabi.EPI_NONE:
             return src.extra["rowsum"]
         if src.kind == "scatter" and src.side == "C" and not src.forced:
-            x, sched, events = self._gather_sources(k.to_table(self.force(src.args[0])))
+            x, gate = self._gather_sources(k.to_table(self.force(src.args[0])))
             self.kernel_log.append(("gta_aggregate_f32:sum", v.pos))
-            return k.aggregate(self.g, x, None, None, epilogue, sched=sched, block_events=events)
+            return k.aggregate(self.g, x, None, None, epilogue, exchange=gate)
         sp = self._split_mul(src)
         if sp is not None:
             xv, wv = sp
@@ -287,9 +284,9 @@ class _Run:
             wt = self.force(wv)
             xl = k.to_table(self.force(xv))
             if wt.dim() == 1 or wt.shape[1] == 1 or (xl.shape[1] // wt.shape[1]) % 4 == 0:
-                x, sched, events = self._gather_sources(xl)
+                x, gate = self._gather_sources(xl)
                 self.kernel_log.append(("gta_aggregate_f32:w", v.pos))
-                return k.aggregate(self.g, x, wt, None, epilogue, sched=sched, block_events=events)
+                return k.aggregate(self.g, x, wt, None, epilogue, exchange=gate)
         if (src.kind == "edge_mm" and not src.forced and src.extra.get("consumers", 1) == 1
                 and src.pos not in self.o["wanted"]):
             # COMP_MM_COMP_ADD (hardware_info.yaml:27-30): sum_k (e_k W) = (sum_k e_k) W -- reduce first, then the

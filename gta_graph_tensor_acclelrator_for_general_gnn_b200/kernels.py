@@ -100,10 +100,11 @@ _agg_ws = _Workspace()      # chain state (partials + flags) of gta_aggregate_f3
 
 def _chain_state(ws: _Workspace, num_slots: int, stride: int, f: int, device):
     """(partials, chain_state) pointers inside one workspace: num_slots*stride floats, then per 128-feature
-    window num_slots int32 chain flags, then one int32 item counter per window (always present)."""
+    window num_slots int32 chain flags, then one int32 item counter per window and the slot-arrival counters
+    of an exchange (always present)."""
     windows = (f + 127) // 128
     base = (num_slots * stride + 3) // 4 * 4
-    buf = ws.get(base + (num_slots + 1) * windows, device)
+    buf = ws.get(base + (num_slots + 1) * windows + _cabi.MAX_RANKS, device)
     return (buf.data_ptr() if num_slots else None), buf.data_ptr() + 4 * base
 
 
@@ -179,12 +180,16 @@ def _launch_blocks(launch, sched: Schedule, block_events):
 @_timed("gta_aggregate_f32")
 def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, rowden: torch.Tensor | None = None,
               epilogue: int = _cabi.EPI_NONE, sched: Schedule | None = None, out: torch.Tensor | None = None,
-              block_events=None):
+              block_events=None, exchange=None):
     """COMP_MUL_COMP_ADD / COMP_ADD gather: ``out[i] = epi(sum_k w[k] (x) x[src k])``;
     with ``rowden`` the weight is ``w[k,h] / rowden[i,h]`` (GAT op 9).  ``block_events[b]`` (optional)
-    is the CUDA event after which column block b of the gathered table is valid (chunked all-gather)."""
+    is the CUDA event after which column block b of the gathered table is valid.  ``exchange`` (a
+    ``dist.Gate``): ``x`` is this step's gathered table of a fused exchange and the launch pulls the peers' slots
+    itself; the work list is then cut at the slot boundaries."""
     lib = _cabi.load()
     _require_cuda(x, w, rowden)
+    if exchange is not None:
+        sched = g.schedule(col_block=exchange.slot_rows)
     sched = sched or g.schedule_for(_ld(x) * 4)
     f = int(x.shape[1])
     rows = sched.row_end - sched.row_begin
@@ -206,12 +211,41 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
         _cabi.check(lib.gta_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
                                           sched.num_slots, _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh,
                                           _cabi.ptr(rowden), _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
-                                          partials, chain, phases, _stream()), "gta_aggregate_f32")
+                                          partials, chain, exchange.byref() if exchange is not None else None,
+                                          phases, _stream()), "gta_aggregate_f32")
     _launch_blocks(launch, sched, block_events)
     return o
 
 
 _gat_ws = _Workspace()      # chain state of the single-pass GAT kernel
+
+
+def gather_peak(table_bytes: int = 40 << 20, f: int = 128, gathers_per_group: int = 4096, iters: int = 5) -> dict:
+    """Measured ceiling of the gather kernels on this device (``gta_gather_peak_probe``): random whole-row gathers
+    from an L2-resident table with the kernels' own load instruction.  Returns ``{"gbs": ..., "rows": ..., ...}``."""
+    lib = _cabi.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = max(table_bytes // (f * 4), 1)
+    table = alloc_table(rows, f, dev)
+    table.normal_()
+    sink = torch.zeros(1 << 20, dtype=torch.float32, device=dev)
+    groups = 0
+    times = []
+    for it in range(iters + 2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        groups = int(lib.gta_gather_peak_probe(_cabi.ptr(table), rows, _ld(table), f, gathers_per_group, _cabi.ptr(sink),
+                                               _stream()))
+        b.record()
+        if groups <= 0:
+            _cabi.check(-groups, "gta_gather_peak_probe")
+        b.synchronize()
+        if it >= 2:
+            times.append(a.elapsed_time(b))
+    ms = min(times)
+    byts = groups * gathers_per_group * f * 4
+    return {"gbs": byts / (ms * 1e-3) / 1e9, "ms": ms, "rows": rows, "row_bytes": f * 4, "table_mb": rows * f * 4 / 2**20,
+            "gathers": groups * gathers_per_group, "how": "gta_gather_peak_probe: best of %d launches" % iters}
 
 
 def er_stats(er: torch.Tensor, col_block: int = 0) -> torch.Tensor | None:
@@ -232,12 +266,15 @@ def er_stats(er: torch.Tensor, col_block: int = 0) -> torch.Tensor | None:
 @_timed("gta_gat_aggregate_f32")
 def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.Tensor, slope: float = LEAKY_SLOPE,
                   epilogue: int = _cabi.EPI_ELU, sched: Schedule | None = None, out: torch.Tensor | None = None,
-                  want_stats: bool = False, block_events=None, bounded: bool = True):
+                  want_stats: bool = False, block_events=None, bounded: bool = True, exchange=None):
     """GAT ops 3-13 in one pass: returns ``out`` or ``(out, rowmax, rowsum)``.  ``bounded`` shifts the softmax
     by the per-(row, column block) bound ``leaky(el + max er)`` where the block's er range allows it (see
-    ``gta_er_stats``); ``False`` or ``want_stats`` runs the online softmax with a running maximum."""
+    ``gta_er_stats``); ``False`` or ``want_stats`` runs the online softmax with a running maximum.  ``exchange``
+    (a ``dist.Gate``): ``z`` / ``er`` are views of this step's gathered table of a fused exchange, see ``aggregate``."""
     lib = _cabi.load()
     _require_cuda(el, er, z)
+    if exchange is not None:
+        sched = g.schedule(col_block=exchange.slot_rows)
     sched = sched or g.schedule_for(_ld(z) * 4)
     f = int(z.shape[1])
     heads = int(el.shape[1])
@@ -255,14 +292,16 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
     partials, chain = _chain_state(_gat_ws, sched.num_slots, stride, f, z.device)
     col_block = sched.col_block if sched.num_blocks > 1 else 0
     # with chunk events the table is still arriving: its er range is not known before the launch
-    stats = er_stats(er, col_block) if bounded and not want_stats and block_events is None else None
+    # (with an exchange the slot owners publish their er range and the kernel reads it from the signal block)
+    stats = er_stats(er, col_block) if bounded and not want_stats and block_events is None and exchange is None else None
 
     def launch(first, count, phases):
         _cabi.check(lib.gta_gat_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
                                               sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el),
                                               _cabi.ptr(er), lder, heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o),
                                               _ld(o), f, epilogue, _cabi.ptr(rowmax), _cabi.ptr(rowsum),
-                                              partials, chain, _cabi.ptr(stats), col_block, phases, _stream()),
+                                              partials, chain, _cabi.ptr(stats), col_block,
+                                              exchange.byref() if exchange is not None else None, phases, _stream()),
                     "gta_gat_aggregate_f32")
     _launch_blocks(launch, sched, block_events)
     if want_stats:

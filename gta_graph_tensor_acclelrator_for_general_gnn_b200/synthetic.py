@@ -154,14 +154,60 @@ def rmat_graph(scale: int, edge_factor: int = 16, seed: int = 0,
     return CooGraph(n, dst[order], src[order], name or f"rmat{scale}")
 
 
+#: degree skew of the ``<shape>-heavy`` variants: P(rank) ~ (rank + 600)^-0.9.  At the Reddit shape the expected
+#: degrees run 109 .. 23 400 around the mean of 492 (max 47.6x the mean, median 0.41x) -- the tail of the real Reddit
+#: graph (max 21 657 = 44x, long low-degree tail), which the default (gamma 0.5, i0 100: 251 .. 12 121, max 24.6x,
+#: median 0.72x) flatters.  A textbook alpha ~ 2.1 sequence is not realisable at this density: its head would need
+#: degrees beyond N - 1 and E/2 = 57 M DISTINCT pairs cannot be drawn from it.
+HEAVY_TAIL = {"gamma": 0.9, "i0": 600.0}
+
+
 def shape_graph(name: str, seed: int = 0, scale: float = 1.0) -> CooGraph:
-    """Graph of a named dataset shape; ``scale`` < 1 shrinks nodes and edges together
-    (used for bounded CPU samples) while keeping the mean degree."""
-    n, e, _ = SHAPES[name]
+    """Graph of a named dataset shape (``<shape>-heavy``: the heavier-tailed degree sequence, HEAVY_TAIL);
+    ``scale`` < 1 shrinks nodes and edges together (used for bounded CPU samples) while keeping the mean degree."""
+    base, heavy = (name[:-6], True) if name.endswith("-heavy") else (name, False)
+    n, e, _ = SHAPES[base]
     if scale != 1.0:
         n = max(int(n * scale), 16)
         e = max(int(e * scale) // 2 * 2, 2)
-    return powerlaw_graph(n, e, seed=seed, name=name if scale == 1.0 else f"{name}x{scale:g}")
+    kw = HEAVY_TAIL if heavy else {}
+    return powerlaw_graph(n, e, seed=seed, name=name if scale == 1.0 else f"{name}x{scale:g}", **kw)
+
+
+def degree_stats(dst: np.ndarray, num_nodes: int) -> dict:
+    """min / median / mean / max in-degree of an edge list (what the bench line states about its workload)."""
+    deg = np.bincount(dst, minlength=num_nodes)
+    return {"min": int(deg.min()), "median": float(np.median(deg)), "mean": float(deg.mean()), "max": int(deg.max()),
+            "max_over_mean": float(deg.max() / max(deg.mean(), 1e-30))}
+
+
+def rmat_graph_device(scale: int, edge_factor: int = 16, seed: int = 0, abcd=(0.57, 0.19, 0.19, 0.05), device="cuda"):
+    """RMAT edge list generated ON THE DEVICE (BASELINE config 5: scale 24 = 16.8 M nodes, 268 M edges -- the numpy
+    generator above needs minutes and tens of GB per rank for that).  Same quadrant probabilities and the same random
+    relabelling, ``torch`` CUDA generator seeded with ``seed`` so every rank of a box draws the identical list.
+    Self loops are redirected to the next node id; duplicate edges are KEPT (a multigraph, which the CSR builder and
+    the kernels handle; about 1 % of the edges at scale 24).  Returns ``(dst int32 [E], src int32 [E], N)``."""
+    import torch
+    n = 1 << scale
+    m = edge_factor * n
+    gen = torch.Generator(device=device).manual_seed(seed)
+    a, b, c, _ = abcd
+    row = torch.zeros(m, dtype=torch.int32, device=device)
+    col = torch.zeros(m, dtype=torch.int32, device=device)
+    for _bit in range(scale):
+        u = torch.rand(m, device=device, generator=gen)
+        rbit = (u >= a + b).to(torch.int32)
+        cbit = (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int32)
+        row = (row << 1) | rbit
+        col = (col << 1) | cbit
+        del u, rbit, cbit
+    col = torch.where(row == col, (col + 1) % n, col)
+    relabel = torch.randperm(n, device=device, generator=gen).to(torch.int32)
+    dst = relabel[row.long()]
+    src = relabel[col.long()]
+    del row, col
+    order = torch.randperm(m, device=device, generator=gen)
+    return dst[order].contiguous(), src[order].contiguous(), n
 
 
 def glorot(rng: np.random.Generator, fan_in: int, fan_out: int) -> np.ndarray:

@@ -94,27 +94,57 @@ int gta_tile_nnz_max(const int64_t* indptr, const int32_t* indices, int64_t num_
 int gta_partition(const int64_t* indptr, int64_t num_nodes, int32_t parts, int64_t* bounds,
                   void* stream);
 
-/* Destination-partitioned execution: the all-gathered source table is [chunks, parts, stride/chunks, F]
- * (each rank's rows padded to `stride`, cut into `chunks` equal pieces; chunk q of every rank is
- * contiguous so it can be all-gathered and aggregated while chunk q+1 is in flight).
- * out[k] = q*(parts*cs) + p*cs + (o - q*cs), p = owner of indices[k], o = indices[k] - bounds[p],
- * cs = stride/chunks, q = o/cs.  chunks = 1 gives p*stride + o, monotonic in the source id. */
+/* Destination-partitioned execution.  The gathered source table of rank r is [parts, stride, F] (each
+ * rank's rows padded to `stride`); slot k holds the rows of rank (r + k) mod parts -- `rotate` = r puts the
+ * rank's own rows first, rotate = 0 is the layout of a plain all-gather.
+ * out[k] = ((p - rotate) mod parts)*stride + (indices[k] - bounds[p]), p = owner of indices[k]. */
 int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* bounds,
-                      int32_t parts, int64_t stride, int32_t chunks, int32_t* out, void* stream);
+                      int32_t parts, int64_t stride, int32_t rotate, int32_t* out, void* stream);
 
-/* Peer-to-peer exchange without SMs (ipc.cu): each rank publishes a slot buffer through CUDA IPC at
- * setup and pulls its peers' slots with device-to-device copies on a copy stream (copy engines over
- * NVLink), so the transfer hides under the aggregation kernel.  gta_ipc_alloc'ed buffers are the only
- * memory this library owns; free them with gta_ipc_free.  handle64 is a 64-byte cudaIpcMemHandle_t. */
+/* ---------------------------------------------------------------------------------------
+ * Exchange of the source-side tables INSIDE the aggregation launch (ipc.cu, aggregate.cu); replaces the
+ * per-layer NCCL all-gather of a destination-partitioned run.
+ *
+ * Every rank owns, per step parity, one gathered table [parts, stride, ld] (gta_ipc_alloc, published to
+ * the peers through CUDA IPC) and one signal block (gta_exchange_signal_bytes()).  A step on rank r:
+ *   1. the producer (gta_gemm_f32) writes the rank's rows [Z | er] into slot 0 of its table;
+ *   2. gta_exchange_publish: er range of those rows (see gta_er_stats) and the step number go to every
+ *      peer's signal block (release, system scope);
+ *   3. gta_aggregate_f32 / gta_gat_aggregate_f32 with a gta_exchange_t: the first `copy_ctas` CTAs of the
+ *      launch pull slot 0 of peer (r + k) mod parts over NVLink into slot k of the local table, k = 1 ..
+ *      parts-1 in ring order, waiting for that peer's step number first; the other CTAs walk the work list
+ *      (column block = slot: own rows first) and wait at the first item of slot k until it has landed.
+ * No collective library call, no SMs taken by a communication kernel, no launch boundary between transfer
+ * and compute.  Tables are double-buffered by step parity: a peer is at most one step ahead.
+ * Every wait is bounded (a rank that never publishes makes the others trap, it does not hang the GPU).
+ * ------------------------------------------------------------------------------------ */
+#define GTA_MAX_RANKS 16
+typedef struct {
+  int32_t world;                        /* parts; <= GTA_MAX_RANKS */
+  int32_t rank;
+  int32_t step;                         /* >= 1, the same on every rank, +1 per layer execution */
+  int32_t copy_ctas;                    /* CTAs that pull (0: library default) */
+  int64_t slot_rows;                    /* stride: rows per slot = col_block of the work list */
+  int64_t row_bytes;                    /* bytes per table row (ld * 4), multiple of 16 */
+  void* table;                          /* this rank's table for this step */
+  void* signals;                        /* this rank's signal block */
+  const void* peer_table[GTA_MAX_RANKS];/* [k]: table (this step's parity) of rank (rank + k) mod world */
+  int64_t slot_valid_rows[GTA_MAX_RANKS];/* [k]: rows of rank (rank + k) mod world */
+} gta_exchange_t;
+size_t gta_exchange_signal_bytes(void);
+/* `er` (may be NULL with heads = 0: no range statistics, GCN) are this rank's `rows` rows; h_peer_signals[q]
+ * is the signal block of rank q as mapped in this process ([rank] = its own). */
+int gta_exchange_publish(const float* er, int64_t lder, int64_t rows, int32_t heads, int32_t rank,
+                         int32_t world, int32_t step, void* const* h_peer_signals, void* stream);
+
+/* Peer-to-peer plumbing: buffers that can be mapped by the other ranks of the box.  gta_ipc_alloc'ed
+ * buffers are the only memory this library owns; free them with gta_ipc_free.  handle64 is a 64-byte
+ * cudaIpcMemHandle_t. */
 int gta_ipc_alloc(size_t bytes, void** ptr);
 int gta_ipc_free(void* ptr);
 int gta_ipc_export(void* ptr, uint8_t* handle64);
 int gta_ipc_open(const uint8_t* handle64, void** mapped);
 int gta_ipc_close(void* mapped);
-/* dst[i] <- src[i] (bytes[i]) for i < n, asynchronously on `stream`; pointers may be peer mappings.
- * h_ arrays live on the host. */
-int gta_copy_many(void* const* h_dst, const void* const* h_src, const int64_t* h_bytes, int32_t n,
-                  void* stream);
 
 /* Degree reorder: perm[new] = old, descending in-degree, stable. */
 size_t gta_reorder_workspace(int64_t num_nodes);
@@ -172,15 +202,25 @@ int gta_gemm_get_mode(void);
  * (warps take items from a counter in work-list order).  Rows that own several items are folded in slot
  * order INSIDE the kernel (each item waits for its predecessor's state, no merge launch): `partials`
  * holds num_slots*f floats (NULL when num_slots == 0); `chain_state` holds, for W = ceil(f/128) feature
- * windows, W*num_slots int32 chain flags (cleared by GTA_PHASE_RESET) followed by W int32 item counters
- * (cleared by every MAIN launch) and is always required.
+ * windows, W*num_slots int32 chain flags (cleared by GTA_PHASE_RESET) followed by W + GTA_MAX_RANKS int32
+ * (item counters and slot-arrival counters, cleared by every MAIN launch) and is always required.
+ * `exchange` (NULL: the source table is complete) makes the launch pull the peers' slots itself, see
+ * gta_exchange_t; the work list must then have been built with col_block = exchange->slot_rows.
  * ------------------------------------------------------------------------------------ */
 int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
                       int64_t num_slots, const int32_t* indices,
                       int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
-                      int32_t epilogue, float* partials, int32_t* chain_state, int32_t phases,
-                      void* stream);
+                      int32_t epilogue, float* partials, int32_t* chain_state,
+                      const gta_exchange_t* exchange, int32_t phases, void* stream);
+
+/* Measured ceiling of the gather kernels (roofline denominator, not part of the path): every resident
+ * lane group gathers `gathers_per_group` pseudo-random rows of `table` ([rows, ld] fp32, f <= 128 features
+ * read per row) with the aggregation kernels' own load instruction and nothing else.  Returns the number of
+ * groups that ran (> 0) or a negative error code (-GTA_ERR_*); time it with events around the call.
+ * `sink` needs 16 bytes per group (never written in practice). */
+int gta_gather_peak_probe(const float* table, int64_t rows, int64_t ld, int32_t f, int64_t gathers_per_group,
+                          float* sink, void* stream);
 
 /* Range of the GAT source-side logits per column block: stats[cb][0][h] / stats[cb][1][h] = ordered-int
  * codes of max_j er[j,h] and max_j -er[j,h] over the sources j of column block cb (col_block source ids
@@ -201,8 +241,9 @@ int gta_er_stats(const float* er, int64_t lder, int64_t num_sources, int64_t col
  * per 128-feature window); chain_state as for gta_aggregate_f32.
  * er_stats (from gta_er_stats with the same col_block; NULL: online softmax with a running maximum):
  * where a block's er range is below 60 the softmax is shifted by a per-(row, block) bound -- same result
- * within rounding, no warp reductions.  Optionally emits rowmax[N,H] and rowsum[N,H] (NULL to skip;
- * asking for rowmax selects the online path, which tracks the true maximum).
+ * within rounding, no warp reductions.  With `exchange` the statistics are taken from the signal block
+ * (published by the slot owners) and er_stats / col_block are ignored.  Optionally emits rowmax[N,H] and
+ * rowsum[N,H] (NULL to skip; asking for rowmax selects the online path, which tracks the true maximum).
  * ------------------------------------------------------------------------------------ */
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads);
 int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
@@ -211,7 +252,8 @@ int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t
                           const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum,
                           float* partials, int32_t* chain_state, const uint32_t* er_stats,
-                          int64_t col_block, int32_t phases, void* stream);
+                          int64_t col_block, const gta_exchange_t* exchange, int32_t phases,
+                          void* stream);
 
 /* GAT block [4,5,6,7,8] alone (COMP_ADD 6, COMP_SF 7, STORE_E 7, COMP_ADD 8 gather):
  *   p[k,h] = exp(leaky_relu(el[i,h] + er[j,h]) - rowmax[i,h]),  rowsum[i,h] = sum_k p[k,h].

@@ -80,7 +80,7 @@ def gemm(x, w, al=None, ar=None, out=None, er_out=None):
     return z, el, er
 
 
-def aggregate(g, x, w=None, rowden=None, epilogue=_cabi.EPI_NONE, sched=None, out=None, block_events=None):
+def aggregate(g, x, w=None, rowden=None, epilogue=_cabi.EPI_NONE, sched=None, out=None, block_events=None, exchange=None):
     src = g.indices.long()
     e = x[src]
     if w is not None:
@@ -106,7 +106,7 @@ def gat_logits(g, el, er, slope=LEAKY_SLOPE, stabilize=True):
 
 
 def gat_aggregate(g, el, er, z, slope=LEAKY_SLOPE, epilogue=_cabi.EPI_ELU, sched=None, out=None,
-                  want_stats=False, block_events=None, bounded=True):
+                  want_stats=False, block_events=None, bounded=True, exchange=None):
     p, rowmax, rowsum = gat_logits(g, el, er, slope, True)
     alpha = p / rowsum[_rows(g)]
     res = _epilogue(_segment_sum(z[g.indices.long()] * _spread(alpha, z.shape[1]), g), epilogue)
