@@ -55,7 +55,7 @@ SIGNATURES = {
     "gta_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_p)]),
     "gta_ipc_close": (C.c_int, [_p]),
     "gta_exchange_signal_bytes": (_sz, []),
-    "gta_exchange_publish": (C.c_int, [_p, _i64, _i64, _i32, _i32, _i32, _i32, C.POINTER(_p), _p]),
+    "gta_exchange_publish": (C.c_int, [_p, _i32, _i32, _i32, _i32, C.POINTER(_p), _p]),
     "gta_reorder_workspace": (_sz, [_i64]),
     "gta_reorder": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "gta_schedule_workspace": (_sz, [_i64, _i64, _i64]),

@@ -130,7 +130,7 @@ __device__ __forceinline__ int warp_max_i32(int v) {
 // see DESIGN.md): 0 = L1 no-allocate, 1 = default, 2 = L1 no-allocate + L2 evict_last, 3 = L2 evict_last,
 // 4 = as 2 without .nc (coherent path)
 #ifndef GTA_AGG_GATHER
-#define GTA_AGG_GATHER 2
+#define GTA_AGG_GATHER 4
 #endif
 __device__ __forceinline__ float4 ld_row_f32x4(const float* p, uint64_t pol_keep) {
   float4 v;
@@ -193,6 +193,7 @@ struct WorkList {
   float* partials;
   int32_t* chain_flags;      // [windows][num_slots]
   int32_t* work_counter;     // [windows], zeroed before every launch
+  int32_t take;              // items a warp takes per grab (a multiple of its 32/LANES groups)
   uint64_t pol_stream;
   uint64_t pol_keep;
 };
@@ -204,10 +205,13 @@ struct WorkList {
 // trip hides under the gathers.  Items are still started in work-list order, which keeps the CTAs on one
 // column block at a time and keeps the chain invariant: whoever holds a predecessor slot started earlier
 // and is running, so a wait can never deadlock, whatever the grid size.
-template <int LANES>
-__device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane) {
+// Long lists of tiny items (RMAT: 16.8 M items of 2 edges per rank) would hammer the counter: a grab then
+// takes several consecutive group-steps at once (wl.take, chosen by the host so that every warp still makes
+// a few dozen grabs).  A warp works through its batch in ascending order, so the smallest unfinished item of
+// the whole list is always somebody's CURRENT item and the chain argument above still holds.
+__device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane, int32_t take) {
   int32_t v = 0;
-  if (lane == 0) v = atomicAdd(counter, 32 / LANES);
+  if (lane == 0) v = atomicAdd(counter, take);
   return v;
 }
 
@@ -240,9 +244,10 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
   int32_t* flags = wl.chain_flags + int64_t(blockIdx.y) * wl.num_slots;
   const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
 
-  int32_t first = __shfl_sync(0xffffffffu, grab_items<LANES>(counter, lane), 0);
+  int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
+  int32_t batch_end = first + wl.take;
+  int32_t pending = grab_items(counter, lane, wl.take);      // the next batch, in flight under this one
   while (first < wl.num_items) {
-    const int32_t pending = grab_items<LANES>(counter, lane);
     const int64_t group = int64_t(first) + lane / LANES;
     const bool have = group < wl.num_items;
     const bool active = have && fo < f;
@@ -368,7 +373,12 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
       }
       if (last && active) st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
     });
-    first = __shfl_sync(0xffffffffu, pending, 0);
+    first += 32 / LANES;
+    if (first >= batch_end) {
+      first = __shfl_sync(0xffffffffu, pending, 0);
+      batch_end = first + wl.take;
+      if (first < wl.num_items) pending = grab_items(counter, lane, wl.take);
+    }
   }
 }
 
@@ -456,9 +466,10 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   const int pstride = gat_partial_stride(f, H);
   const int stats = f + int(blockIdx.y) * gat_stats_stride(H);
 
-  int32_t first = __shfl_sync(0xffffffffu, grab_items<LANES>(counter, lane), 0);
+  int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
+  int32_t batch_end = first + wl.take;
+  int32_t pending = grab_items(counter, lane, wl.take);      // the next batch, in flight under this one
   while (first < wl.num_items) {
-    const int32_t pending = grab_items<LANES>(counter, lane);
     const int64_t group = int64_t(first) + lane / LANES;
     const bool have = group < wl.num_items;
     const bool active = have && fo < f;
@@ -645,7 +656,12 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
         }
       }
     });
-    first = __shfl_sync(0xffffffffu, pending, 0);
+    first += 32 / LANES;
+    if (first >= batch_end) {
+      first = __shfl_sync(0xffffffffu, pending, 0);
+      batch_end = first + wl.take;
+      if (first < wl.num_items) pending = grab_items(counter, lane, wl.take);
+    }
   }
 }
 
@@ -686,9 +702,10 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
   const int pstride = gat_partial_stride(f, heads);
   const int stats = f + int(blockIdx.y) * gat_stats_stride(heads);
 
-  int32_t first = __shfl_sync(0xffffffffu, grab_items<LANES>(counter, lane), 0);
+  int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
+  int32_t batch_end = first + wl.take;
+  int32_t pending = grab_items(counter, lane, wl.take);      // the next batch, in flight under this one
   while (first < wl.num_items) {
-    const int32_t pending = grab_items<LANES>(counter, lane);
     const int64_t group = int64_t(first) + lane / LANES;
     const bool have = group < wl.num_items;
     const bool active = have && fo < f;
@@ -820,7 +837,12 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
         }
       }
     });
-    first = __shfl_sync(0xffffffffu, pending, 0);
+    first += 32 / LANES;
+    if (first >= batch_end) {
+      first = __shfl_sync(0xffffffffu, pending, 0);
+      batch_end = first + wl.take;
+      if (first < wl.num_items) pending = grab_items(counter, lane, wl.take);
+    }
   }
 }
 
@@ -945,6 +967,17 @@ static int resident_ctas(K kernel) {
   return cached;
 }
 
+// items per grab: a multiple of the warp's 32/lanes groups, at most 8 group-steps, and small enough that every
+// resident warp still makes about 32 grabs (load balance at the end of the list)
+template <typename K>
+static int32_t take_for(K kernel, int64_t num_items, int lanes) {
+  const int groups = 32 / lanes;
+  const int64_t warps = int64_t(resident_ctas(kernel)) * (kAggThreads / 32);
+  int64_t steps = num_items / (warps * groups * 32);
+  steps = steps < 1 ? 1 : (steps > 8 ? 8 : steps);
+  return int32_t(steps * groups);
+}
+
 template <typename K>
 static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f, const Exchange& ex) {
   const int64_t need = (num_items * lanes + kAggThreads - 1) / kAggThreads;
@@ -952,6 +985,11 @@ static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f, const
   // the copy CTAs of an exchange come first in the grid, so they are resident before any CTA can wait on them
   const int64_t copy = ex.world > 1 ? ex.copy_ctas : 0;
   return dim3((unsigned)((need < cap ? need : cap) + copy), (unsigned)((f + 127) / 128));
+}
+
+static WorkList with_take(WorkList wl, int32_t take) {
+  wl.take = take;
+  return wl;
 }
 
 // gta_exchange_t (host) -> Exchange (kernel parameter); arrived[] lives behind the item counters
@@ -991,7 +1029,9 @@ static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkL
                                int64_t ldo, int f, int epi) {
 #define GTA_AGG(K, D)                                                                                          \
   aggregate_kernel<LANES, K, D><<<persistent_grid(aggregate_kernel<LANES, K, D>, wl.num_items, LANES, f, ex),   \
-                                  kAggThreads, 0, st>>>(wl, ex, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi)
+                                  kAggThreads, 0, st>>>(with_take(wl, take_for(aggregate_kernel<LANES, K, D>,    \
+                                                                               wl.num_items, LANES)),           \
+                                                        ex, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi)
   if (wkind == 0) GTA_AGG(0, false);
   else if (wkind == 1 && !div) GTA_AGG(1, false);
   else if (wkind == 1 && div) GTA_AGG(1, true);
@@ -1007,7 +1047,8 @@ static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const Ex
                         int64_t col_block) {
 #define GTA_GAT(L)                                                                                              \
   gat_aggregate_kernel<L, H><<<persistent_grid(gat_aggregate_kernel<L, H>, wl.num_items, L, f, ex), kAggThreads, \
-                               0, st>>>(wl, ex, el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi,     \
+                               0, st>>>(with_take(wl, take_for(gat_aggregate_kernel<L, H>, wl.num_items, L)), ex, \
+                                        el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi,           \
                                         rowmax, rowsum, er_stats, stats_pitch, col_block)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
@@ -1062,7 +1103,7 @@ int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* r
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
   GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_aggregate_f32: bad item count");
-  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 0, 0};
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
   int rc = prepare_worklist("gta_aggregate_f32", wl, chain_state, f, phases, st);
   if (rc != GTA_OK) return rc;
   if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
@@ -1146,7 +1187,7 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
   GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_gat_aggregate_f32: bad item count");
-  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 0, 0};
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
   int rc = prepare_worklist("gta_gat_aggregate_f32", wl, chain_state, f, phases, st);
   if (rc != GTA_OK) return rc;
   if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
@@ -1196,7 +1237,8 @@ int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_
   } else {
 #define GTA_LLH(L)                                                                                                  \
   gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f, ex), kAggThreads, 0, \
-                                st>>>(wl, ex, el, er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,         \
+                                st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl.num_items, L)), ex, el,   \
+                                      er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,                     \
                                       epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
     switch (lanes) {
       case 4: GTA_LLH(4); break;

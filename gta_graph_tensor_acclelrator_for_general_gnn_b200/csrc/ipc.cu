@@ -10,7 +10,8 @@
 //
 //   gta_ipc_alloc / gta_ipc_free     tables and signal blocks (cudaMalloc'ed so the IPC handle names a base pointer)
 //   gta_ipc_export / gta_ipc_open    64-byte handle out / peer mapping in (lazy peer access)
-//   gta_exchange_publish             "my slot is written": er range + step number into every peer's signal block
+//   gta_exchange_publish             "my slot is written": er range (from gta_er_stats) + step number into every
+//                                    peer's signal block
 #include <string.h>
 
 #include "common.cuh"
@@ -18,36 +19,18 @@
 
 namespace gta {
 
-// One CTA.  Range of this rank's er rows per head (ordered-int codes, as gta_er_stats), written with the
-// step number to the signal block of every rank q at the slot index q uses for this rank.
-__global__ void __launch_bounds__(1024)
-exchange_publish_kernel(const float* __restrict__ er, int64_t lder, int64_t rows, int heads, int rank, int world,
-                        int step, SignalPointers peers) {
-  __shared__ uint32_t s_code[2 * 32];
+// One small CTA.  `stats` = this rank's er range per head as gta_er_stats writes it for one column block
+// ([max codes (heads) | max -er codes (heads)], NULL: none); it goes, with the step number, to the signal
+// block of every rank q at the slot index q uses for this rank.
+__global__ void __launch_bounds__(128)
+exchange_publish_kernel(const uint32_t* __restrict__ stats, int heads, int rank, int world, int step,
+                        SignalPointers peers) {
   const int t = threadIdx.x;
-  if (t < 64) s_code[t] = 0u;
-  __syncthreads();
-  if (heads > 0) {
-    const int h = t & (heads - 1);
-    float mx = -INFINITY, mn = INFINITY;
-    bool seen = false;
-    for (int64_t r = t / heads; r < rows; r += blockDim.x / heads) {
-      const float v = er[r * lder + h];
-      mx = fmaxf(mx, v);
-      mn = fminf(mn, v);
-      seen = true;
-    }
-    if (seen) {
-      atomicMax(&s_code[h], ordered_code(mx));
-      atomicMax(&s_code[32 + h], ordered_code(-mn));
-    }
-  }
-  __syncthreads();
   const int parity = step & 1;
   for (int i = t; i < world * 2 * heads; i += blockDim.x) {
-    const int q = i / (2 * heads), j = i % (2 * heads);          // peer q, word j of [max codes | -min codes]
+    const int q = i / (2 * heads), j = i % (2 * heads);
     const int slot = rank >= q ? rank - q : rank - q + world;    // where q keeps this rank
-    peers.sig[q]->stats[parity][slot][j] = s_code[(j / heads) * 32 + (j % heads)];
+    peers.sig[q]->stats[parity][slot][j] = stats[j];
   }
   __threadfence_system();
   __syncthreads();
@@ -99,19 +82,18 @@ int gta_ipc_close(void* mapped) {
 
 size_t gta_exchange_signal_bytes(void) { return sizeof(ExchangeSignals); }
 
-int gta_exchange_publish(const float* er, int64_t lder, int64_t rows, int32_t heads, int32_t rank, int32_t world,
-                         int32_t step, void* const* h_peer_signals, void* stream_) {
+int gta_exchange_publish(const uint32_t* stats, int32_t heads, int32_t rank, int32_t world, int32_t step,
+                         void* const* h_peer_signals, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(h_peer_signals && world >= 1 && world <= GTA_MAX_RANKS && rank >= 0 && rank < world && step >= 1 && rows >= 0,
+  GTA_REQUIRE(h_peer_signals && world >= 1 && world <= GTA_MAX_RANKS && rank >= 0 && rank < world && step >= 1,
               "gta_exchange_publish: bad arguments (world %d, rank %d, step %d)", world, rank, step);
-  GTA_REQUIRE(heads == 0 || (er && lder >= heads), "gta_exchange_publish: er is required for %d heads", heads);
-  if (heads < 0 || heads > 32 || (heads & (heads - 1)) != 0) heads = 0;      // no statistics: the consumers run the online softmax
+  GTA_REQUIRE(heads >= 0 && heads <= 32 && (heads == 0 || stats), "gta_exchange_publish: %d heads without statistics", heads);
   SignalPointers peers{};
   for (int q = 0; q < world; ++q) {
     GTA_REQUIRE(h_peer_signals[q], "gta_exchange_publish: signal block of rank %d is not mapped", q);
     peers.sig[q] = static_cast<ExchangeSignals*>(h_peer_signals[q]);
   }
-  exchange_publish_kernel<<<1, 1024, 0, st>>>(er, lder, rows, heads, rank, world, step, peers);
+  exchange_publish_kernel<<<1, 128, 0, st>>>(stats, heads, rank, world, step, peers);
   GTA_CHECK_LAUNCH("exchange_publish_kernel");
   return GTA_OK;
 }

@@ -335,10 +335,10 @@ class FusedExchange:
         parity = self.step & 1
         tables, signals = self._peer_ptrs(width, device, parity)
         sig_arr = (C.c_void_p * p.world)(*signals)
-        heads = int(er.shape[1]) if er is not None else 0
-        lder = (int(er.stride(0)) if er.shape[0] > 1 else max(int(er.stride(0)), heads)) if er is not None else 0
-        _cabi.check(lib.gta_exchange_publish(_cabi.ptr(er), lder, p.rows, heads, p.rank, p.world, self.step, sig_arr,
-                                             _stream()), "gta_exchange_publish")
+        stats = kernels.er_stats(er, 0) if er is not None and p.rows > 0 else None      # None: no power-of-two head count
+        heads = int(er.shape[1]) if stats is not None else 0
+        _cabi.check(lib.gta_exchange_publish(_cabi.ptr(stats), heads, p.rank, p.world, self.step, sig_arr, _stream()),
+                    "gta_exchange_publish")
         ex = _cabi.Exchange()
         ex.world, ex.rank, ex.step, ex.copy_ctas = p.world, p.rank, self.step, self.copy_ctas
         ex.slot_rows, ex.row_bytes = p.stride, st["ld"] * 4

@@ -108,8 +108,8 @@ int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* 
  * Every rank owns, per step parity, one gathered table [parts, stride, ld] (gta_ipc_alloc, published to
  * the peers through CUDA IPC) and one signal block (gta_exchange_signal_bytes()).  A step on rank r:
  *   1. the producer (gta_gemm_f32) writes the rank's rows [Z | er] into slot 0 of its table;
- *   2. gta_exchange_publish: er range of those rows (see gta_er_stats) and the step number go to every
- *      peer's signal block (release, system scope);
+ *   2. gta_er_stats over those rows, then gta_exchange_publish: the er range and the step number go to
+ *      every peer's signal block (release, system scope);
  *   3. gta_aggregate_f32 / gta_gat_aggregate_f32 with a gta_exchange_t: the first `copy_ctas` CTAs of the
  *      launch pull slot 0 of peer (r + k) mod parts over NVLink into slot k of the local table, k = 1 ..
  *      parts-1 in ring order, waiting for that peer's step number first; the other CTAs walk the work list
@@ -132,10 +132,11 @@ typedef struct {
   int64_t slot_valid_rows[GTA_MAX_RANKS];/* [k]: rows of rank (rank + k) mod world */
 } gta_exchange_t;
 size_t gta_exchange_signal_bytes(void);
-/* `er` (may be NULL with heads = 0: no range statistics, GCN) are this rank's `rows` rows; h_peer_signals[q]
- * is the signal block of rank q as mapped in this process ([rank] = its own). */
-int gta_exchange_publish(const float* er, int64_t lder, int64_t rows, int32_t heads, int32_t rank,
-                         int32_t world, int32_t step, void* const* h_peer_signals, void* stream);
+/* `stats` = this rank's er range as gta_er_stats(er, lder, rows, 0, heads, stats) wrote it (2*heads uint32;
+ * NULL with heads = 0: none, the consumers run the online softmax -- GCN, or a head count gta_er_stats
+ * refuses).  h_peer_signals[q] is the signal block of rank q as mapped in this process ([rank] = its own). */
+int gta_exchange_publish(const uint32_t* stats, int32_t heads, int32_t rank, int32_t world, int32_t step,
+                         void* const* h_peer_signals, void* stream);
 
 /* Peer-to-peer plumbing: buffers that can be mapped by the other ranks of the box.  gta_ipc_alloc'ed
  * buffers are the only memory this library owns; free them with gta_ipc_free.  handle64 is a 64-byte

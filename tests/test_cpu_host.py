@@ -206,7 +206,7 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     refused("gta_edge_binary_f32", lib.gta_edge_binary_f32(n, n, 0, 1, 0, n, 0, 3, 3, n, 0, 4, 4, n, 4, 4, n))
     refused("gta_node_unary_f32", lib.gta_node_unary_f32(9, 0.2, n, 4, n, 4, 4, 1, n))
     refused("gta_schedule_build", lib.gta_schedule_build(n, n, 0, 1, 1, 0, 0, n, 0, n, n, n, n, 0, n))
-    refused("gta_exchange_publish", lib.gta_exchange_publish(n, 0, 0, 0, 0, 99, 1, n, n))
+    refused("gta_exchange_publish", lib.gta_exchange_publish(n, 0, 0, 99, 1, n, n))
     assert lib.gta_exchange_signal_bytes() >= 64 + 2 * 16 * 64 * 4
     refused("gta_gemm_set_mode", lib.gta_gemm_set_mode(7))
     assert lib.gta_gemm_get_mode() in (0, 1, 2)
