@@ -105,14 +105,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(network, n, e, fin, f, h, s=4):
-    """SURVEY.md section 8d, no-reuse gather model.  Returns (layer bytes, dominant-kernel bytes)."""
-    gemm = n * fin * s + fin * f * s + n * f * s
+def algorithmic_bytes(network, n, e, fin, f, h, s=4, sz=None):
+    """SURVEY.md section 8d, no-reuse gather model.  Returns (layer bytes, dominant-kernel bytes).  ``sz`` = bytes per
+    element of the gathered table Z (2 in the bf16 storage mode; X, el, er, edge weights and the output stay fp32)."""
+    sz = s if sz is None else sz
+    gemm = n * fin * s + fin * f * s + n * f * sz
     if network == "GAT":
         gemm += 2 * f * h * s + 2 * n * h * s
-        edge = (n + 1) * 4 + e * 4 + e * h * s + n * h * s + e * f * s + n * f * s
+        edge = (n + 1) * 4 + e * 4 + e * h * s + n * h * s + e * f * sz + n * f * s
     else:
-        edge = (n + 1) * 4 + e * (4 + s) + e * f * s + n * f * s
+        edge = (n + 1) * 4 + e * (4 + s) + e * f * sz + n * f * s
     return gemm + edge, edge
 
 
@@ -346,6 +348,9 @@ def main():
                          "NCCL all-gather per layer (the round-1 path, kept as the baseline)")
     ap.add_argument("--copy-ctas", type=int, default=0, help="fused exchange: CTAs that pull (0 = library default)")
     ap.add_argument("--no-graph", action="store_true", help="issue kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="bf16 = bf16 STORAGE MODE: the gathered table Z in bf16, fp32 accumulation (its own tolerance: "
+                         "rtol 2e-2, atol 1e-2 rowscale); never the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = resolve_workload(args.workload)
@@ -451,10 +456,14 @@ def main():
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
+    feature_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    sz = 2 if args.dtype == "bf16" else 4
+
     def step(x_dev):
         return executor.execute(program, op_info, g, {0: x_dev}, weights, edge_inputs, network=network,
                                 is_reorder=reorder, fuse_across_blocks=not args.no_fuse, source_table=exchange,
-                                check_shapes=(world == 1 and not shape.startswith("rmat")))[final_op]
+                                check_shapes=(world == 1 and not shape.startswith("rmat")),
+                                feature_dtype=feature_dtype)[final_op]
 
     def barrier():
         if world > 1:
@@ -613,6 +622,7 @@ def main():
         rows_sel = P.select_rows(indptr_l, budget)
         ip_s, ix_s = P.sub_csr(indptr_l, indices_l, rows_sel)
         y_h = y_first.cpu().numpy()[rows_sel]
+        tol = P.BF16 if args.dtype == "bf16" else P.RTOL
         if big:
             deg_l = np.diff(indptr_l)
             pos = np.repeat(indptr_l[rows_sel] - ip_s[:-1], deg_l[rows_sel]) + np.arange(int(ip_s[-1]), dtype=np.int64)
@@ -620,12 +630,12 @@ def main():
             parity = parity_big(P, torch, y_h, ip_s, ix_s, rows_sel, ew_rows, x_d, w_d, z_dev[0], big_table, part)
         elif network == "GAT":
             z64, zabs, el64, er64 = P.host_tables(x_h, w_h, al_h, ar_h)
-            parity = P.check_gat(y_h, ip_s, ix_s, el64[r0 + rows_sel], er64, z64, zabs)
+            parity = P.check_gat(y_h, ip_s, ix_s, el64[r0 + rows_sel], er64, z64, zabs, rtol=tol)
         else:
             z64, zabs, _, _ = P.host_tables(x_h, w_h)
             deg_l = np.diff(indptr_l)
             pos = np.repeat(indptr_l[rows_sel] - ip_s[:-1], deg_l[rows_sel]) + np.arange(int(ip_s[-1]), dtype=np.int64)
-            parity = P.check_gcn(y_h, ip_s, ix_s, edge_w.cpu().numpy().reshape(-1)[pos], z64, zabs)
+            parity = P.check_gcn(y_h, ip_s, ix_s, edge_w.cpu().numpy().reshape(-1)[pos], z64, zabs, rtol=tol)
         parity.update(bitwise_rerun=bitwise, rows_of=int(r1 - r0), edges_of=int(indptr_l[-1]),
                       checked="rank 0's destination rows [%d,%d)%s" % (r0, r1, "" if rows_sel.shape[0] == r1 - r0 else
                                                                       " (512 highest-degree rows + every k-th row)"),
@@ -634,8 +644,8 @@ def main():
     # ---- roofline of the dominant kernel ------------------------------------------------------
     dom = "gta_gat_aggregate_f32" if network == "GAT" else "gta_aggregate_f32"
     dom_ms = float(np.mean(per_kernel[dom])) if dom in per_kernel else None
-    _, dom_bytes = algorithmic_bytes(network, r1 - r0, e_local, fin, f_out, max(heads, 1))
-    layer_bytes, _ = algorithmic_bytes(network, n, e, fin, f_out, max(heads, 1))
+    _, dom_bytes = algorithmic_bytes(network, r1 - r0, e_local, fin, f_out, max(heads, 1), sz=sz)
+    layer_bytes, _ = algorithmic_bytes(network, n, e, fin, f_out, max(heads, 1), sz=sz)
     peak, peak_src = measured_peak()
     traffic, traffic_src = measured_traffic(args.workload, dom, world)
     roofline = None
@@ -644,8 +654,8 @@ def main():
         # the gather term alone against the MEASURED gather ceiling of this device (L2-resident random rows, the
         # kernel's own load instruction): what the kernel is actually bound by when the table (or its column block)
         # fits L2.  Not meaningful when the table is far larger than L2 (RMAT-24: HBM-bound, use frac).
-        gp = kernels.gather_peak(f=min(f_out, 128))
-        gather_bytes = e_local * f_out * 4
+        gp = kernels.gather_peak(f=min(f_out * sz // 4, 128))      # same row BYTES as the kernel gathers
+        gather_bytes = e_local * f_out * sz
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
@@ -694,8 +704,9 @@ def main():
         par = "single GPU"
     line = {"metric": METRIC, "value": value, "unit": "GTEPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args, wl), "baseline_metric": baseline_metric(), "parallelism": par,
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args, wl) + (" [bf16 storage of Z, fp32 accumulate]" if args.dtype == "bf16" else ""),
+                       "baseline_metric": baseline_metric(), "parallelism": par,
                        "degrees": degree_stats,
                        "l2": "inputs larger than L2: CSR indices %.0f MB + X %.0f MB + Z %.0f MB re-read every step" % (
                            e * 4 / 1e6, n * fin * 4 / 1e6, n * f_out * 4 / 1e6),

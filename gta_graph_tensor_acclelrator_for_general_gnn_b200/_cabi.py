@@ -63,9 +63,17 @@ SIGNATURES = {
     "gta_schedule_col_blocks": (_i32, [_i64, _i64]),
     "gta_schedule_build": (C.c_int, [_p, _p, _i64, _i64, _i64, _i32, _i64, _p, _i64, _p, C.POINTER(_i64),
                                      C.POINTER(_i64), _p, _sz, _p]),
+    "gta_schedule_build_cuts": (C.c_int, [_p, _p, _i64, _i64, _i32, C.POINTER(_i64), _i32, _p, _i64, _p, C.POINTER(_i64),
+                                          C.POINTER(_i64), _p, _sz, _p]),
     "gta_gemm_workspace": (_sz, [_i32, _i32]),
     "gta_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _i64, _p, _sz,
                                _p]),
+    "gta_gemm_f32_zbf16": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _p, _i32, _p, _p, _i64, _p, _sz,
+                                     _p]),
+    "gta_aggregate_bf16": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
+                                     _p, _p, _p, _i32, _p]),
+    "gta_gat_aggregate_bf16": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _f32, _p, _i64, _p, _i64,
+                                         _i32, _i32, _p, _p, _p, _p, _p, _i64, _p, _i32, _p]),
     "gta_gemm_set_mode": (C.c_int, [C.c_int]),
     "gta_gemm_get_mode": (C.c_int, []),
     "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,

@@ -24,6 +24,7 @@
 //
 // Determinism.  Every item is reduced by exactly one group in ascending source order and the chain
 // is a left fold in slot order: a fixed-shape reduction, bitwise reproducible run to run, no atomics.
+#include <cuda_bf16.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -82,7 +83,12 @@ __device__ __forceinline__ void chain_wait(const int32_t* flag) {
   }
   __trap();      // the predecessor never published: a protocol bug must not hang the GPU
 }
+// Called by ONE lane after a __syncwarp of its group: the barrier orders the other lanes' state stores before
+// this lane, and its fence + release store make them visible, cumulatively, to whoever acquires the flag -- the
+// idiom of a cooperative grid barrier (block barrier, then one thread fences and signals).  One fence per
+// item instead of one per lane: a membar.gl is the most expensive instruction of a short item.
 __device__ __forceinline__ void chain_publish(int32_t* flag) {
+  __threadfence();
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
 }
 // predecessor state was written by another SM during this launch: read it at L2, never from L1
@@ -216,19 +222,87 @@ __device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane, int32_
 }
 
 // ----------------------------------------------------------------------------------------
+// storage type of the gathered table: fp32, or bf16 with fp32 accumulation (SURVEY.md section 8d "bf16 mode";
+// the reference's IR declares data_format FP16, template/IR_defination.yaml:10-27).  A lane always moves
+// 16-byte pieces of a row: 4 fp32 or 8 bf16 features.
+// ----------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int kPer = 4;
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kPer = 8;
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {      // bf16 -> fp32 is a shift
+    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+    f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+    f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+  }
+};
+// 16 bytes of a gathered row (cache policy: see ld_row_f32x4)
+__device__ __forceinline__ uint4 ld_row_raw(const char* p, uint64_t pol_keep) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_keep));
+  return v;
+}
+__device__ __forceinline__ const char* row_addr(const char* base, uint32_t id, uint32_t row_bytes) {
+  return base + uint64_t(id) * row_bytes;
+}
+template <typename T>
+__device__ __forceinline__ void fma_row(float (&acc)[Elem<T>::kPer], float w, const uint4& raw) {
+  float f[Elem<T>::kPer];
+  Elem<T>::unpack(raw, f);
+#pragma unroll
+  for (int c = 0; c < Elem<T>::kPer; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+}
+// kPer consecutive fp32 of an output / partial row
+template <int KP>
+__device__ __forceinline__ void st_out(float* p, const float (&a)[KP], float scale, int epi) {
+#pragma unroll
+  for (int q = 0; q < KP / 4; ++q)
+    st_stream_f32x4(p + 4 * q, make_float4(apply_epilogue(a[4 * q] * scale, epi), apply_epilogue(a[4 * q + 1] * scale, epi),
+                                           apply_epilogue(a[4 * q + 2] * scale, epi), apply_epilogue(a[4 * q + 3] * scale, epi)));
+}
+template <int KP>
+__device__ __forceinline__ void st_state(float* p, const float (&a)[KP]) {
+#pragma unroll
+  for (int q = 0; q < KP / 4; ++q)
+    *reinterpret_cast<float4*>(p + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+}
+template <int KP>
+__device__ __forceinline__ void ld_state(const float* p, float (&a)[KP]) {
+#pragma unroll
+  for (int q = 0; q < KP / 4; ++q) {
+    const float4 t = ld_state_f32x4(p + 4 * q);
+    a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // weighted aggregate
 //   WKIND 0: no weight, 1: scalar weight per edge (wh == 1), 2: per-head weight (wh > 1,
-//   (f / wh) % 4 == 0 so a lane's 4 features share a head)
+//   (f / wh) % kPer == 0 so a lane's features share a head; V == 1 only)
+//   V: 16-byte pieces per lane and gathered row.  V = 2 lets one warp take a whole 1 KB row (256 fp32
+//   features, the RMAT config) in one pass instead of walking the work list once per 128-feature window:
+//   the indices, the item records and the page-table entries of a row are then touched once, not twice.
 // ----------------------------------------------------------------------------------------
 constexpr int kAggUnroll = GTA_AGG_UNROLL;
 constexpr int kGatUnroll = GTA_GAT_UNROLL;
 constexpr int kLlhUnroll = GTA_LLH_UNROLL;
 
-template <int LANES, int WKIND, bool DIV>
-__global__ void __launch_bounds__(kAggThreads, GTA_AGG_MINBLOCKS)
+template <typename T, int V, int LANES, int WKIND, bool DIV>
+__global__ void __launch_bounds__(kAggThreads, (V == 1 && sizeof(T) == 4) ? GTA_AGG_MINBLOCKS : 8)
 aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ w, int wh,
-                 const float* __restrict__ rowden, const float* __restrict__ x, const uint32_t row_bytes,
+                 const float* __restrict__ rowden, const T* __restrict__ x, const uint32_t row_bytes,
                  float* __restrict__ out, int64_t ldo, int f, int epilogue) {
+  static_assert(V == 1 || (LANES == 32 && WKIND != 2), "two pieces per lane: full warps, no per-head weights");
+  constexpr int KP = Elem<T>::kPer;
+  constexpr int kWindow = LANES * KP * V;          // features one pass of a group covers
+  constexpr int kEdges = kAggUnroll;      // edges whose loads (V each) are in flight together
   __shared__ __align__(16) uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
     exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
@@ -236,13 +310,17 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
   }
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
-  const int fo = blockIdx.y * 128 + 4 * l;
+  const int fo = blockIdx.y * kWindow + KP * l;          // piece v sits at fo + v * LANES * KP
   uint2* se = s_a[threadIdx.x >> 5];
   const uint2* mine = se + (lane & ~(LANES - 1));
   const uint4* mine2 = reinterpret_cast<const uint4*>(mine);      // two staged edges per LDS.128
   int32_t* counter = wl.work_counter + blockIdx.y;
   int32_t* flags = wl.chain_flags + int64_t(blockIdx.y) * wl.num_slots;
   const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
+  bool on[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) on[v] = fo + v * LANES * KP < f;
+  const char* xf = reinterpret_cast<const char*>(x + (on[0] ? fo : 0));
 
   int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
   int32_t batch_end = first + wl.take;
@@ -250,19 +328,22 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
   while (first < wl.num_items) {
     const int64_t group = int64_t(first) + lane / LANES;
     const bool have = group < wl.num_items;
-    const bool active = have && fo < f;
+    const bool active = have && on[0];
     const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
     const int count = have ? it.z : 0;
     const int max_count = (LANES == 32) ? count : warp_max_i32(count);
     const int32_t* idx_base = wl.indices + it.y;
     const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
-    const float* xf = x + (active ? fo : 0);
     int head = 0;
     float den = 1.f;
     if (WKIND == 2) head = active ? fo / (f / wh) : 0;
     if (DIV && have) den = rowden[int64_t(it.x) * wh + head];
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[V][KP];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int c = 0; c < KP; ++c) acc[v][c] = 0.f;
     // software pipeline: ids (and scalar weights) of batch b+1 are in flight under the gathers of batch b
     int idx_nxt = 0;
     float w_nxt = 0.f;
@@ -270,8 +351,8 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
       idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
       if (WKIND == 1) w_nxt = ld_stream_f32(w_base + l, pol_stream);
     }
-    if (ex.world > 1) {          // the item's slot may still be on its way from a peer
-      if (l == 0 && count > 0) exchange_gate(ex, idx_nxt);
+    if (ex.world > 1) {          // the item's slots may still be on their way from the peers
+      if (l == 0 && count > 0) exchange_gate(ex, __ldg(idx_base + count - 1));
       __syncwarp();
     }
     for (int base = 0; base < max_count; base += LANES) {
@@ -289,53 +370,59 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
       se[lane] = make_uint2(uint32_t(my_idx), __float_as_uint(WKIND == 1 ? my_w : 1.f));
       __syncwarp();
       const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
-      if (full) {
-        // whole batch, no predicates: kAggUnroll loads in flight, then their FMAs (the outer loop stays
+      if (full && (V == 1 || on[V - 1])) {
+        // whole batch, no predicates: kEdges * V loads in flight, then their FMAs (the outer loop stays
         // rolled: unrolled, ptxas hoists every load of the batch and spills)
         if (LANES < 32 || active) {
 #pragma unroll 1
-          for (int j = 0; j < LANES; j += kAggUnroll) {
-            uint4 ed[kAggUnroll / 2];
-            float4 v[kAggUnroll];
+          for (int j = 0; j < LANES; j += kEdges) {
+            uint4 ed[kEdges / 2];
+            uint4 raw[kEdges][V];
 #pragma unroll
-            for (int u = 0; u < kAggUnroll / 2; ++u)
+            for (int u = 0; u < kEdges / 2; ++u)
               if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
-            for (int u = 0; u < kAggUnroll / 2; ++u) {
-              if (j + 2 * u < LANES) {
-                v[2 * u] = ld_row_f32x4(row_ptr(xf, ed[u].x, row_bytes), pol_keep);
-                v[2 * u + 1] = ld_row_f32x4(row_ptr(xf, ed[u].z, row_bytes), pol_keep);
+            for (int u = 0; u < kEdges; ++u) {
+              if (j + u < LANES) {
+                const char* rp = row_addr(xf, (u & 1) ? ed[u / 2].z : ed[u / 2].x, row_bytes);
+#pragma unroll
+                for (int v = 0; v < V; ++v) raw[u][v] = ld_row_raw(rp + v * LANES * 16, pol_keep);
               }
             }
 #pragma unroll
-            for (int u = 0; u < kAggUnroll; ++u) {
+            for (int u = 0; u < kEdges; ++u) {
               if (j + u < LANES) {
                 float ws = __uint_as_float((u & 1) ? ed[u / 2].w : ed[u / 2].y);
                 if (WKIND == 2) {
                   ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
                   if (DIV) ws = ws / den;
                 }
-                fma4(acc, ws, v[u]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) fma_row<T>(acc[v], ws, raw[u][v]);
               }
             }
           }
         }
       } else {
         const int nmax = (LANES == 32) ? n : LANES;
-        for (int j = 0; j < nmax; j += kAggUnroll) {
-          float4 v[kAggUnroll];
-          float wv[kAggUnroll];
+        for (int j = 0; j < nmax; j += kEdges) {
+          uint4 raw[kEdges][V];
+          float wv[kEdges];
 #pragma unroll
-          for (int u = 0; u < kAggUnroll; ++u) {
+          for (int u = 0; u < kEdges; ++u) {
             if (j + u < LANES) {
               const uint2 ed = mine[j + u];
-              const bool ok = active && (j + u) < n;
+              const bool ok = have && (j + u) < n;
               float ws = ok ? __uint_as_float(ed.y) : 0.f;
-              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok) v[u] = ld_row_f32x4(row_ptr(xf, ed.x, row_bytes), pol_keep);
+              const char* rp = row_addr(xf, ed.x, row_bytes);
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                raw[u][v] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok && on[v]) raw[u][v] = ld_row_raw(rp + v * LANES * 16, pol_keep);
+              }
               if (WKIND == 2) {
                 ws = 0.f;
-                if (ok) {
+                if (ok && active) {
                   ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
                   if (DIV) ws = ws / den;
                 }
@@ -344,8 +431,10 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
             }
           }
 #pragma unroll
-          for (int u = 0; u < kAggUnroll; ++u)
-            if (j + u < LANES) fma4(acc, wv[u], v[u]);
+          for (int u = 0; u < kEdges; ++u)
+            if (j + u < LANES)
+#pragma unroll
+              for (int v = 0; v < V; ++v) fma_row<T>(acc[v], wv[u], raw[u][v]);
         }
       }
       __syncwarp();
@@ -359,19 +448,29 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
         if (it.w != s0) {
           if (l == 0) chain_wait(flags + it.w - 1);
           __syncwarp(group_mask<LANES>(lane));
-          if (active) {
-            const float4 p = ld_state_f32x4(wl.partials + int64_t(it.w - 1) * f + fo);
-            acc.x = p.x + acc.x; acc.y = p.y + acc.y; acc.z = p.z + acc.z; acc.w = p.w + acc.w;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            if (have && on[v]) {
+              float p[KP];
+              ld_state<KP>(wl.partials + int64_t(it.w - 1) * f + fo + v * LANES * KP, p);
+#pragma unroll
+              for (int c = 0; c < KP; ++c) acc[v][c] = p[c] + acc[v][c];
+            }
           }
         }
         if (!last) {
-          if (active) *reinterpret_cast<float4*>(wl.partials + int64_t(it.w) * f + fo) = acc;
-          __threadfence();
-          __syncwarp(group_mask<LANES>(lane));
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (have && on[v]) st_state<KP>(wl.partials + int64_t(it.w) * f + fo + v * LANES * KP, acc[v]);
+          __syncwarp(group_mask<LANES>(lane));          // the group's stores happen-before lane 0's release
           if (l == 0) chain_publish(flags + it.w);
         }
       }
-      if (last && active) st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
+      if (last) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (have && on[v]) st_out<KP>(out + int64_t(it.x) * ldo + fo + v * LANES * KP, acc[v], 1.f, epilogue);
+      }
     });
     first += 32 / LANES;
     if (first >= batch_end) {
@@ -427,18 +526,27 @@ __device__ __forceinline__ float pick(const float (&v)[H], int h) {
 constexpr float kBoundRange = 60.f;
 // er_stats[cb*pitch + h] = code(max er), er_stats[cb*pitch + heads + h] = code(max -er); 0 = "no source seen".
 // pitch = 2*heads for a gta_er_stats buffer, 64 for the statistics of a signal block (exchange.cuh).
-__device__ __forceinline__ bool block_bound(const uint32_t* er_stats, int64_t cb, int pitch, int heads, int h,
-                                            float* er_max) {
-  const uint32_t cmax = __ldcg(er_stats + cb * pitch + h), cneg = __ldcg(er_stats + cb * pitch + heads + h);
+__device__ __forceinline__ bool block_bound(const uint32_t* er_stats, int64_t cb0, int64_t cb1, int pitch, int heads,
+                                            int h, float* er_max) {
+  // an item may span several statistics blocks (an exchange groups its peers' slots): the bound and the
+  // range test are taken over their union
+  uint32_t cmax = 0u, cneg = 0u;
+  bool seen = true;
+  for (int64_t cb = cb0; cb <= cb1; ++cb) {
+    const uint32_t a = __ldcg(er_stats + cb * pitch + h), b = __ldcg(er_stats + cb * pitch + heads + h);
+    seen = seen && a != 0u && b != 0u;
+    cmax = a > cmax ? a : cmax;
+    cneg = b > cneg ? b : cneg;
+  }
   const float hi = ordered_decode(cmax), lo = -ordered_decode(cneg);
   *er_max = hi;
-  return cmax != 0u && cneg != 0u && (hi - lo) < kBoundRange;      // NaN compares false
+  return seen && (hi - lo) < kBoundRange;      // NaN compares false
 }
 
-template <int LANES, int H>
+template <typename T, int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? GTA_GAT_MINBLOCKS : (GTA_GAT_MINBLOCKS + 1) / 2)
 gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ el, const float* __restrict__ er,
-                     int64_t lder, float slope, const float* __restrict__ z, const uint32_t row_bytes,
+                     int64_t lder, float slope, const T* __restrict__ z, const uint32_t row_bytes,
                      float* __restrict__ out, int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
                      float* __restrict__ rowsum, const uint32_t* er_stats, int stats_pitch, int64_t col_block) {
   // per warp: H rows of 32 staged edges, entry = {source id, softmax numerator}.  Row pitch kS = 34
@@ -447,6 +555,8 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   // hits 4 disjoint bank quads (68 words = 4 mod 32).  Round 1 staged [edge][head]: 4-way conflicts on
   // every store, 27 % of the L1/TEX data-pipe wavefronts of the kernel.
   constexpr int kS = 34;
+  constexpr int KP = Elem<T>::kPer;
+  constexpr int kWindow = LANES * KP;
   __shared__ __align__(16) uint2 s_e[kAggWarps][H * kS];
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
     exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
@@ -455,7 +565,7 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int gbase = lane & ~(LANES - 1);          // first lane of my group inside the warp
-  const int fo = blockIdx.y * 128 + 4 * l;
+  const int fo = blockIdx.y * kWindow + KP * l;
   const int head = (fo < f) ? fo / (f / H) : 0;
   uint2* se = s_e[threadIdx.x >> 5];
   const uint2* mine = se + head * kS + gbase;
@@ -465,6 +575,7 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
   const int pstride = gat_partial_stride(f, H);
   const int stats = f + int(blockIdx.y) * gat_stats_stride(H);
+  const char* zf = reinterpret_cast<const char*>(z + (fo < f ? fo : 0));
 
   int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
   int32_t batch_end = first + wl.take;
@@ -477,13 +588,14 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
     const int count = have ? it.z : 0;
     const int max_count = (LANES == 32) ? count : warp_max_i32(count);
     const int32_t* idx_base = wl.indices + it.y;
-    const float* zf = z + (active ? fo : 0);
 
     float elr[H], m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
     if (have) load_heads<H>(el + int64_t(it.x) * H, elr);
 #pragma unroll
     for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; if (!have) elr[h] = 0.f; }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[KP];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) acc[c] = 0.f;
 
     // software pipeline: source ids are loaded two batches ahead and the er rows one batch ahead, so
     // the id -> er -> softmax dependency chain of batch b+1 hides under the row gathers of batch b
@@ -493,8 +605,10 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
     for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
     if (l < count) idx_cur = ld_stream_i32(idx_base + l, pol_stream);
     if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
-    if (ex.world > 1) {          // the item's slot (z, er and its er range) may still be on its way from a peer
-      if (l == 0 && count > 0) exchange_gate(ex, idx_cur);
+    // an item's sources are ascending: its last id names the highest slot (statistics block) it touches
+    const int last_src = (count > 0 && (ex.world > 1 || er_stats != nullptr)) ? __ldg(idx_base + count - 1) : 0;
+    if (ex.world > 1) {          // the item's slots (z, er and their er range) may still be on their way from the peers
+      if (l == 0 && count > 0) exchange_gate(ex, last_src);
       __syncwarp();
     }
     if (l < count) load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
@@ -505,11 +619,12 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
       bool ok = true;
       const int first_src = __shfl_sync(0xffffffffu, idx_cur, gbase);
       if (count > 0) {
-        const int64_t cb = col_block > 0 ? int64_t(first_src) / col_block : 0;
+        const int64_t cb0 = col_block > 0 ? int64_t(first_src) / col_block : 0;
+        const int64_t cb1 = col_block > 0 ? int64_t(last_src) / col_block : 0;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           float hi;
-          ok = block_bound(er_stats, cb, stats_pitch, H, h, &hi) && ok;
+          ok = block_bound(er_stats, cb0, cb1, stats_pitch, H, h, &hi) && ok;
           if (ok) m[h] = leaky(elr[h] + hi, slope);
         }
       }
@@ -551,7 +666,8 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
           my_scale = (h == head) ? sc : my_scale;
           se[h * kS + lane] = make_uint2(uint32_t(my_idx), __float_as_uint(p));
         }
-        acc.x *= my_scale; acc.y *= my_scale; acc.z *= my_scale; acc.w *= my_scale;
+#pragma unroll
+        for (int c = 0; c < KP; ++c) acc[c] *= my_scale;
       }
       __syncwarp();
       const bool full = (LANES == 32) ? (n == LANES) : __all_sync(0xffffffffu, n == LANES && active);
@@ -560,22 +676,22 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
 #pragma unroll 1
           for (int j = 0; j < LANES; j += kGatUnroll) {
             uint4 ed[kGatUnroll / 2];
-            float4 v[kGatUnroll];
+            uint4 raw[kGatUnroll];
 #pragma unroll
             for (int u = 0; u < kGatUnroll / 2; ++u)
               if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
             for (int u = 0; u < kGatUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
-                v[2 * u] = ld_row_f32x4(row_ptr(zf, ed[u].x, row_bytes), pol_keep);
-                v[2 * u + 1] = ld_row_f32x4(row_ptr(zf, ed[u].z, row_bytes), pol_keep);
+                raw[2 * u] = ld_row_raw(row_addr(zf, ed[u].x, row_bytes), pol_keep);
+                raw[2 * u + 1] = ld_row_raw(row_addr(zf, ed[u].z, row_bytes), pol_keep);
               }
             }
 #pragma unroll
             for (int u = 0; u < kGatUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
-                fma4(acc, __uint_as_float(ed[u].y), v[2 * u]);
-                fma4(acc, __uint_as_float(ed[u].w), v[2 * u + 1]);
+                fma_row<T>(acc, __uint_as_float(ed[u].y), raw[2 * u]);
+                fma_row<T>(acc, __uint_as_float(ed[u].w), raw[2 * u + 1]);
               }
             }
           }
@@ -583,20 +699,20 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
       } else {
         const int nmax = (LANES == 32) ? n : LANES;
         for (int j = 0; j < nmax; j += kGatUnroll) {
-          float4 v[kGatUnroll];
+          uint4 raw[kGatUnroll];
           float pv[kGatUnroll];
 #pragma unroll
           for (int u = 0; u < kGatUnroll; ++u) {
             if (j + u < LANES) {
               const uint2 ed = mine[j + u];
               pv[u] = __uint_as_float(ed.y);
-              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, ed.x, row_bytes), pol_keep);
+              raw[u] = make_uint4(0u, 0u, 0u, 0u);
+              if (active && (j + u) < n) raw[u] = ld_row_raw(row_addr(zf, ed.x, row_bytes), pol_keep);
             }
           }
 #pragma unroll
           for (int u = 0; u < kGatUnroll; ++u)
-            if (j + u < LANES) fma4(acc, pv[u], v[u]);
+            if (j + u < LANES) fma_row<T>(acc, pv[u], raw[u]);
         }
       }
       __syncwarp();
@@ -627,27 +743,27 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
             b_mine = (h == head) ? b : b_mine;
           }
           if (active) {
-            const float4 p = ld_state_f32x4(prev + fo);
-            acc.x = fmaf(p.x, a_mine, acc.x * b_mine); acc.y = fmaf(p.y, a_mine, acc.y * b_mine);
-            acc.z = fmaf(p.z, a_mine, acc.z * b_mine); acc.w = fmaf(p.w, a_mine, acc.w * b_mine);
+            float p[KP];
+            ld_state<KP>(prev + fo, p);
+#pragma unroll
+            for (int c = 0; c < KP; ++c) acc[c] = fmaf(p[c], a_mine, acc[c] * b_mine);
           }
         }
         if (!last) {
           float* part = wl.partials + int64_t(it.w) * pstride;
-          if (active) *reinterpret_cast<float4*>(part + fo) = acc;
+          if (active) st_state<KP>(part + fo, acc);
           if (l < H) {
             part[stats + l] = pick<H>(m, l);
             part[stats + H + l] = pick<H>(s, l);
           }
-          __threadfence();
-          __syncwarp(group_mask<LANES>(lane));
+          __syncwarp(group_mask<LANES>(lane));          // the group's stores happen-before lane 0's release
           if (l == 0) chain_publish(flags + it.w);
         }
       }
       if (last && have) {
         if (active) {
           const float sh = pick<H>(s, head);
-          st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, sh > 0.f ? 1.f / sh : 0.f, epilogue));
+          st_out<KP>(out + int64_t(it.x) * ldo + fo, acc, sh > 0.f ? 1.f / sh : 0.f, epilogue);
         }
         if (blockIdx.y == 0 && l < H) {
           const float ml = pick<H>(m, l);
@@ -720,8 +836,9 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int idx_nxt = 0;
     if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+    const int last_src = (count > 0 && (ex.world > 1 || er_stats != nullptr)) ? __ldg(idx_base + count - 1) : 0;
     if (ex.world > 1) {
-      if (l == 0 && count > 0) exchange_gate(ex, idx_nxt);
+      if (l == 0 && count > 0) exchange_gate(ex, last_src);
       __syncwarp();
     }
     // bound path (see gat_aggregate_kernel): a lane only needs the bound of its own head; the choice is
@@ -730,11 +847,12 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
     int first_src = 0;
     if (er_stats != nullptr) first_src = __shfl_sync(0xffffffffu, idx_nxt, lane & ~(LANES - 1));
     if (er_stats != nullptr && count > 0) {
-      const int64_t cb = col_block > 0 ? int64_t(first_src) / col_block : 0;
+      const int64_t cb0 = col_block > 0 ? int64_t(first_src) / col_block : 0;
+      const int64_t cb1 = col_block > 0 ? int64_t(last_src) / col_block : 0;
       bool ok = true;
       for (int h = 0; h < heads; ++h) {          // every head of the block must pass: lanes of one item agree
         float hi;
-        ok = block_bound(er_stats, cb, stats_pitch, heads, h, &hi) && ok;
+        ok = block_bound(er_stats, cb0, cb1, stats_pitch, heads, h, &hi) && ok;
         if (h == head) m = leaky(elh + hi, slope);
       }
       bounded = ok;
@@ -824,8 +942,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
             part[stats + head] = m;
             part[stats + heads + head] = s;
           }
-          __threadfence();
-          __syncwarp(group_mask<LANES>(lane));
+          __syncwarp(group_mask<LANES>(lane));          // the group's stores happen-before lane 0's release
           if (l == 0) chain_publish(flags + it.w);
         }
       }
@@ -948,14 +1065,15 @@ gat_logits_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict_
   }
 }
 
-static int lanes_for(int f) {
-  int v = (f < 128 ? f : 128) / 4;
+// lanes per item for rows of f features, kper features per 16-byte piece, v pieces per lane
+static int lanes_for(int f, int kper = 4, int v = 1) {
+  const int window = 32 * kper * v;
+  int need = ((f < window ? f : window) + kper * v - 1) / (kper * v);
   int l = 1;
-  while (l < v) l <<= 1;
+  while (l < need) l <<= 1;
   return l < 4 ? 4 : l;
 }
 
-// persistent grid: as many CTAs as fit on the device at once (or fewer when the list is short)
 template <typename K>
 static int resident_ctas(K kernel) {
   static int cached = 0;          // one static per kernel instantiation
@@ -1023,33 +1141,43 @@ static int make_exchange(const char* who, const gta_exchange_t* h, int32_t* arri
   return GTA_OK;
 }
 
-template <int LANES>
+template <typename T, int V, int LANES>
 static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkList& wl, const Exchange& ex,
-                               const float* w, int wh, const float* rowden, const float* x, int64_t ldx, float* out,
+                               const float* w, int wh, const float* rowden, const T* x, int64_t ldx, float* out,
                                int64_t ldo, int f, int epi) {
-#define GTA_AGG(K, D)                                                                                          \
-  aggregate_kernel<LANES, K, D><<<persistent_grid(aggregate_kernel<LANES, K, D>, wl.num_items, LANES, f, ex),   \
-                                  kAggThreads, 0, st>>>(with_take(wl, take_for(aggregate_kernel<LANES, K, D>,    \
-                                                                               wl.num_items, LANES)),           \
-                                                        ex, w, wh, rowden, x, uint32_t(ldx) * 4u, out, ldo, f, epi)
+  constexpr int kWin = LANES * Elem<T>::kPer * V;
+#define GTA_AGG(K, D)                                                                                               \
+  do {                                                                                                              \
+    auto kern = aggregate_kernel<T, V, LANES, K, D>;                                                                \
+    dim3 grid = persistent_grid(kern, wl.num_items, LANES, 1, ex);                                                  \
+    grid.y = (unsigned)((f + kWin - 1) / kWin);                                                                     \
+    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl.num_items, LANES)), ex, w, wh, rowden, x,    \
+                                       uint32_t(ldx * sizeof(T)), out, ldo, f, epi);                                \
+  } while (0)
   if (wkind == 0) GTA_AGG(0, false);
   else if (wkind == 1 && !div) GTA_AGG(1, false);
   else if (wkind == 1 && div) GTA_AGG(1, true);
-  else if (wkind == 2 && !div) GTA_AGG(2, false);
-  else GTA_AGG(2, true);
+  else if constexpr (V == 1) {
+    if (!div) GTA_AGG(2, false);
+    else GTA_AGG(2, true);
+  }
 #undef GTA_AGG
 }
 
-template <int H>
+template <typename T, int H>
 static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const Exchange& ex, const float* el,
-                        const float* er, int64_t lder, float slope, const float* z, int64_t ldz, float* out, int64_t ldo,
+                        const float* er, int64_t lder, float slope, const T* z, int64_t ldz, float* out, int64_t ldo,
                         int f, int epi, float* rowmax, float* rowsum, const uint32_t* er_stats, int stats_pitch,
                         int64_t col_block) {
-#define GTA_GAT(L)                                                                                              \
-  gat_aggregate_kernel<L, H><<<persistent_grid(gat_aggregate_kernel<L, H>, wl.num_items, L, f, ex), kAggThreads, \
-                               0, st>>>(with_take(wl, take_for(gat_aggregate_kernel<L, H>, wl.num_items, L)), ex, \
-                                        el, er, lder, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epi,           \
-                                        rowmax, rowsum, er_stats, stats_pitch, col_block)
+#define GTA_GAT(L)                                                                                                  \
+  do {                                                                                                              \
+    auto kern = gat_aggregate_kernel<T, L, H>;                                                                      \
+    dim3 grid = persistent_grid(kern, wl.num_items, L, 1, ex);                                                      \
+    grid.y = (unsigned)((f + L * Elem<T>::kPer - 1) / (L * Elem<T>::kPer));                                         \
+    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl.num_items, L)), ex, el, er, lder, slope, z,  \
+                                       uint32_t(ldz * sizeof(T)), out, ldo, f, epi, rowmax, rowsum, er_stats,       \
+                                       stats_pitch, col_block);                                                     \
+  } while (0)
   switch (lanes) {
     case 4: if (H <= 4) { GTA_GAT(4); return GTA_OK; } break;
     case 8: if (H <= 8) { GTA_GAT(8); return GTA_OK; } break;
@@ -1087,6 +1215,136 @@ static int prepare_worklist(const char* who, WorkList& wl, int32_t* chain_state,
   return GTA_OK;
 }
 
+// ---- the two aggregation entry points, for either storage type of the gathered table ---------------
+template <typename T>
+static int aggregate_impl(const char* who, const int32_t* items_, int64_t num_items, const int32_t* row_slots,
+                          int64_t num_slots, const int32_t* indices, int32_t wmode, const float* w, int32_t wh,
+                          const float* rowden, const T* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
+                          int32_t epilogue, float* partials, int32_t* chain_state, const gta_exchange_t* exchange,
+                          int32_t phases, void* stream_) {
+  constexpr int KP = Elem<T>::kPer;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  GTA_REQUIRE(f > 0 && f % KP == 0, "%s: f=%d must be a positive multiple of %d (pad the table)", who, f, KP);
+  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "%s: bad item count", who);
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
+  int rc = prepare_worklist(who, wl, chain_state, f, phases, st);
+  if (rc != GTA_OK) return rc;
+  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
+  GTA_REQUIRE(items_ && indices && x && out, "%s: null pointer", who);
+  GTA_REQUIRE(ldx % KP == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f && ldx * int64_t(sizeof(T)) < (int64_t(1) << 32),
+              "%s: leading dimensions must be whole 16-byte pieces, >= f, and a row below 4 GiB", who);
+  GTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "%s: tables must be 16-byte aligned", who);
+  GTA_REQUIRE(wmode >= GTA_W_NONE && wmode <= GTA_W_EDGE_DIV, "%s: bad wmode %d", who, wmode);
+  int wkind = 0;
+  bool div = wmode == GTA_W_EDGE_DIV;
+  if (wmode != GTA_W_NONE) {
+    GTA_REQUIRE(w && wh >= 1 && f % wh == 0, "%s: weight width %d must divide f=%d", who, wh, f);
+    GTA_REQUIRE(!div || rowden, "%s: rowden required for GTA_W_EDGE_DIV", who);
+    wkind = wh == 1 ? 1 : 2;
+    if (wkind == 2 && (f / wh) % KP != 0) {
+      set_error("%s: per-head width f/wh=%d is not a multiple of %d", who, f / wh, KP);
+      return GTA_ERR_UNSUPPORTED;
+    }
+  }
+  Exchange ex;
+  rc = make_exchange(who, exchange, wl.work_counter + (f + 127) / 128, ldx * int64_t(sizeof(T)), &ex);
+  if (rc != GTA_OK) return rc;
+  GTA_REQUIRE(ex.world <= 1 || ex.table == reinterpret_cast<const char*>(x), "%s: x is not the exchange table", who);
+  // rows wider than one 32-lane pass of single pieces: two pieces per lane (one walk of the work list, not two)
+  if (f > 32 * KP && wkind != 2) {
+    dispatch_aggregate<T, 2, 32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue);
+  } else {
+    switch (lanes_for(f, KP)) {
+      case 4: dispatch_aggregate<T, 1, 4>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+      case 8: dispatch_aggregate<T, 1, 8>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+      case 16: dispatch_aggregate<T, 1, 16>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+      default: dispatch_aggregate<T, 1, 32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    }
+  }
+  GTA_CHECK_LAUNCH("aggregate_kernel");
+  return GTA_OK;
+}
+
+template <typename T>
+static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t num_items, const int32_t* row_slots,
+                              int64_t num_slots, const int32_t* indices, const float* el, const float* er, int64_t lder,
+                              int32_t heads, float slope, const T* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                              int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_state,
+                              const uint32_t* er_stats, int64_t col_block, const gta_exchange_t* exchange,
+                              int32_t phases, void* stream_) {
+  constexpr int KP = Elem<T>::kPer;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  GTA_REQUIRE(f > 0 && f % KP == 0, "%s: f=%d must be a positive multiple of %d", who, f, KP);
+  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "%s: bad item count", who);
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
+  int rc = prepare_worklist(who, wl, chain_state, f, phases, st);
+  if (rc != GTA_OK) return rc;
+  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
+  GTA_REQUIRE(items_ && indices && el && er && z && out, "%s: null pointer", who);
+  GTA_REQUIRE(ldz % KP == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f && ldz * int64_t(sizeof(T)) < (int64_t(1) << 32),
+              "%s: leading dimensions must be whole 16-byte pieces, >= f, and a row below 4 GiB", who);
+  GTA_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
+              "%s: tables must be 16-byte aligned", who);
+  GTA_REQUIRE(heads >= 1 && f % heads == 0, "%s: heads=%d must divide f=%d", who, heads, f);
+  GTA_REQUIRE(lder >= heads && (heads % 4 != 0 || lder % 4 == 0) && (heads % 2 != 0 || lder % 2 == 0),
+              "%s: er row stride %lld breaks the vector alignment of %d heads", who, (long long)lder, heads);
+  if ((f / heads) % KP != 0) {
+    set_error("%s: per-head width f/heads=%d is not a multiple of %d", who, f / heads, KP);
+    return GTA_ERR_UNSUPPORTED;
+  }
+  Exchange ex;
+  rc = make_exchange(who, exchange, wl.work_counter + (f + 127) / 128, ldz * int64_t(sizeof(T)), &ex);
+  if (rc != GTA_OK) return rc;
+  int stats_pitch = 2 * heads;
+  if (ex.world > 1) {
+    GTA_REQUIRE(ex.table == reinterpret_cast<const char*>(z), "%s: z is not the exchange table", who);
+    // the slot owners published their er range with the step; a slot's statistics are valid once it has landed
+    er_stats = &ex.signals->stats[ex.step & 1][0][0];
+    stats_pitch = 64;
+    col_block = ex.slot_rows;
+    if ((heads & (heads - 1)) != 0 || heads > 32) er_stats = nullptr;
+  }
+  // the bound path does not track the true row maximum: callers that want it back run the online softmax
+  if (rowmax != nullptr) er_stats = nullptr;
+  const int lanes = lanes_for(f, KP);
+  // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
+  // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint; fp32 tables only)
+  const bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
+  if (staged) {
+    rc = GTA_ERR_UNSUPPORTED;
+#define GTA_GAT_H(HH) rc = dispatch_gat<T, HH>(lanes, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
+    switch (heads) {
+      case 1: GTA_GAT_H(1); break;
+      case 2: GTA_GAT_H(2); break;
+      default: GTA_GAT_H(4); break;
+    }
+#undef GTA_GAT_H
+    if (rc != GTA_OK) {
+      set_error("%s: no kernel for heads=%d, f=%d", who, heads, f);
+      return rc;
+    }
+  } else if constexpr (sizeof(T) == 4) {
+#define GTA_LLH(L)                                                                                                  \
+  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f, ex), kAggThreads, 0, \
+                                st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl.num_items, L)), ex, el,   \
+                                      er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,                     \
+                                      epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
+    switch (lanes) {
+      case 4: GTA_LLH(4); break;
+      case 8: GTA_LLH(8); break;
+      case 16: GTA_LLH(16); break;
+      default: GTA_LLH(32); break;
+    }
+#undef GTA_LLH
+  } else {
+    set_error("%s: %d heads on a bf16 table has no kernel yet (fp32 tables: any head count)", who, heads);
+    return GTA_ERR_UNSUPPORTED;
+  }
+  GTA_CHECK_LAUNCH("gat_aggregate_kernel");
+  return GTA_OK;
+}
+
 }  // namespace gta
 
 using namespace gta;
@@ -1095,45 +1353,23 @@ extern "C" {
 
 int32_t gta_gat_partial_stride(int32_t f, int32_t heads) { return gat_partial_stride(f, heads); }
 
-int gta_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
                       const int32_t* indices, int32_t wmode, const float* w, int32_t wh, const float* rowden,
                       const float* x, int64_t ldx, float* out, int64_t ldo, int32_t f, int32_t epilogue,
                       float* partials, int32_t* chain_state, const gta_exchange_t* exchange, int32_t phases,
-                      void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_aggregate_f32: f=%d must be a positive multiple of 4 (pad the table)", f);
-  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_aggregate_f32: bad item count");
-  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
-  int rc = prepare_worklist("gta_aggregate_f32", wl, chain_state, f, phases, st);
-  if (rc != GTA_OK) return rc;
-  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
-  GTA_REQUIRE(items_ && indices && x && out, "gta_aggregate_f32: null pointer");
-  GTA_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f && ldx < (int64_t(1) << 30), "gta_aggregate_f32: leading dimensions must be multiples of 4, >= f and < 2^30");
-  GTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gta_aggregate_f32: tables must be 16-byte aligned");
-  GTA_REQUIRE(wmode >= GTA_W_NONE && wmode <= GTA_W_EDGE_DIV, "gta_aggregate_f32: bad wmode %d", wmode);
-  int wkind = 0;
-  bool div = wmode == GTA_W_EDGE_DIV;
-  if (wmode != GTA_W_NONE) {
-    GTA_REQUIRE(w && wh >= 1 && f % wh == 0, "gta_aggregate_f32: weight width %d must divide f=%d", wh, f);
-    GTA_REQUIRE(!div || rowden, "gta_aggregate_f32: rowden required for GTA_W_EDGE_DIV");
-    wkind = wh == 1 ? 1 : 2;
-    if (wkind == 2 && (f / wh) % 4 != 0) {
-      set_error("gta_aggregate_f32: per-head width f/wh=%d is not a multiple of 4", f / wh);
-      return GTA_ERR_UNSUPPORTED;
-    }
-  }
-  Exchange ex;
-  rc = make_exchange("gta_aggregate_f32", exchange, wl.work_counter + (f + 127) / 128, ldx, &ex);
-  if (rc != GTA_OK) return rc;
-  GTA_REQUIRE(ex.world <= 1 || ex.table == reinterpret_cast<const char*>(x), "gta_aggregate_f32: x is not the exchange table");
-  switch (lanes_for(f)) {
-    case 4: dispatch_aggregate<4>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    case 8: dispatch_aggregate<8>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    case 16: dispatch_aggregate<16>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    default: dispatch_aggregate<32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-  }
-  GTA_CHECK_LAUNCH("aggregate_kernel");
-  return GTA_OK;
+                      void* stream) {
+  return aggregate_impl<float>("gta_aggregate_f32", items, num_items, row_slots, num_slots, indices, wmode, w, wh, rowden,
+                               x, ldx, out, ldo, f, epilogue, partials, chain_state, exchange, phases, stream);
+}
+
+int gta_aggregate_bf16(const int32_t* items, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+                       const int32_t* indices, int32_t wmode, const float* w, int32_t wh, const float* rowden,
+                       const void* x, int64_t ldx, float* out, int64_t ldo, int32_t f, int32_t epilogue,
+                       float* partials, int32_t* chain_state, const gta_exchange_t* exchange, int32_t phases,
+                       void* stream) {
+  return aggregate_impl<__nv_bfloat16>("gta_aggregate_bf16", items, num_items, row_slots, num_slots, indices, wmode, w, wh,
+                                       rowden, static_cast<const __nv_bfloat16*>(x), ldx, out, ldo, f, epilogue, partials,
+                                       chain_state, exchange, phases, stream);
 }
 
 int gta_gather_peak_probe(const float* table, int64_t rows, int64_t ld, int32_t f, int64_t gathers_per_group,
@@ -1178,78 +1414,27 @@ int gta_er_stats(const float* er, int64_t lder, int64_t num_sources, int64_t col
   return GTA_OK;
 }
 
-int gta_gat_aggregate_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+int gta_gat_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
                           const int32_t* indices, const float* el, const float* er, int64_t lder, int32_t heads,
                           float slope, const float* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_state,
                           const uint32_t* er_stats, int64_t col_block, const gta_exchange_t* exchange,
-                          int32_t phases, void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(f > 0 && f % 4 == 0, "gta_gat_aggregate_f32: f=%d must be a positive multiple of 4", f);
-  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "gta_gat_aggregate_f32: bad item count");
-  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
-  int rc = prepare_worklist("gta_gat_aggregate_f32", wl, chain_state, f, phases, st);
-  if (rc != GTA_OK) return rc;
-  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
-  GTA_REQUIRE(items_ && indices && el && er && z && out, "gta_gat_aggregate_f32: null pointer");
-  GTA_REQUIRE(ldz % 4 == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f && ldz < (int64_t(1) << 30), "gta_gat_aggregate_f32: leading dimensions must be multiples of 4, >= f and < 2^30");
-  GTA_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
-              "gta_gat_aggregate_f32: tables must be 16-byte aligned");
-  GTA_REQUIRE(heads >= 1 && f % heads == 0, "gta_gat_aggregate_f32: heads=%d must divide f=%d", heads, f);
-  GTA_REQUIRE(lder >= heads && (heads % 4 != 0 || lder % 4 == 0) && (heads % 2 != 0 || lder % 2 == 0),
-              "gta_gat_aggregate_f32: er row stride %lld breaks the vector alignment of %d heads", (long long)lder, heads);
-  if ((f / heads) % 4 != 0) {
-    set_error("gta_gat_aggregate_f32: per-head width f/heads=%d is not a multiple of 4", f / heads);
-    return GTA_ERR_UNSUPPORTED;
-  }
-  Exchange ex;
-  rc = make_exchange("gta_gat_aggregate_f32", exchange, wl.work_counter + (f + 127) / 128, ldz, &ex);
-  if (rc != GTA_OK) return rc;
-  int stats_pitch = 2 * heads;
-  if (ex.world > 1) {
-    GTA_REQUIRE(ex.table == reinterpret_cast<const char*>(z), "gta_gat_aggregate_f32: z is not the exchange table");
-    // the slot owners published their er range with the step; a slot's statistics are valid once it has landed
-    er_stats = &ex.signals->stats[ex.step & 1][0][0];
-    stats_pitch = 64;
-    col_block = ex.slot_rows;
-    if ((heads & (heads - 1)) != 0 || heads > 32) er_stats = nullptr;
-  }
-  // the bound path does not track the true row maximum: callers that want it back run the online softmax
-  if (rowmax != nullptr) er_stats = nullptr;
-  const int lanes = lanes_for(f);
-  // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
-  // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint)
-  const bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
-  if (staged) {
-    rc = GTA_ERR_UNSUPPORTED;
-#define GTA_GAT_H(HH) rc = dispatch_gat<HH>(lanes, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
-    switch (heads) {
-      case 1: GTA_GAT_H(1); break;
-      case 2: GTA_GAT_H(2); break;
-      default: GTA_GAT_H(4); break;
-    }
-#undef GTA_GAT_H
-    if (rc != GTA_OK) {
-      set_error("gta_gat_aggregate_f32: no kernel for heads=%d, f=%d", heads, f);
-      return rc;
-    }
-  } else {
-#define GTA_LLH(L)                                                                                                  \
-  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f, ex), kAggThreads, 0, \
-                                st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl.num_items, L)), ex, el,   \
-                                      er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,                     \
-                                      epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
-    switch (lanes) {
-      case 4: GTA_LLH(4); break;
-      case 8: GTA_LLH(8); break;
-      case 16: GTA_LLH(16); break;
-      default: GTA_LLH(32); break;
-    }
-#undef GTA_LLH
-  }
-  GTA_CHECK_LAUNCH("gat_aggregate_kernel");
-  return GTA_OK;
+                          int32_t phases, void* stream) {
+  return gat_aggregate_impl<float>("gta_gat_aggregate_f32", items, num_items, row_slots, num_slots, indices, el, er, lder,
+                                   heads, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, partials, chain_state,
+                                   er_stats, col_block, exchange, phases, stream);
+}
+
+int gta_gat_aggregate_bf16(const int32_t* items, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+                           const int32_t* indices, const float* el, const float* er, int64_t lder, int32_t heads,
+                           float slope, const void* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                           int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_state,
+                           const uint32_t* er_stats, int64_t col_block, const gta_exchange_t* exchange,
+                           int32_t phases, void* stream) {
+  return gat_aggregate_impl<__nv_bfloat16>("gta_gat_aggregate_bf16", items, num_items, row_slots, num_slots, indices, el,
+                                           er, lder, heads, slope, static_cast<const __nv_bfloat16*>(z), ldz, out, ldo, f,
+                                           epilogue, rowmax, rowsum, partials, chain_state, er_stats, col_block, exchange,
+                                           phases, stream);
 }
 
 int gta_gat_logits_f32(const int64_t* indptr, const int32_t* indices, int64_t row_begin, int64_t row_end,

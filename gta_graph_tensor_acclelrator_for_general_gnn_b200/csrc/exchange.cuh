@@ -90,10 +90,12 @@ __device__ __forceinline__ void exchange_pull(const Exchange& ex, int cta) {
   }
 }
 
-// Gate of a work-list group: `src` is any source id of the item (its first); slot 0 is the rank's own rows.
-// Called by ONE lane of the group, followed by a group-wide __syncwarp by the caller.
-__device__ __forceinline__ void exchange_gate(const Exchange& ex, int32_t src) {
-  const int64_t k = int64_t(src) / ex.slot_rows;
+// Gate of a work-list group: `last_src` is the item's LAST (= highest) source id.  The copy CTAs finish the
+// slots in ring order, so once the slot of the last source has landed every earlier slot the item touches
+// has too.  Slot 0 is the rank's own rows.  Called by ONE lane of the group, followed by a group-wide
+// __syncwarp by the caller.
+__device__ __forceinline__ void exchange_gate(const Exchange& ex, int32_t last_src) {
+  const int64_t k = int64_t(last_src) / ex.slot_rows;
   if (k > 0) wait_at_least<false>(ex.arrived + k, ex.copy_ctas);
 }
 

@@ -12,7 +12,7 @@ int attn_project_launch(const float* z, int64_t ldz, int64_t num_rows, int f, co
 // returns GTA_ERR_UNSUPPORTED when the shape is outside the tensor-core kernel's rules
 int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
                    int k, int f, const float* al, const float* ar, int heads, float* el, float* er, int64_t lder,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st);
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, int z_bf16 = 0);
 size_t gemm_tc_workspace(int k, int f);
 }  // namespace gta
 
@@ -57,6 +57,27 @@ int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, float
   if (rc != GTA_OK) return rc;
   if (want_attn) return attn_project_launch(z, ldz, num_rows, f, al, ar, heads, el, er, lder, st);
   return GTA_OK;
+}
+
+// bf16 storage mode: the same fp32-accurate product, Z rounded to bf16 once in the
+// epilogue of the tcgen05 kernel (ldz counts bf16 elements, a multiple of 8); el / er from the fp32 accumulators.
+int gta_gemm_f32_zbf16(const float* x, int64_t ldx, const float* w, int64_t ldw, void* z, int64_t ldz, int64_t num_rows,
+                       int32_t k, int32_t f, const float* al, const float* ar, int32_t heads, float* el, float* er,
+                       int64_t lder, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (num_rows == 0) return GTA_OK;
+  GTA_REQUIRE(x && w && z, "gta_gemm_f32_zbf16: null pointer");
+  GTA_REQUIRE(num_rows > 0 && k > 0 && f > 0, "gta_gemm_f32_zbf16: non-positive shape");
+  GTA_REQUIRE(ldx >= k && ldw >= f && ldz >= f, "gta_gemm_f32_zbf16: leading dimension smaller than the row");
+  const bool want_attn = (el && al) || (er && ar);
+  GTA_REQUIRE(!want_attn || heads >= 1, "gta_gemm_f32_zbf16: heads must be >= 1 when el/er are requested");
+  if (lder <= 0) lder = heads;
+  int rc = gemm_tc_launch(x, ldx, w, ldw, static_cast<float*>(z), ldz, num_rows, k, f, al, ar, heads, el, er, lder, workspace,
+                          workspace_bytes, st, 1);
+  if (rc == GTA_ERR_UNSUPPORTED)
+    set_error("gta_gemm_f32_zbf16: shape k=%d f=%d ldx=%lld ldz=%lld (or a missing workspace) is outside the tcgen05 kernel's "
+              "rules; the bf16 storage mode has no FFMA fallback", k, f, (long long)ldx, (long long)ldz);
+  return rc;
 }
 
 }  // extern "C"

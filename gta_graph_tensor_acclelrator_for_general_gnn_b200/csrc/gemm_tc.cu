@@ -17,6 +17,7 @@
 //               MMAs overlap tile t's epilogue), fp32 row stores, el/er dot products
 // Roofline: HBM-bound (X read once: 53 FLOP/B at Reddit shape against a ~170 FLOP/B TF32 ridge).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -29,7 +30,8 @@ constexpr int kTcMaxStages = 4;
 constexpr uint32_t kTcATileBytes = kTcBM * kTcBK * 4;   // 16 KB
 
 struct TcParams {
-  float* z;
+  float* z;          // fp32 rows, or bf16 rows when z_bf16 (ldz then counts bf16 elements)
+  int z_bf16;
   int64_t ldz;
   int64_t num_rows;
   int k_blocks;
@@ -250,12 +252,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
             : "r"(taddr + uint32_t(c0)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (live) {
+        if (live && !p.z_bf16) {
           float* zr = p.z + row * p.ldz + c0;
 #pragma unroll
           for (int v = 0; v < 4; ++v)
             *reinterpret_cast<float4*>(zr + 4 * v) = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+        } else if (live) {
+          // bf16 storage mode: the fp32 accumulator is rounded once, here (el/er below still use the fp32 values)
+          __nv_bfloat16* zr = reinterpret_cast<__nv_bfloat16*>(p.z) + row * p.ldz + c0;
+          uint32_t packed[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(r[2 * v]), __uint_as_float(r[2 * v + 1]));
+            packed[v] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          *reinterpret_cast<uint4*>(zr) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *reinterpret_cast<uint4*>(zr + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
         if (HMAX > 0) {
 #pragma unroll
@@ -373,10 +386,10 @@ size_t gemm_tc_workspace(int k, int f) {
 
 int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, float* z, int64_t ldz, int64_t num_rows,
                    int k, int f, const float* al, const float* ar, int heads, float* el, float* er, int64_t lder,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                   void* workspace, size_t workspace_bytes, cudaStream_t st, int z_bf16) {
   const bool want_attn = (el && al) || (er && ar);
   if (f % 16 != 0 || f < 16 || f > 256) return GTA_ERR_UNSUPPORTED;
-  if (ldx % 4 != 0 || ldz % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(z) & 15))
+  if (ldx % 4 != 0 || ldz % (z_bf16 ? 8 : 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(z) & 15))
     return GTA_ERR_UNSUPPORTED;
   if (want_attn && (heads < 1 || heads > 16)) return GTA_ERR_UNSUPPORTED;
   if (num_rows >= (int64_t(1) << 31) - kTcBM) return GTA_ERR_UNSUPPORTED;
@@ -399,7 +412,7 @@ int gemm_tc_launch(const float* x, int64_t ldx, const float* w, int64_t ldw, flo
   if (rc != GTA_OK) return rc;
 
   TcParams p{};
-  p.z = z; p.ldz = ldz; p.num_rows = num_rows; p.k_blocks = kp / kTcBK; p.f = f;
+  p.z = z; p.z_bf16 = z_bf16; p.ldz = ldz; p.num_rows = num_rows; p.k_blocks = kp / kTcBK; p.f = f;
   p.heads = want_attn ? heads : 0;
   p.lder = lder;
   p.al = want_attn ? al : nullptr; p.ar = want_attn ? ar : nullptr;

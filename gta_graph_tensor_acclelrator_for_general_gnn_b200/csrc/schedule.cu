@@ -20,6 +20,13 @@ namespace gta {
 
 constexpr int kMaxColBlocks = 64;
 
+// upper source-id bound of every column block (block cb holds sources below end[cb] that are not in an
+// earlier block): uniform (cb + 1) * col_block, or the caller's cut points (an exchange walks its peers'
+// slots in a few groups of growing size)
+struct BlockEnds {
+  int64_t end[kMaxColBlocks];
+};
+
 // first position in indices[b,e) whose source id is >= bound
 __device__ __forceinline__ int64_t lower_bound_src(const int32_t* __restrict__ indices, int64_t b, int64_t e, int64_t bound) {
   while (b < e) {
@@ -33,7 +40,7 @@ __device__ __forceinline__ int32_t items_of(int64_t len, int32_t chunk) { return
 
 // counts[cb * rows + r] = items of (column block cb, row r); row_items[r] = total of the row
 __global__ void sched_count_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                   int64_t row_begin, int64_t rows, int32_t chunk, int64_t col_block, int32_t n_cb,
+                                   int64_t row_begin, int64_t rows, int32_t chunk, const BlockEnds ends, int32_t n_cb,
                                    int32_t* __restrict__ counts, int32_t* __restrict__ row_slots_in) {
   int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -46,7 +53,7 @@ __global__ void sched_count_kernel(const int64_t* __restrict__ indptr, const int
     } else {
       int64_t lo = b;
       for (int32_t cb = 0; cb < n_cb; ++cb) {
-        int64_t hi = (cb == n_cb - 1) ? e : lower_bound_src(indices, lo, e, int64_t(cb + 1) * col_block);
+        int64_t hi = (cb == n_cb - 1) ? e : lower_bound_src(indices, lo, e, ends.end[cb]);
         int32_t n = items_of(hi - lo, chunk);
         if (cb == 0 && b == e) n = 1;           // an empty row still writes its zero output
         counts[int64_t(cb) * rows + r] = n;
@@ -59,7 +66,7 @@ __global__ void sched_count_kernel(const int64_t* __restrict__ indptr, const int
 }
 
 __global__ void sched_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                  int64_t row_begin, int64_t rows, int32_t chunk, int64_t col_block, int32_t n_cb,
+                                  int64_t row_begin, int64_t rows, int32_t chunk, const BlockEnds ends, int32_t n_cb,
                                   const int32_t* __restrict__ item_off, const int32_t* __restrict__ row_slots,
                                   int4* __restrict__ items) {
   int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -71,7 +78,7 @@ __global__ void sched_fill_kernel(const int64_t* __restrict__ indptr, const int3
     int32_t slot = slot0;
     int64_t lo = b;
     for (int32_t cb = 0; cb < n_cb; ++cb) {
-      int64_t hi = (cb == n_cb - 1) ? e : lower_bound_src(indices, lo, e, int64_t(cb + 1) * col_block);
+      int64_t hi = (cb == n_cb - 1) ? e : lower_bound_src(indices, lo, e, ends.end[cb]);
       int32_t n = items_of(hi - lo, chunk);
       if (cb == 0 && b == e) n = 1;
       int32_t o = item_off[int64_t(cb) * rows + r];
@@ -119,23 +126,56 @@ int64_t gta_schedule_max_items(int64_t num_rows, int64_t num_edges, int32_t chun
   return num_rows * col_blocks_for(num_sources, col_block) + num_edges / chunk + 1;
 }
 
+// shared body: n_cb column blocks whose upper bounds are ends.end[0 .. n_cb-2] (the last block takes the rest)
+static int schedule_build_impl(const int64_t* indptr, const int32_t* indices, int64_t row_begin, int64_t row_end,
+                               int32_t chunk, const BlockEnds& ends, int32_t n_cb, int64_t ws_col_block,
+                               int64_t ws_sources, int32_t* items, int64_t items_capacity, int32_t* row_slots,
+                               int64_t* h_counts, int64_t* h_block_begin, void* workspace, size_t workspace_bytes,
+                               void* stream_);
+
 int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t row_begin, int64_t row_end,
                        int64_t num_sources, int32_t chunk, int64_t col_block, int32_t* items,
                        int64_t items_capacity, int32_t* row_slots, int64_t* h_counts, int64_t* h_block_begin,
                        void* workspace, size_t workspace_bytes, void* stream_) {
+  const int32_t n_cb = col_blocks_for(num_sources, col_block);
+  GTA_REQUIRE(n_cb <= kMaxColBlocks, "gta_schedule_build: %d column blocks exceed the limit of %d", n_cb, kMaxColBlocks);
+  BlockEnds ends{};
+  for (int32_t cb = 0; cb < n_cb; ++cb) ends.end[cb] = int64_t(cb + 1) * col_block;
+  return schedule_build_impl(indptr, indices, row_begin, row_end, chunk, ends, n_cb, col_block, num_sources, items,
+                             items_capacity, row_slots, h_counts, h_block_begin, workspace, workspace_bytes, stream_);
+}
+
+int gta_schedule_build_cuts(const int64_t* indptr, const int32_t* indices, int64_t row_begin, int64_t row_end,
+                            int32_t chunk, const int64_t* h_cuts, int32_t num_cuts, int32_t* items,
+                            int64_t items_capacity, int32_t* row_slots, int64_t* h_counts, int64_t* h_block_begin,
+                            void* workspace, size_t workspace_bytes, void* stream_) {
+  GTA_REQUIRE(num_cuts >= 0 && num_cuts < kMaxColBlocks && (num_cuts == 0 || h_cuts), "gta_schedule_build_cuts: %d cuts", num_cuts);
+  BlockEnds ends{};
+  for (int32_t c = 0; c < num_cuts; ++c) {
+    GTA_REQUIRE(h_cuts[c] > (c ? h_cuts[c - 1] : 0), "gta_schedule_build_cuts: cut points must be positive and ascending");
+    ends.end[c] = h_cuts[c];
+  }
+  // workspace as for num_cuts + 1 uniform blocks: gta_schedule_workspace(rows, num_cuts + 1, 1)
+  return schedule_build_impl(indptr, indices, row_begin, row_end, chunk, ends, num_cuts + 1, 1, num_cuts + 1, items,
+                             items_capacity, row_slots, h_counts, h_block_begin, workspace, workspace_bytes, stream_);
+}
+
+static int schedule_build_impl(const int64_t* indptr, const int32_t* indices, int64_t row_begin, int64_t row_end,
+                               int32_t chunk, const BlockEnds& ends, int32_t n_cb, int64_t ws_col_block,
+                               int64_t ws_sources, int32_t* items, int64_t items_capacity, int32_t* row_slots,
+                               int64_t* h_counts, int64_t* h_block_begin, void* workspace, size_t workspace_bytes,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GTA_REQUIRE(indptr && items && row_slots && h_counts && workspace, "gta_schedule_build: null pointer");
   GTA_REQUIRE(chunk >= 32, "gta_schedule_build: chunk must be >= 32");
   GTA_REQUIRE(row_end >= row_begin, "gta_schedule_build: negative row range");
-  const int32_t n_cb = col_blocks_for(num_sources, col_block);
-  GTA_REQUIRE(n_cb <= kMaxColBlocks, "gta_schedule_build: %d column blocks exceed the limit of %d", n_cb, kMaxColBlocks);
   GTA_REQUIRE(n_cb == 1 || indices, "gta_schedule_build: column blocking needs the CSR indices");
   const int64_t rows = row_end - row_begin;
   h_counts[0] = h_counts[1] = 0;
   if (h_block_begin)
     for (int32_t cb = 0; cb <= n_cb; ++cb) h_block_begin[cb] = 0;
   if (rows == 0) return GTA_OK;
-  const size_t need = gta_schedule_workspace(rows, num_sources, col_block);
+  const size_t need = gta_schedule_workspace(rows, ws_sources, ws_col_block);
   if (workspace_bytes < need) {
     set_error("gta_schedule_build: workspace %zu < required %zu", workspace_bytes, need);
     return GTA_ERR_WORKSPACE;
@@ -152,7 +192,7 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
   // both scans run one entry past the end so the last output is the total
   GTA_CUDA(cudaMemsetAsync(counts + (n - 1), 0, 4, stream));
   GTA_CUDA(cudaMemsetAsync(slots_in + rows, 0, 4, stream));
-  sched_count_kernel<<<sched_grid(rows), 256, 0, stream>>>(indptr, indices, row_begin, rows, chunk, col_block, n_cb,
+  sched_count_kernel<<<sched_grid(rows), 256, 0, stream>>>(indptr, indices, row_begin, rows, chunk, ends, n_cb,
                                                           counts, slots_in);
   GTA_CHECK_LAUNCH("sched_count_kernel");
   GTA_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, cub_bytes, counts, item_off, n, stream));
@@ -170,7 +210,7 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
     set_error("gta_schedule_build: %d items exceed capacity %lld", totals[0], (long long)items_capacity);
     return GTA_ERR_WORKSPACE;
   }
-  sched_fill_kernel<<<sched_grid(rows), 256, 0, stream>>>(indptr, indices, row_begin, rows, chunk, col_block, n_cb,
+  sched_fill_kernel<<<sched_grid(rows), 256, 0, stream>>>(indptr, indices, row_begin, rows, chunk, ends, n_cb,
                                                          item_off, row_slots, reinterpret_cast<int4*>(items));
   GTA_CHECK_LAUNCH("sched_fill_kernel");
   h_counts[0] = totals[0];

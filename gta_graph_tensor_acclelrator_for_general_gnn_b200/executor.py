@@ -168,8 +168,9 @@ class _Run:
         k = kernels
         if v.kind == "mm":
             x = k.to_table(self.force(v.args[0]))
-            v.tensor = k.gemm(x, v.weight)
-            self.kernel_log.append(("gta_gemm_f32", v.pos))
+            zt = self.o["feature_dtype"] if v.pos in self.o["gathered"] and v.pos not in self.o["wanted"] else torch.float32
+            v.tensor = k.gemm(x, v.weight, z_dtype=zt)
+            self.kernel_log.append(("gta_gemm_f32" if zt == torch.float32 else "gta_gemm_f32_zbf16", v.pos))
         elif v.kind == "edge_mm":
             self._guard(v.args[0].width, f"the input of edge COMP_MM op {v.pos}")
             self._guard(v.width, f"edge COMP_MM op {v.pos}")
@@ -364,7 +365,7 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
             network: str | None = None, is_reorder: bool = False, semantics: dict | None = None,
             fuse_across_blocks: bool = True, stabilize: bool = True, slope: float = kernels.LEAKY_SLOPE,
             max_edge_bytes: int = 8 << 30, outputs=None, source_table=None, return_log: bool = False,
-            check_shapes: bool = True, legacy_comp_types=None):
+            check_shapes: bool = True, legacy_comp_types=None, feature_dtype=torch.float32):
     """Run an ISA program functionally.
 
     program      : isa.Program, a path to ``Results/Insts/*.yaml`` or the raw list interpret() built
@@ -376,6 +377,9 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
     outputs      : op positions to return (default: ops with an empty output_list)
     legacy_comp_types : COMP_TYPE per op position for V1/V2-era op graphs that lack the field
                    (V2/simpletest.yaml: ``isa.LEGACY_SIMPLETEST_COMP_TYPES``)
+    feature_dtype : ``torch.bfloat16`` = bf16 STORAGE MODE: the output of a COMP_MM that is
+                   gathered over the edges (Z) is stored in bf16 and accumulated in fp32 by the fused aggregate
+                   kernels; tolerance rtol 2e-2, atol 1e-2 rowscale.  Single GPU, fused plans only.
     Returns {op position: tensor} (and the kernel log with ``return_log``).
     """
     if isinstance(op_info, (str, os.PathLike)):
@@ -429,8 +433,15 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
             if q != -1:
                 consumers[q] += 1
 
+    if feature_dtype not in (torch.float32, torch.bfloat16):
+        raise ExecutionError("feature_dtype is torch.float32 or torch.bfloat16")
+    if feature_dtype == torch.bfloat16 and source_table is not None:
+        raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute", "the bf16 storage mode is single-GPU for now")
+    # ops whose output is gathered over the edges (consumed by a scatter): the tables the storage mode applies to
+    gathered = {q for p in range(n_ops) if op_info[p]["TYPE"] == "scatter" for q in prods[p] if q != -1}
     opts = {"slope": float(slope), "stabilize": bool(stabilize), "max_edge_bytes": int(max_edge_bytes),
-            "source_table": source_table or (lambda t: t), "wanted": set(wanted)}
+            "source_table": source_table or (lambda t: t), "wanted": set(wanted), "feature_dtype": feature_dtype,
+            "gathered": gathered}
     run = _Run(graph, opts)
     env: dict[int, Value] = {}
 
@@ -538,8 +549,9 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                 if hasattr(ex, "local_views") and x.shape[0] == ex.part.rows:
                     # partitioned run: Z and er go straight into this rank's slot of the gathered table
                     views = ex.local_views(int(v.weight.shape[1]), env[kids[1]].width, x.device)
+                zt = opts["feature_dtype"] if p in opts["gathered"] and p not in opts["wanted"] else torch.float32
                 z, el, er = kernels.gemm(x, v.weight, env[kids[0]].weight, env[kids[1]].weight,
-                                         out=views[0] if views else None, er_out=views[1] if views else None)
+                                         out=views[0] if views else None, er_out=views[1] if views else None, z_dtype=zt)
                 v.tensor, env[kids[0]].tensor, env[kids[1]].tensor = z, el, er
                 run.kernel_log.append(("gta_gemm_f32+el/er", p))
 

@@ -41,6 +41,7 @@ class Schedule:
     row_begin: int
     row_end: int
     block_begin: list = None  # first item of every column block, then the item count (host ints)
+    col_cuts: tuple = ()      # explicit column-block cut points (source ids) instead of a uniform col_block
 
     @property
     def num_blocks(self) -> int:
@@ -84,12 +85,14 @@ class DeviceGraph:
     def num_rows(self) -> int:
         return int(self.indptr.shape[0]) - 1
 
-    def schedule(self, chunk: int = DEFAULT_CHUNK, col_block: int = 0) -> Schedule:  # noqa: D401
-        """Cached work list; ``col_block`` = source ids per column block (0 = no blocking)."""
-        key = (chunk, col_block)
+    def schedule(self, chunk: int = DEFAULT_CHUNK, col_block: int = 0, col_cuts=None) -> Schedule:  # noqa: D401
+        """Cached work list; ``col_block`` = source ids per column block (0 = no blocking), or ``col_cuts`` =
+        explicit ascending cut points (column block b = sources in [cuts[b-1], cuts[b]))."""
+        cuts = tuple(int(c) for c in col_cuts) if col_cuts else ()
+        key = (chunk, col_block, cuts)
         if key not in self.schedules:
             self.schedules[key] = build_schedule(self.indptr, self.indices, 0, self.num_rows, self.num_edges,
-                                                 self.num_sources or self.num_nodes, chunk, col_block)
+                                                 self.num_sources or self.num_nodes, chunk, col_block, cuts)
         return self.schedules[key]
 
     def schedule_for(self, row_bytes: int, chunk: int = DEFAULT_CHUNK) -> Schedule:
@@ -164,24 +167,34 @@ def csr_from_npz(file_path: str, drop_diagonal: bool = False):
 
 
 def build_schedule(indptr: torch.Tensor, indices: torch.Tensor, row_begin: int, row_end: int, num_edges: int,
-                   num_sources: int, chunk: int = DEFAULT_CHUNK, col_block: int = 0) -> Schedule:
+                   num_sources: int, chunk: int = DEFAULT_CHUNK, col_block: int = 0, col_cuts=()) -> Schedule:
     lib = _cabi.load()
     _require_cuda(indptr, indices)
     rows = row_end - row_begin
-    cap = int(lib.gta_schedule_max_items(rows, num_edges, chunk, num_sources, col_block))
+    if col_cuts:      # sized as num_cuts + 1 uniform blocks
+        ws_sources, ws_block = len(col_cuts) + 1, 1
+    else:
+        ws_sources, ws_block = num_sources, col_block
+    cap = int(lib.gta_schedule_max_items(rows, num_edges, chunk, ws_sources, ws_block))
     items = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=indptr.device)
     row_slots = torch.zeros(rows + 1, dtype=torch.int32, device=indptr.device)
-    ws_bytes = lib.gta_schedule_workspace(rows, num_sources, col_block)
+    ws_bytes = lib.gta_schedule_workspace(rows, ws_sources, ws_block)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=indptr.device)
     counts = (C.c_int64 * 2)()
-    n_cb = int(lib.gta_schedule_col_blocks(num_sources, col_block))
+    n_cb = int(lib.gta_schedule_col_blocks(ws_sources, ws_block))
     block_begin = (C.c_int64 * (n_cb + 1))()
-    _cabi.check(lib.gta_schedule_build(_cabi.ptr(indptr), _cabi.ptr(indices), row_begin, row_end, num_sources, chunk,
-                                       col_block, _cabi.ptr(items), cap, _cabi.ptr(row_slots), counts, block_begin,
-                                       _cabi.ptr(ws), ws_bytes, _stream()), "gta_schedule_build")
+    if col_cuts:
+        cuts = (C.c_int64 * len(col_cuts))(*col_cuts)
+        _cabi.check(lib.gta_schedule_build_cuts(_cabi.ptr(indptr), _cabi.ptr(indices), row_begin, row_end, chunk, cuts,
+                                                len(col_cuts), _cabi.ptr(items), cap, _cabi.ptr(row_slots), counts,
+                                                block_begin, _cabi.ptr(ws), ws_bytes, _stream()), "gta_schedule_build_cuts")
+    else:
+        _cabi.check(lib.gta_schedule_build(_cabi.ptr(indptr), _cabi.ptr(indices), row_begin, row_end, num_sources, chunk,
+                                           col_block, _cabi.ptr(items), cap, _cabi.ptr(row_slots), counts, block_begin,
+                                           _cabi.ptr(ws), ws_bytes, _stream()), "gta_schedule_build")
     n_items, n_slots = int(counts[0]), int(counts[1])
     return Schedule(items[:max(n_items, 1)], row_slots, n_items, n_slots, chunk, col_block, row_begin, row_end,
-                    [int(v) for v in block_begin])
+                    [int(v) for v in block_begin], tuple(col_cuts))
 
 
 # ---- tile tables: calculate_sparsity / cal_min_sparsity / gen_size -------------------------

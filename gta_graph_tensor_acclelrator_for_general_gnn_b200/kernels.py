@@ -41,22 +41,29 @@ def pad4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
-def alloc_table(rows: int, width: int, device, zero: bool = False) -> torch.Tensor:
-    """[rows, width] fp32 view of a buffer whose row pitch is padded to 16 bytes."""
-    ld = pad4(width)
-    buf = (torch.zeros if zero else torch.empty)((max(rows, 1), ld), dtype=torch.float32, device=device)
+def pad_row(n: int, dtype=torch.float32) -> int:
+    """Row pitch in elements: whole 16-byte pieces (4 fp32, 8 bf16)."""
+    per = 16 // torch.empty((), dtype=dtype).element_size()
+    return (n + per - 1) // per * per
+
+
+def alloc_table(rows: int, width: int, device, zero: bool = False, dtype=torch.float32) -> torch.Tensor:
+    """[rows, width] view of a buffer whose row pitch is padded to 16 bytes (fp32, or bf16 in the bf16 storage mode)."""
+    ld = pad_row(width, dtype)
+    buf = (torch.zeros if zero else torch.empty)((max(rows, 1), ld), dtype=dtype, device=device)
     return buf[:rows, :width]
 
 
 def to_table(x: torch.Tensor) -> torch.Tensor:
     """Return ``x`` if its layout is already legal, else a padded copy (pad columns zeroed)."""
-    if x.dtype != torch.float32:
-        raise TypeError("fp32 tables only")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("fp32 tables (or bf16 in the bf16 storage mode) only")
     if x.dim() == 1:
         x = x[:, None]
-    if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(0) >= x.shape[1]:
+    per = 16 // x.element_size()
+    if x.stride(1) == 1 and x.stride(0) % per == 0 and x.data_ptr() % 16 == 0 and x.stride(0) >= x.shape[1]:
         return x
-    t = alloc_table(x.shape[0], x.shape[1], x.device, zero=True)
+    t = alloc_table(x.shape[0], x.shape[1], x.device, zero=True, dtype=x.dtype)
     t.copy_(x)
     return t
 
@@ -115,10 +122,11 @@ def set_gemm_mode(mode: str) -> None:
 
 @_timed("gta_gemm_f32")
 def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: torch.Tensor | None = None,
-         out: torch.Tensor | None = None, er_out: torch.Tensor | None = None):
+         out: torch.Tensor | None = None, er_out: torch.Tensor | None = None, z_dtype=torch.float32):
     """COMP_MM applynode: ``Z = X.W`` and optionally the fused GAT ops 1/2 ``el = Z.Al``,
     ``er = Z.Ar``.  Returns ``Z`` or ``(Z, el, er)``.  ``out`` / ``er_out`` may be (strided) views of a
-    larger table, e.g. this rank's slot of the gathered ``[F | H]`` source table."""
+    larger table, e.g. this rank's slot of the gathered ``[F | H]`` source table.  ``z_dtype=torch.bfloat16``
+    (bf16 storage mode) rounds Z once in the epilogue; el / er come from the fp32 accumulators."""
     lib = _cabi.load()
     _require_cuda(x, w, al, ar)
     n, k = x.shape
@@ -126,7 +134,9 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
     if k != k2:
         raise ValueError(f"X is [{n},{k}] but W is [{k2},{f}]")
     w = w.contiguous()
-    z = out if out is not None else alloc_table(n, f, x.device)
+    z = out if out is not None else alloc_table(n, f, x.device, dtype=z_dtype)
+    if z.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("Z is fp32 or bf16")
     heads = 0
     el = er = None
     if al is not None or ar is not None:
@@ -141,11 +151,10 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
                 raise ValueError("er_out must be an [N, H] view with unit column stride")
     ws_bytes = int(lib.gta_gemm_workspace(k, f))
     ws = _gemm_ws.get((ws_bytes + 3) // 4, x.device)
-    _cabi.check(lib.gta_gemm_f32(_cabi.ptr(x), _ld(x), _cabi.ptr(w), f, _cabi.ptr(z), _ld(z), n, k, f,
-                                 _cabi.ptr(al), _cabi.ptr(ar), heads, _cabi.ptr(el), _cabi.ptr(er),
-                                 (int(er.stride(0)) if er is not None and n > 1 else heads),
-                                 _cabi.ptr(ws), ws_bytes, _stream()),
-                "gta_gemm_f32")
+    fn, name = (lib.gta_gemm_f32, "gta_gemm_f32") if z.dtype == torch.float32 else (lib.gta_gemm_f32_zbf16, "gta_gemm_f32_zbf16")
+    _cabi.check(fn(_cabi.ptr(x), _ld(x), _cabi.ptr(w), f, _cabi.ptr(z), _ld(z), n, k, f,
+                   _cabi.ptr(al), _cabi.ptr(ar), heads, _cabi.ptr(el), _cabi.ptr(er),
+                   (int(er.stride(0)) if er is not None and n > 1 else heads), _cabi.ptr(ws), ws_bytes, _stream()), name)
     if al is None and ar is None:
         return z
     return z, el, er
@@ -189,13 +198,16 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
     lib = _cabi.load()
     _require_cuda(x, w, rowden)
     if exchange is not None:
-        sched = g.schedule(col_block=exchange.slot_rows)
-    sched = sched or g.schedule_for(_ld(x) * 4)
+        sched = g.schedule(col_cuts=exchange.block_cuts)
+    sched = sched or g.schedule_for(_ld(x) * x.element_size())
     f = int(x.shape[1])
     rows = sched.row_end - sched.row_begin
     o = out if out is not None else alloc_table(rows, f, x.device)
-    if f % 4 and _ld(x) >= pad4(f) and _ld(o) >= pad4(f):
-        f = pad4(f)      # run over the pad columns too (independent columns, never read back)
+    per = 16 // x.element_size()
+    if f % per and _ld(x) >= pad_row(f, x.dtype) and _ld(o) >= pad_row(f, x.dtype):
+        f = pad_row(f, x.dtype)      # run over the pad columns too (independent columns, never read back)
+    fn, fname = (lib.gta_aggregate_f32, "gta_aggregate_f32") if x.dtype == torch.float32 else \
+        (lib.gta_aggregate_bf16, "gta_aggregate_bf16")
     wmode, wh = _cabi.W_NONE, 0
     if w is not None:
         if w.dim() == 1:
@@ -208,11 +220,11 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
     partials, chain = _chain_state(_agg_ws, sched.num_slots, f, f, x.device)
 
     def launch(first, count, phases):
-        _cabi.check(lib.gta_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
-                                          sched.num_slots, _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh,
-                                          _cabi.ptr(rowden), _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
-                                          partials, chain, exchange.byref() if exchange is not None else None,
-                                          phases, _stream()), "gta_aggregate_f32")
+        _cabi.check(fn(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
+                       sched.num_slots, _cabi.ptr(g.indices), wmode, _cabi.ptr(w), wh,
+                       _cabi.ptr(rowden), _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
+                       partials, chain, exchange.byref() if exchange is not None else None,
+                       phases, _stream()), fname)
     _launch_blocks(launch, sched, block_events)
     return o
 
@@ -274,8 +286,8 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
     lib = _cabi.load()
     _require_cuda(el, er, z)
     if exchange is not None:
-        sched = g.schedule(col_block=exchange.slot_rows)
-    sched = sched or g.schedule_for(_ld(z) * 4)
+        sched = g.schedule(col_cuts=exchange.block_cuts)
+    sched = sched or g.schedule_for(_ld(z) * z.element_size())
     f = int(z.shape[1])
     heads = int(el.shape[1])
     rows = sched.row_end - sched.row_begin
@@ -295,14 +307,16 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
     # (with an exchange the slot owners publish their er range and the kernel reads it from the signal block)
     stats = er_stats(er, col_block) if bounded and not want_stats and block_events is None and exchange is None else None
 
+    fn, fname = (lib.gta_gat_aggregate_f32, "gta_gat_aggregate_f32") if z.dtype == torch.float32 else \
+        (lib.gta_gat_aggregate_bf16, "gta_gat_aggregate_bf16")
+
     def launch(first, count, phases):
-        _cabi.check(lib.gta_gat_aggregate_f32(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
-                                              sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el),
-                                              _cabi.ptr(er), lder, heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o),
-                                              _ld(o), f, epilogue, _cabi.ptr(rowmax), _cabi.ptr(rowsum),
-                                              partials, chain, _cabi.ptr(stats), col_block,
-                                              exchange.byref() if exchange is not None else None, phases, _stream()),
-                    "gta_gat_aggregate_f32")
+        _cabi.check(fn(sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots),
+                       sched.num_slots, _cabi.ptr(g.indices), _cabi.ptr(el),
+                       _cabi.ptr(er), lder, heads, slope, _cabi.ptr(z), _ld(z), _cabi.ptr(o),
+                       _ld(o), f, epilogue, _cabi.ptr(rowmax), _cabi.ptr(rowsum),
+                       partials, chain, _cabi.ptr(stats), col_block,
+                       exchange.byref() if exchange is not None else None, phases, _stream()), fname)
     _launch_blocks(launch, sched, block_events)
     if want_stats:
         return o, rowmax, rowsum

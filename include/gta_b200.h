@@ -113,7 +113,8 @@ int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* 
  *   3. gta_aggregate_f32 / gta_gat_aggregate_f32 with a gta_exchange_t: the first `copy_ctas` CTAs of the
  *      launch pull slot 0 of peer (r + k) mod parts over NVLink into slot k of the local table, k = 1 ..
  *      parts-1 in ring order, waiting for that peer's step number first; the other CTAs walk the work list
- *      (column block = slot: own rows first) and wait at the first item of slot k until it has landed.
+ *      (column blocks = the own slot, then groups of peer slots in ring order) and wait, per item, until the
+ *      slot of the item's last source has landed (slots land in order).
  * No collective library call, no SMs taken by a communication kernel, no launch boundary between transfer
  * and compute.  Tables are double-buffered by step parity: a peer is at most one step ahead.
  * Every wait is bounded (a rank that never publishes makes the others trap, it does not hang the GPU).
@@ -173,6 +174,17 @@ int gta_schedule_build(const int64_t* indptr, const int32_t* indices, int64_t ro
                        int32_t* items, int64_t items_capacity, int32_t* row_slots,
                        int64_t* h_counts, int64_t* h_block_begin, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* The same with explicit column blocks: block b holds the sources in [h_cuts[b-1], h_cuts[b]) (h_cuts[-1] = 0,
+ * the last block everything from h_cuts[num_cuts-1] on); num_cuts + 1 blocks, host array of ascending positive
+ * source ids.  An exchange uses it to walk its own slot, then a few GROUPS of peer slots (dist.py): per-slot
+ * blocks cut an 8-GPU Reddit-shape row into 8 items of 61 edges and lost 47 % to per-item overhead.
+ * Workspace / capacity: gta_schedule_workspace(rows, num_cuts + 1, 1), gta_schedule_max_items(rows, E, chunk,
+ * num_cuts + 1, 1). */
+int gta_schedule_build_cuts(const int64_t* indptr, const int32_t* indices, int64_t row_begin,
+                            int64_t row_end, int32_t chunk, const int64_t* h_cuts, int32_t num_cuts,
+                            int32_t* items, int64_t items_capacity, int32_t* row_slots,
+                            int64_t* h_counts, int64_t* h_block_begin, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * COMP_MM (applynode)  --  interpreter.py:145-161 with Weight_Size; simulator.py:338-341.
@@ -189,6 +201,32 @@ int gta_gemm_f32(const float* x, int64_t ldx, const float* w, int64_t ldw,
                  float* z, int64_t ldz, int64_t num_rows, int32_t k, int32_t f,
                  const float* al, const float* ar, int32_t heads, float* el, float* er,
                  int64_t lder, void* workspace, size_t workspace_bytes, void* stream);
+/* bf16 STORAGE MODE (the reference's IR declares data_format FP16,
+ * template/IR_defination.yaml:10-27): the gathered table Z is stored in bf16, everything is accumulated in
+ * fp32.  Tolerance of the mode: rtol 2e-2, atol 1e-2 * rowscale.  gta_gemm_f32_zbf16 is gta_gemm_f32 with Z
+ * rounded to bf16 once, in the epilogue (z: bf16 rows, ldz in bf16 elements, a multiple of 8; el / er fp32 from
+ * the fp32 accumulators; tcgen05 kernel only).  gta_aggregate_bf16 / gta_gat_aggregate_bf16 are the
+ * aggregation entry points over such a table (x / z: bf16 rows, ldx / ldz in bf16 elements, f a multiple of
+ * 8, per-head width a multiple of 8; out, partials, weights, el, er stay fp32; head counts 1, 2, 4). */
+int gta_gemm_f32_zbf16(const float* x, int64_t ldx, const float* w, int64_t ldw,
+                       void* z, int64_t ldz, int64_t num_rows, int32_t k, int32_t f,
+                       const float* al, const float* ar, int32_t heads, float* el, float* er,
+                       int64_t lder, void* workspace, size_t workspace_bytes, void* stream);
+int gta_aggregate_bf16(const int32_t* items, int64_t num_items, const int32_t* row_slots,
+                       int64_t num_slots, const int32_t* indices,
+                       int32_t wmode, const float* w, int32_t wh, const float* rowden,
+                       const void* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
+                       int32_t epilogue, float* partials, int32_t* chain_state,
+                       const gta_exchange_t* exchange, int32_t phases, void* stream);
+int gta_gat_aggregate_bf16(const int32_t* items, int64_t num_items, const int32_t* row_slots,
+                           int64_t num_slots, const int32_t* indices,
+                           const float* el, const float* er, int64_t lder, int32_t heads, float slope,
+                           const void* z, int64_t ldz, float* out, int64_t ldo, int32_t f,
+                           int32_t epilogue, float* rowmax, float* rowsum,
+                           float* partials, int32_t* chain_state, const uint32_t* er_stats,
+                           int64_t col_block, const gta_exchange_t* exchange, int32_t phases,
+                           void* stream);
+
 /* kernel choice of gta_gemm_f32: 0 = auto (tcgen05 3xTF32 when the shape is eligible, else
  * FFMA), 1 = force the FFMA kernel, 2 = force tcgen05 (GTA_ERR_UNSUPPORTED if ineligible). */
 int gta_gemm_set_mode(int mode);
@@ -206,7 +244,8 @@ int gta_gemm_get_mode(void);
  * windows, W*num_slots int32 chain flags (cleared by GTA_PHASE_RESET) followed by W + GTA_MAX_RANKS int32
  * (item counters and slot-arrival counters, cleared by every MAIN launch) and is always required.
  * `exchange` (NULL: the source table is complete) makes the launch pull the peers' slots itself, see
- * gta_exchange_t; the work list must then have been built with col_block = exchange->slot_rows.
+ * gta_exchange_t; the work list's column blocks must then end on slot boundaries (multiples of
+ * exchange->slot_rows), the first block being slot 0 alone.
  * ------------------------------------------------------------------------------------ */
 int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
                       int64_t num_slots, const int32_t* indices,

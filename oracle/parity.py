@@ -54,15 +54,20 @@ def sub_csr(indptr: np.ndarray, indices: np.ndarray, rows: np.ndarray):
     return out_ptr, np.ascontiguousarray(indices[pos], dtype=np.int32)
 
 
+#: the bf16 storage mode's own tolerance: rtol 2e-2, atol 1e-2 * rowscale
+BF16 = (2e-2, 1e-2)
+
+
 def _report(y, y64, scale, rows, edges, rtol):
     y = np.asarray(y, dtype=np.float64)
-    bound = rtol * np.abs(y64) + rtol * scale + 1e-30
+    rtol, atol = rtol if isinstance(rtol, tuple) else (rtol, rtol)
+    bound = rtol * np.abs(y64) + atol * scale + 1e-30
     err = np.abs(y - y64)
     finite = bool(np.all(np.isfinite(y)))
     worst = float(np.max(err / bound)) if err.size else 0.0
     return {"rows": int(rows), "edges": int(edges), "max_err_over_tol": worst if finite else float("inf"),
             "max_abs_err": float(err.max()) if err.size else 0.0, "finite": finite,
-            "tolerance": f"|y-y64| <= {rtol:g}*|y64| + {rtol:g}*rowscale, rowscale = sum_k |coef_k|*(|X|.|W|)[src k]",
+            "tolerance": f"|y-y64| <= {rtol:g}*|y64| + {atol:g}*rowscale, rowscale = sum_k |coef_k|*(|X|.|W|)[src k]",
             "oracle": "oracle/gta_oracle.c fp64 (OpenMP), ascending-source reduction"}
 
 

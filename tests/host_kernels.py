@@ -65,7 +65,7 @@ def _leaky(x, slope):
     return torch.where(x > 0, x, x * slope)
 
 
-def gemm(x, w, al=None, ar=None, out=None, er_out=None):
+def gemm(x, w, al=None, ar=None, out=None, er_out=None, z_dtype=torch.float32):
     z = x @ w
     if out is not None:
         out.copy_(z)

@@ -183,3 +183,28 @@ def test_split_launch_crosses_chains():
     w = torch.rand(e, device="cuda")
     assert torch.equal(kernels.aggregate(full, z, w, sched=sched, block_events=[None] * 4),
                        kernels.aggregate(full, z, w, sched=sched))
+
+
+def test_schedule_cut_points_equal_uniform_blocks():
+    """gta_schedule_build_cuts with cut points at multiples of a block size is gta_schedule_build with that block
+    size; uneven cuts (an exchange's slot groups) keep every edge exactly once, in order, inside its block."""
+    import torch
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import dist as gdist, graph
+    n, e = 3000, 90000
+    g = synthetic.powerlaw_graph(n, e, seed=8, i0=3.0)
+    full = graph.csr_from_coo(g.dst, g.src, n)
+    a = full.schedule(col_block=800)
+    b = full.schedule(col_cuts=(800, 1600, 2400))
+    assert a.num_items == b.num_items and a.num_slots == b.num_slots and a.block_begin == b.block_begin
+    assert torch.equal(a.items[:a.num_items], b.items[:b.num_items]) and torch.equal(a.row_slots, b.row_slots)
+    cuts = (500, 2000)
+    c = full.schedule(col_cuts=cuts)
+    items = c.items[:c.num_items].cpu().numpy()
+    indices = full.indices.cpu().numpy()
+    assert items[:, 2].sum() == e and c.num_blocks == 3
+    bounds = (0,) + cuts + (n,)
+    for blk in range(3):
+        for it in items[c.block_begin[blk]:c.block_begin[blk + 1]]:
+            srcs = indices[it[1]:it[1] + it[2]]
+            assert srcs.size == 0 or (srcs[0] >= bounds[blk] and srcs[-1] < bounds[blk + 1])
+    assert gdist.slot_groups(8) == [[0], [1, 2, 3], [4, 5, 6, 7]] and gdist.slot_groups(2) == [[0], [1]]

@@ -39,7 +39,12 @@ def main():
     for case in args.cases:
         name, n, e, f, h = case.split(":")
         n, e, f, h = int(n), int(e), int(f), int(h)
-        dst, src = device_powerlaw(n, e)
+        if name.startswith("rmat"):      # rmat<scale>:0:0:F:H -- the bench's device RMAT generator
+            from gta_graph_tensor_acclelrator_for_general_gnn_b200 import synthetic
+            dst, src, n = synthetic.rmat_graph_device(int(name[4:]))
+            e = int(dst.shape[0])
+        else:
+            dst, src = device_powerlaw(n, e)
         g = graph.csr_from_coo(dst, src, n)
         del dst, src
         z = kernels.alloc_table(n, f, "cuda")
@@ -50,10 +55,13 @@ def main():
         for kind, ncb in [(k, c) for k in args.kinds for c in args.col_blocks]:
             sched = g.schedule(args.chunk, 0 if ncb <= 1 else -(-n // ncb))
             ev = [None] * sched.num_blocks if args.split_launch else None
-            # "gat": softmax shifted by the per-block bound (default); "gato": online softmax with a running maximum
-            fn = (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched, block_events=ev)) if kind == "gat" else \
-                 (lambda: kernels.gat_aggregate(g, el, er, z, sched=sched, block_events=ev, bounded=False)) if kind == "gato" else \
-                 (lambda: kernels.aggregate(g, z, w, sched=sched, block_events=ev))
+            # "gat": softmax shifted by the per-block bound (default); "gato": online softmax with a running maximum;
+            # a trailing "b": the table stored in bf16
+            zz = kernels.to_table(z.to(torch.bfloat16)) if kind.endswith("b") else z
+            base = kind[:-1] if kind.endswith("b") else kind
+            fn = (lambda: kernels.gat_aggregate(g, el, er, zz, sched=sched, block_events=ev)) if base == "gat" else \
+                 (lambda: kernels.gat_aggregate(g, el, er, zz, sched=sched, block_events=ev, bounded=False)) if base == "gato" else \
+                 (lambda: kernels.aggregate(g, zz, w, sched=sched, block_events=ev))
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
@@ -64,7 +72,7 @@ def main():
             t1.record()
             torch.cuda.synchronize()
             ms = t0.elapsed_time(t1) / args.iters
-            byt = e * (4 + f * 4 + (h * 4 if kind.startswith("gat") else 4)) + n * (f * 4 + 8)
+            byt = e * (4 + f * zz.element_size() + (h * 4 if kind.startswith("gat") else 4)) + n * (f * 4 + 8)
             print(f"{name:8s} {kind:5s} cb={ncb} chunk={args.chunk} N={n} E={e} F={f} H={h} items={sched.num_items} slots={sched.num_slots} "
                   f"{ms:8.3f} ms  {e / ms / 1e6:7.2f} GTEPS  {byt / ms / 1e6:8.1f} GB/s algorithmic", flush=True)
         del g, z, el, er, w
