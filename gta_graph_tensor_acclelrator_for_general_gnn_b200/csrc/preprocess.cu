@@ -21,12 +21,22 @@ static int bits_for(int64_t n) {
 
 // ---- COO -> CSR ------------------------------------------------------------------------
 
+// Ids outside the graph (dst not in [0, num_nodes), src < 0) would make unpack_rows_kernel write row pointers far
+// out of bounds: they are counted in *bad and their key is clamped to row 0, and gta_csr_build reports
+// GTA_ERR_INVALID instead of crashing on a damaged edge list.
 __global__ void pack_keys_kernel(const int32_t* __restrict__ dst, const int32_t* __restrict__ src,
-                                 int64_t n, uint64_t* __restrict__ keys, int64_t* __restrict__ vals) {
+                                 int64_t n, int64_t num_nodes, uint64_t* __restrict__ keys, int64_t* __restrict__ vals,
+                                 int32_t* __restrict__ bad) {
   int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (; i < n; i += stride) {
-    keys[i] = (uint64_t(uint32_t(dst[i])) << 32) | uint32_t(src[i]);
+    int32_t d = dst[i], c = src[i];
+    if (d < 0 || d >= num_nodes || c < 0) {
+      atomicAdd(bad, 1);
+      d = 0;
+      c = 0;
+    }
+    keys[i] = (uint64_t(uint32_t(d)) << 32) | uint32_t(c);
     vals[i] = i;
   }
 }
@@ -58,6 +68,7 @@ struct CsrWorkspace {
   int64_t* vals_out;
   void* cub_temp;
   size_t cub_bytes;
+  int32_t* bad;       // count of edges whose ids are outside the graph
   size_t total;
 };
 
@@ -75,6 +86,7 @@ static CsrWorkspace carve_csr(void* base, int64_t e, int64_t n) {
   w.vals_out = reinterpret_cast<int64_t*>(b + off); off += ebytes;
   w.cub_temp = b + off; off += align_up(cub_bytes, 256);
   w.cub_bytes = cub_bytes;
+  w.bad = reinterpret_cast<int32_t*>(b + off); off += 256;
   w.total = off;
   return w;
 }
@@ -198,7 +210,9 @@ int gta_csr_build(const int32_t* dst, const int32_t* src, int64_t num_edges, int
     return GTA_ERR_WORKSPACE;
   }
   if (num_edges > 0) {
-    pack_keys_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(dst, src, num_edges, w.keys_in, w.vals_in);
+    GTA_CUDA(cudaMemsetAsync(w.bad, 0, sizeof(int32_t), stream));
+    pack_keys_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(dst, src, num_edges, num_nodes, w.keys_in, w.vals_in,
+                                                                  w.bad);
     GTA_CHECK_LAUNCH("pack_keys_kernel");
     int64_t* vals_out = perm ? perm : w.vals_out;
     size_t cub_bytes = w.cub_bytes;
@@ -208,6 +222,13 @@ int gta_csr_build(const int32_t* dst, const int32_t* src, int64_t num_edges, int
   }
   unpack_rows_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(w.keys_out, num_edges, num_nodes, indices, indptr);
   GTA_CHECK_LAUNCH("unpack_rows_kernel");
+  if (num_edges > 0) {      // a set-up call: one small read-back so that a damaged edge list is an error, not a crash
+    int32_t bad = 0;
+    GTA_CUDA(cudaMemcpyAsync(&bad, w.bad, sizeof(bad), cudaMemcpyDeviceToHost, stream));
+    GTA_CUDA(cudaStreamSynchronize(stream));
+    GTA_REQUIRE(bad == 0, "gta_csr_build: %d edges name a destination outside [0, %lld) or a negative source", bad,
+                (long long)num_nodes);
+  }
   return GTA_OK;
 }
 

@@ -217,6 +217,7 @@ def calculate_sparsity(g: DeviceGraph, row: int, col: int = 1, tile_begin: int =
         raise NotImplementedError("the reference only ever calls col = 1 (code/preprocessing.py:86)")
     if row <= 0:
         raise ValueError("row tile size must be positive")
+    _require_simple(g)
     lib = _cabi.load()
     tiles = -(-g.num_nodes // row)
     tile_end = tiles if tile_end is None else tile_end
@@ -226,9 +227,28 @@ def calculate_sparsity(g: DeviceGraph, row: int, col: int = 1, tile_begin: int =
     return out
 
 
+def _require_simple(g: DeviceGraph) -> None:
+    """The tile tables count non-zeros of a dense adjacency upstream (np.count_nonzero, preprocessing.py:37): a
+    repeated (dst, src) pair is ONE entry there but one count per edge here.  Checked once per graph."""
+    if "simple" not in g.schedules:
+        e = g.num_edges
+        dup = False
+        if e > 1:
+            same_src = g.indices[1:] == g.indices[:-1]
+            row_start = torch.zeros(e, dtype=torch.bool, device=g.indices.device)
+            starts = g.indptr[1:-1]
+            row_start[starts[starts < e]] = True
+            dup = bool((same_src & ~row_start[1:]).any().item())
+        g.schedules["simple"] = not dup
+    if not g.schedules["simple"]:
+        raise ValueError("the graph has duplicate (dst, src) edges: the reference's tile tables are defined on a dense "
+                         "adjacency, where a repeated pair is one non-zero; deduplicate the edge list first")
+
+
 def cal_min_sparsity(g: DeviceGraph, tile_size: int, workspace_bytes: int = 256 << 20) -> int:
     """Maximum tile nnz for one tile size (code/preprocessing.py:53-63; the reference's name
     says min, its code takes the max), streamed in bounded batches of row tiles."""
+    _require_simple(g)
     lib = _cabi.load()
     need = 256 + 4 * g.num_nodes
     ws_bytes = max(need, min(workspace_bytes, 256 + 4 * g.num_nodes * (-(-g.num_nodes // tile_size))))

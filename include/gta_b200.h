@@ -70,14 +70,19 @@ void gta_launch_count_reset(void);
  * ------------------------------------------------------------------------------------ */
 
 /* COO -> CSR by (dst, src) ascending, stable.  indptr[N+1] int64, indices[E] int32,
- * perm[E] int64 (may be NULL): perm[k] = input position of CSR edge k. */
+ * perm[E] int64 (may be NULL): perm[k] = input position of CSR edge k.  Duplicate edges are kept (a
+ * multigraph).  Synchronises the stream once: an edge whose destination is outside [0, N) or whose source
+ * is negative makes the call return GTA_ERR_INVALID (the outputs are then undefined). */
 size_t gta_csr_build_workspace(int64_t num_edges, int64_t num_nodes);
 int gta_csr_build(const int32_t* dst, const int32_t* src, int64_t num_edges, int64_t num_nodes,
                   int64_t* indptr, int32_t* indices, int64_t* perm,
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* calculate_sparsity(row = tile_rows, col = 1) (code/preprocessing.py:12-40): counts[tr*N + c]
- * = number of edges with dst in row tile tr and src == c, self loops excluded.
+ * = number of edges with dst in row tile tr and src == c, self loops excluded.  Precondition: no
+ * duplicate (dst, src) pairs -- the reference counts non-zeros of a dense adjacency
+ * (np.count_nonzero, preprocessing.py:37), where a repeated pair is one entry; a multigraph would be
+ * counted per edge here.  graph.calculate_sparsity checks it.
  * Only row tiles [tile_begin, tile_end) are produced (counts has (tile_end-tile_begin)*N
  * entries), so Reddit-size tables can be streamed. */
 int gta_tile_nnz(const int64_t* indptr, const int32_t* indices, int64_t num_nodes,

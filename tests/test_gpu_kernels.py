@@ -47,6 +47,24 @@ def test_csr_build_bit_exact(T, name, n, e, seed, i0):
     assert np.array_equal(dg.perm.cpu().numpy(), perm)
 
 
+def test_damaged_edge_lists_are_refused_not_crashed_on(T):
+    """A destination outside [0, N) or a negative id (unpack_rows_kernel used to write row pointers out of
+    bounds for them) comes back as GTA_ERR_INVALID; duplicate edges make the tile tables refuse (the reference's
+    tables count non-zeros of a dense adjacency)."""
+    dst = np.array([0, 1, 2, 3], dtype=np.int32)
+    src = np.array([1, 2, 3, 0], dtype=np.int32)
+    for bad_dst, bad_src in (([0, 1, 2, 6], src), ([0, -1, 2, 3], src), (dst, [1, 2, -3, 0]), ([0, 1, 2, 2**31 - 1], src)):
+        with pytest.raises(T.cabi.GtaError, match="outside"):
+            T.graph.csr_from_coo(np.asarray(bad_dst, dtype=np.int32), np.asarray(bad_src, dtype=np.int32), 6)
+    ok = T.graph.csr_from_coo(dst, src, 6)          # the library is still usable afterwards
+    assert ok.num_edges == 4
+    multi = T.graph.csr_from_coo(np.array([0, 0, 1], dtype=np.int32), np.array([2, 2, 0], dtype=np.int32), 3)
+    with pytest.raises(ValueError, match="duplicate"):
+        T.graph.calculate_sparsity(multi, 2)
+    with pytest.raises(ValueError, match="duplicate"):
+        T.graph.cal_min_sparsity(multi, 2)
+
+
 def test_csr_build_duplicates_and_empty(T):
     # duplicate edges keep input order (stable); isolated nodes give empty rows
     dst = np.array([3, 1, 3, 3, 0, 1], dtype=np.int32)
