@@ -199,7 +199,7 @@ struct WorkList {
   float* partials;
   int32_t* chain_flags;      // [windows][num_slots]
   int32_t* work_counter;     // [windows], zeroed before every launch
-  int32_t take;              // items a warp takes per grab (a multiple of its 32/LANES groups)
+  int32_t take;              // 1: warps take items from the counter; 0: static striding (long lists of tiny items)
   uint64_t pol_stream;
   uint64_t pol_keep;
 };
@@ -211,14 +211,44 @@ struct WorkList {
 // trip hides under the gathers.  Items are still started in work-list order, which keeps the CTAs on one
 // column block at a time and keeps the chain invariant: whoever holds a predecessor slot started earlier
 // and is running, so a wait can never deadlock, whatever the grid size.
-// Long lists of tiny items (RMAT: 16.8 M items of 2 edges per rank) would hammer the counter: a grab then
-// takes several consecutive group-steps at once (wl.take, chosen by the host so that every warp still makes
-// a few dozen grabs).  A warp works through its batch in ascending order, so the smallest unfinished item of
-// the whole list is always somebody's CURRENT item and the chain argument above still holds.
-__device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane, int32_t take) {
-  int32_t v = 0;
-  if (lane == 0) v = atomicAdd(counter, take);
-  return v;
+// Long lists of tiny items (RMAT: millions of items of a few edges) do not need the balancing and would
+// hammer the counter: with wl.take == 0 the warps stride through the list statically (warp w takes groups
+// w, w + W, ...; the host then sizes the grid so that all W warps are resident, which the chain argument now
+// needs).  Consecutive items still go to different warps -- taking several consecutive items per grab
+// instead was measured 3x slower on RMAT-20: a hub row's chain of 1024-edge items then serialises, every
+// warp sitting on its predecessor's publish while that warp works through the rest of its batch.
+struct ItemCursor {
+  int32_t first;       // first item of the warp's current group-step
+  int32_t pending;     // dynamic: the next grab (lane 0), in flight
+  int32_t stride;      // static: items between two steps of this warp
+};
+template <int LANES>
+__device__ __forceinline__ ItemCursor cursor_begin(const WorkList& wl, const Exchange& ex, int32_t* counter, int lane) {
+  constexpr int kGroups = 32 / LANES;
+  ItemCursor c;
+  if (wl.take > 0) {
+    int32_t v = 0;
+    if (lane == 0) v = atomicAdd(counter, kGroups);
+    c.first = __shfl_sync(0xffffffffu, v, 0);
+    c.pending = 0;
+    if (lane == 0) c.pending = atomicAdd(counter, kGroups);
+    c.stride = 0;
+  } else {
+    const int copy = ex.world > 1 ? ex.copy_ctas : 0;
+    c.first = ((int32_t(blockIdx.x) - copy) * kAggWarps + int32_t(threadIdx.x >> 5)) * kGroups;
+    c.stride = (int32_t(gridDim.x) - copy) * kAggWarps * kGroups;
+    c.pending = 0;
+  }
+  return c;
+}
+template <int LANES>
+__device__ __forceinline__ void cursor_next(ItemCursor& c, const WorkList& wl, int32_t* counter, int lane) {
+  if (wl.take > 0) {
+    c.first = __shfl_sync(0xffffffffu, c.pending, 0);
+    if (c.first < wl.num_items && lane == 0) c.pending = atomicAdd(counter, 32 / LANES);
+  } else {
+    c.first = (c.first > 0x7fffffff - c.stride) ? 0x7fffffff : c.first + c.stride;
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -226,38 +256,65 @@ __device__ __forceinline__ int32_t grab_items(int32_t* counter, int lane, int32_
 // the reference's IR declares data_format FP16, template/IR_defination.yaml:10-27).  A lane always moves
 // 16-byte pieces of a row: 4 fp32 or 8 bf16 features.
 // ----------------------------------------------------------------------------------------
-template <typename T> struct Elem;
-template <> struct Elem<float> {
-  static constexpr int kPer = 4;
-  static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
+// A PIECE is what one lane moves of one gathered row: its storage type, how many features, how many bytes.
+//   F32x4   4 fp32 in 16 bytes            (512-byte rows at 32 lanes: the fp32 mode)
+//   Bf16x8  8 bf16 in 16 bytes            (rows wider than 128 features)
+//   Bf16x4  4 bf16 in  8 bytes            (rows of up to 128 features keep all 32 lanes on ONE item: the per-batch
+//                                          work -- staging, softmax -- is then spread over 32 edges, not 16; measured
+//                                          on the Reddit shape: Bf16x8 at 16 lanes per item was no faster than fp32)
+struct F32x4 {
+  using T = float;
+  using Raw = uint4;
+  static constexpr int kPer = 4, kBytes = 16;
+  static __device__ __forceinline__ Raw load(const char* p, uint64_t pol) {
+    Raw v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+  }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[4]) {
     f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
   }
 };
-template <> struct Elem<__nv_bfloat16> {
-  static constexpr int kPer = 8;
-  static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {      // bf16 -> fp32 is a shift
+struct Bf16x8 {
+  using T = __nv_bfloat16;
+  using Raw = uint4;
+  static constexpr int kPer = 8, kBytes = 16;
+  static __device__ __forceinline__ Raw load(const char* p, uint64_t pol) { return F32x4::load(p, pol); }
+  static __device__ __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[8]) {      // bf16 -> fp32 is a shift
     f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
     f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
     f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
     f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
   }
 };
-// 16 bytes of a gathered row (cache policy: see ld_row_f32x4)
-__device__ __forceinline__ uint4 ld_row_raw(const char* p, uint64_t pol_keep) {
-  uint4 v;
-  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol_keep));
-  return v;
-}
+struct Bf16x4 {
+  using T = __nv_bfloat16;
+  using Raw = uint2;
+  static constexpr int kPer = 4, kBytes = 8;
+  static __device__ __forceinline__ Raw load(const char* p, uint64_t pol) {
+    Raw v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+                 : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+  }
+  static __device__ __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&f)[4]) {
+    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
 __device__ __forceinline__ const char* row_addr(const char* base, uint32_t id, uint32_t row_bytes) {
   return base + uint64_t(id) * row_bytes;
 }
-template <typename T>
-__device__ __forceinline__ void fma_row(float (&acc)[Elem<T>::kPer], float w, const uint4& raw) {
-  float f[Elem<T>::kPer];
-  Elem<T>::unpack(raw, f);
+template <typename P>
+__device__ __forceinline__ void fma_row(float (&acc)[P::kPer], float w, const typename P::Raw& raw) {
+  float f[P::kPer];
+  P::unpack(raw, f);
 #pragma unroll
-  for (int c = 0; c < Elem<T>::kPer; ++c) acc[c] = fmaf(w, f[c], acc[c]);
+  for (int c = 0; c < P::kPer; ++c) acc[c] = fmaf(w, f[c], acc[c]);
 }
 // kPer consecutive fp32 of an output / partial row
 template <int KP>
@@ -294,13 +351,14 @@ constexpr int kAggUnroll = GTA_AGG_UNROLL;
 constexpr int kGatUnroll = GTA_GAT_UNROLL;
 constexpr int kLlhUnroll = GTA_LLH_UNROLL;
 
-template <typename T, int V, int LANES, int WKIND, bool DIV>
-__global__ void __launch_bounds__(kAggThreads, (V == 1 && sizeof(T) == 4) ? GTA_AGG_MINBLOCKS : 8)
+template <typename P, int V, int LANES, int WKIND, bool DIV>
+__global__ void __launch_bounds__(kAggThreads, (V == 1 && P::kPer == 4) ? GTA_AGG_MINBLOCKS : 8)
 aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ w, int wh,
-                 const float* __restrict__ rowden, const T* __restrict__ x, const uint32_t row_bytes,
+                 const float* __restrict__ rowden, const typename P::T* __restrict__ x, const uint32_t row_bytes,
                  float* __restrict__ out, int64_t ldo, int f, int epilogue) {
   static_assert(V == 1 || (LANES == 32 && WKIND != 2), "two pieces per lane: full warps, no per-head weights");
-  constexpr int KP = Elem<T>::kPer;
+  using Raw = typename P::Raw;
+  constexpr int KP = P::kPer;
   constexpr int kWindow = LANES * KP * V;          // features one pass of a group covers
   constexpr int kEdges = kAggUnroll;      // edges whose loads (V each) are in flight together
   __shared__ __align__(16) uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
@@ -322,11 +380,9 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
   for (int v = 0; v < V; ++v) on[v] = fo + v * LANES * KP < f;
   const char* xf = reinterpret_cast<const char*>(x + (on[0] ? fo : 0));
 
-  int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
-  int32_t batch_end = first + wl.take;
-  int32_t pending = grab_items(counter, lane, wl.take);      // the next batch, in flight under this one
-  while (first < wl.num_items) {
-    const int64_t group = int64_t(first) + lane / LANES;
+  ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
+  while (cur.first < wl.num_items) {
+    const int64_t group = int64_t(cur.first) + lane / LANES;
     const bool have = group < wl.num_items;
     const bool active = have && on[0];
     const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
@@ -377,7 +433,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
 #pragma unroll 1
           for (int j = 0; j < LANES; j += kEdges) {
             uint4 ed[kEdges / 2];
-            uint4 raw[kEdges][V];
+            Raw raw[kEdges][V];
 #pragma unroll
             for (int u = 0; u < kEdges / 2; ++u)
               if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
@@ -386,7 +442,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
               if (j + u < LANES) {
                 const char* rp = row_addr(xf, (u & 1) ? ed[u / 2].z : ed[u / 2].x, row_bytes);
 #pragma unroll
-                for (int v = 0; v < V; ++v) raw[u][v] = ld_row_raw(rp + v * LANES * 16, pol_keep);
+                for (int v = 0; v < V; ++v) raw[u][v] = P::load(rp + v * LANES * P::kBytes, pol_keep);
               }
             }
 #pragma unroll
@@ -398,7 +454,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
                   if (DIV) ws = ws / den;
                 }
 #pragma unroll
-                for (int v = 0; v < V; ++v) fma_row<T>(acc[v], ws, raw[u][v]);
+                for (int v = 0; v < V; ++v) fma_row<P>(acc[v], ws, raw[u][v]);
               }
             }
           }
@@ -406,7 +462,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
       } else {
         const int nmax = (LANES == 32) ? n : LANES;
         for (int j = 0; j < nmax; j += kEdges) {
-          uint4 raw[kEdges][V];
+          Raw raw[kEdges][V];
           float wv[kEdges];
 #pragma unroll
           for (int u = 0; u < kEdges; ++u) {
@@ -417,8 +473,8 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
               const char* rp = row_addr(xf, ed.x, row_bytes);
 #pragma unroll
               for (int v = 0; v < V; ++v) {
-                raw[u][v] = make_uint4(0u, 0u, 0u, 0u);
-                if (ok && on[v]) raw[u][v] = ld_row_raw(rp + v * LANES * 16, pol_keep);
+                raw[u][v] = P::zero();
+                if (ok && on[v]) raw[u][v] = P::load(rp + v * LANES * P::kBytes, pol_keep);
               }
               if (WKIND == 2) {
                 ws = 0.f;
@@ -434,7 +490,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
           for (int u = 0; u < kEdges; ++u)
             if (j + u < LANES)
 #pragma unroll
-              for (int v = 0; v < V; ++v) fma_row<T>(acc[v], wv[u], raw[u][v]);
+              for (int v = 0; v < V; ++v) fma_row<P>(acc[v], wv[u], raw[u][v]);
         }
       }
       __syncwarp();
@@ -472,12 +528,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
           if (have && on[v]) st_out<KP>(out + int64_t(it.x) * ldo + fo + v * LANES * KP, acc[v], 1.f, epilogue);
       }
     });
-    first += 32 / LANES;
-    if (first >= batch_end) {
-      first = __shfl_sync(0xffffffffu, pending, 0);
-      batch_end = first + wl.take;
-      if (first < wl.num_items) pending = grab_items(counter, lane, wl.take);
-    }
+    cursor_next<LANES>(cur, wl, counter, lane);
   }
 }
 
@@ -543,10 +594,10 @@ __device__ __forceinline__ bool block_bound(const uint32_t* er_stats, int64_t cb
   return seen && (hi - lo) < kBoundRange;      // NaN compares false
 }
 
-template <typename T, int LANES, int H>
+template <typename P, int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? GTA_GAT_MINBLOCKS : (GTA_GAT_MINBLOCKS + 1) / 2)
 gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ el, const float* __restrict__ er,
-                     int64_t lder, float slope, const T* __restrict__ z, const uint32_t row_bytes,
+                     int64_t lder, float slope, const typename P::T* __restrict__ z, const uint32_t row_bytes,
                      float* __restrict__ out, int64_t ldo, int f, int epilogue, float* __restrict__ rowmax,
                      float* __restrict__ rowsum, const uint32_t* er_stats, int stats_pitch, int64_t col_block) {
   // per warp: H rows of 32 staged edges, entry = {source id, softmax numerator}.  Row pitch kS = 34
@@ -555,7 +606,8 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   // hits 4 disjoint bank quads (68 words = 4 mod 32).  Round 1 staged [edge][head]: 4-way conflicts on
   // every store, 27 % of the L1/TEX data-pipe wavefronts of the kernel.
   constexpr int kS = 34;
-  constexpr int KP = Elem<T>::kPer;
+  using Raw = typename P::Raw;
+  constexpr int KP = P::kPer;
   constexpr int kWindow = LANES * KP;
   __shared__ __align__(16) uint2 s_e[kAggWarps][H * kS];
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
@@ -577,11 +629,9 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   const int stats = f + int(blockIdx.y) * gat_stats_stride(H);
   const char* zf = reinterpret_cast<const char*>(z + (fo < f ? fo : 0));
 
-  int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
-  int32_t batch_end = first + wl.take;
-  int32_t pending = grab_items(counter, lane, wl.take);      // the next batch, in flight under this one
-  while (first < wl.num_items) {
-    const int64_t group = int64_t(first) + lane / LANES;
+  ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
+  while (cur.first < wl.num_items) {
+    const int64_t group = int64_t(cur.first) + lane / LANES;
     const bool have = group < wl.num_items;
     const bool active = have && fo < f;
     const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
@@ -676,22 +726,22 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
 #pragma unroll 1
           for (int j = 0; j < LANES; j += kGatUnroll) {
             uint4 ed[kGatUnroll / 2];
-            uint4 raw[kGatUnroll];
+            Raw raw[kGatUnroll];
 #pragma unroll
             for (int u = 0; u < kGatUnroll / 2; ++u)
               if (j + 2 * u < LANES) ed[u] = mine2[(j >> 1) + u];
 #pragma unroll
             for (int u = 0; u < kGatUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
-                raw[2 * u] = ld_row_raw(row_addr(zf, ed[u].x, row_bytes), pol_keep);
-                raw[2 * u + 1] = ld_row_raw(row_addr(zf, ed[u].z, row_bytes), pol_keep);
+                raw[2 * u] = P::load(row_addr(zf, ed[u].x, row_bytes), pol_keep);
+                raw[2 * u + 1] = P::load(row_addr(zf, ed[u].z, row_bytes), pol_keep);
               }
             }
 #pragma unroll
             for (int u = 0; u < kGatUnroll / 2; ++u) {
               if (j + 2 * u < LANES) {
-                fma_row<T>(acc, __uint_as_float(ed[u].y), raw[2 * u]);
-                fma_row<T>(acc, __uint_as_float(ed[u].w), raw[2 * u + 1]);
+                fma_row<P>(acc, __uint_as_float(ed[u].y), raw[2 * u]);
+                fma_row<P>(acc, __uint_as_float(ed[u].w), raw[2 * u + 1]);
               }
             }
           }
@@ -699,20 +749,20 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
       } else {
         const int nmax = (LANES == 32) ? n : LANES;
         for (int j = 0; j < nmax; j += kGatUnroll) {
-          uint4 raw[kGatUnroll];
+          Raw raw[kGatUnroll];
           float pv[kGatUnroll];
 #pragma unroll
           for (int u = 0; u < kGatUnroll; ++u) {
             if (j + u < LANES) {
               const uint2 ed = mine[j + u];
               pv[u] = __uint_as_float(ed.y);
-              raw[u] = make_uint4(0u, 0u, 0u, 0u);
-              if (active && (j + u) < n) raw[u] = ld_row_raw(row_addr(zf, ed.x, row_bytes), pol_keep);
+              raw[u] = P::zero();
+              if (active && (j + u) < n) raw[u] = P::load(row_addr(zf, ed.x, row_bytes), pol_keep);
             }
           }
 #pragma unroll
           for (int u = 0; u < kGatUnroll; ++u)
-            if (j + u < LANES) fma_row<T>(acc, pv[u], raw[u]);
+            if (j + u < LANES) fma_row<P>(acc, pv[u], raw[u]);
         }
       }
       __syncwarp();
@@ -772,12 +822,7 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
         }
       }
     });
-    first += 32 / LANES;
-    if (first >= batch_end) {
-      first = __shfl_sync(0xffffffffu, pending, 0);
-      batch_end = first + wl.take;
-      if (first < wl.num_items) pending = grab_items(counter, lane, wl.take);
-    }
+    cursor_next<LANES>(cur, wl, counter, lane);
   }
 }
 
@@ -818,11 +863,9 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
   const int pstride = gat_partial_stride(f, heads);
   const int stats = f + int(blockIdx.y) * gat_stats_stride(heads);
 
-  int32_t first = __shfl_sync(0xffffffffu, grab_items(counter, lane, wl.take), 0);
-  int32_t batch_end = first + wl.take;
-  int32_t pending = grab_items(counter, lane, wl.take);      // the next batch, in flight under this one
-  while (first < wl.num_items) {
-    const int64_t group = int64_t(first) + lane / LANES;
+  ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
+  while (cur.first < wl.num_items) {
+    const int64_t group = int64_t(cur.first) + lane / LANES;
     const bool have = group < wl.num_items;
     const bool active = have && fo < f;
     const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
@@ -954,12 +997,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
         }
       }
     });
-    first += 32 / LANES;
-    if (first >= batch_end) {
-      first = __shfl_sync(0xffffffffu, pending, 0);
-      batch_end = first + wl.take;
-      if (first < wl.num_items) pending = grab_items(counter, lane, wl.take);
-    }
+    cursor_next<LANES>(cur, wl, counter, lane);
   }
 }
 
@@ -1085,23 +1123,22 @@ static int resident_ctas(K kernel) {
   return cached;
 }
 
-// items per grab: a multiple of the warp's 32/lanes groups, at most 8 group-steps, and small enough that every
-// resident warp still makes about 32 grabs (load balance at the end of the list)
+// dynamic item fetch, or static striding once every resident warp would get 64 or more group-steps anyway
 template <typename K>
 static int32_t take_for(K kernel, int64_t num_items, int lanes) {
   const int groups = 32 / lanes;
   const int64_t warps = int64_t(resident_ctas(kernel)) * (kAggThreads / 32);
-  int64_t steps = num_items / (warps * groups * 32);
-  steps = steps < 1 ? 1 : (steps > 8 ? 8 : steps);
-  return int32_t(steps * groups);
+  return num_items / (warps * groups) >= 64 ? 0 : 1;
 }
 
 template <typename K>
 static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f, const Exchange& ex) {
   const int64_t need = (num_items * lanes + kAggThreads - 1) / kAggThreads;
-  const int64_t cap = resident_ctas(kernel);
-  // the copy CTAs of an exchange come first in the grid, so they are resident before any CTA can wait on them
+  int64_t cap = resident_ctas(kernel);
+  // the copy CTAs of an exchange come first in the grid, so they are resident before any CTA can wait on them;
+  // with static striding every work CTA must be resident too (a chain may wait on any of them)
   const int64_t copy = ex.world > 1 ? ex.copy_ctas : 0;
+  if (take_for(kernel, num_items, lanes) == 0 && cap > copy + 1) cap -= copy;
   return dim3((unsigned)((need < cap ? need : cap) + copy), (unsigned)((f + 127) / 128));
 }
 
@@ -1111,15 +1148,15 @@ static WorkList with_take(WorkList wl, int32_t take) {
 }
 
 // gta_exchange_t (host) -> Exchange (kernel parameter); arrived[] lives behind the item counters
-static int make_exchange(const char* who, const gta_exchange_t* h, int32_t* arrived, int64_t ld_elems, Exchange* ex) {
+static int make_exchange(const char* who, const gta_exchange_t* h, int32_t* arrived, int64_t pitch_bytes, Exchange* ex) {
   memset(ex, 0, sizeof(*ex));
   if (h == nullptr || h->world <= 1) return GTA_OK;
   GTA_REQUIRE(h->world <= GTA_MAX_RANKS && h->rank >= 0 && h->rank < h->world && h->step >= 1,
               "%s: exchange world %d rank %d step %d", who, h->world, h->rank, h->step);
   GTA_REQUIRE(h->table && h->signals && h->slot_rows > 0, "%s: exchange table / signals / slot_rows missing", who);
-  GTA_REQUIRE(h->row_bytes == ld_elems * 4 && h->row_bytes % 16 == 0,
+  GTA_REQUIRE(h->row_bytes == pitch_bytes && h->row_bytes % 16 == 0,
               "%s: exchange row_bytes %lld does not match the table's row pitch %lld", who, (long long)h->row_bytes,
-              (long long)(ld_elems * 4));
+              (long long)pitch_bytes);
   GTA_REQUIRE((h->slot_rows * h->row_bytes) % 128 == 0,
               "%s: a slot (%lld rows of %lld bytes) must be a whole number of 128-byte lines", who,
               (long long)h->slot_rows, (long long)h->row_bytes);
@@ -1141,14 +1178,15 @@ static int make_exchange(const char* who, const gta_exchange_t* h, int32_t* arri
   return GTA_OK;
 }
 
-template <typename T, int V, int LANES>
+template <typename P, int V, int LANES>
 static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkList& wl, const Exchange& ex,
-                               const float* w, int wh, const float* rowden, const T* x, int64_t ldx, float* out,
-                               int64_t ldo, int f, int epi) {
-  constexpr int kWin = LANES * Elem<T>::kPer * V;
+                               const float* w, int wh, const float* rowden, const typename P::T* x, int64_t ldx,
+                               float* out, int64_t ldo, int f, int epi) {
+  using T = typename P::T;
+  constexpr int kWin = LANES * P::kPer * V;
 #define GTA_AGG(K, D)                                                                                               \
   do {                                                                                                              \
-    auto kern = aggregate_kernel<T, V, LANES, K, D>;                                                                \
+    auto kern = aggregate_kernel<P, V, LANES, K, D>;                                                                \
     dim3 grid = persistent_grid(kern, wl.num_items, LANES, 1, ex);                                                  \
     grid.y = (unsigned)((f + kWin - 1) / kWin);                                                                     \
     kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl.num_items, LANES)), ex, w, wh, rowden, x,    \
@@ -1164,18 +1202,19 @@ static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkL
 #undef GTA_AGG
 }
 
-template <typename T, int H>
+template <typename P, int H>
 static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const Exchange& ex, const float* el,
-                        const float* er, int64_t lder, float slope, const T* z, int64_t ldz, float* out, int64_t ldo,
+                        const float* er, int64_t lder, float slope, const typename P::T* z, int64_t ldz, float* out, int64_t ldo,
                         int f, int epi, float* rowmax, float* rowsum, const uint32_t* er_stats, int stats_pitch,
                         int64_t col_block) {
 #define GTA_GAT(L)                                                                                                  \
   do {                                                                                                              \
-    auto kern = gat_aggregate_kernel<T, L, H>;                                                                      \
+    auto kern = gat_aggregate_kernel<P, L, H>;                                                                      \
     dim3 grid = persistent_grid(kern, wl.num_items, L, 1, ex);                                                      \
-    grid.y = (unsigned)((f + L * Elem<T>::kPer - 1) / (L * Elem<T>::kPer));                                         \
+    grid.y = (unsigned)((f + L * P::kPer - 1) / (L * P::kPer));                                                     \
     kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl.num_items, L)), ex, el, er, lder, slope, z,  \
-                                       uint32_t(ldz * sizeof(T)), out, ldo, f, epi, rowmax, rowsum, er_stats,       \
+                                       uint32_t(ldz * sizeof(typename P::T)), out, ldo, f, epi, rowmax, rowsum,     \
+                                       er_stats,                                                                    \
                                        stats_pitch, col_block);                                                     \
   } while (0)
   switch (lanes) {
@@ -1216,22 +1255,46 @@ static int prepare_worklist(const char* who, WorkList& wl, int32_t* chain_state,
 }
 
 // ---- the two aggregation entry points, for either storage type of the gathered table ---------------
+template <typename P>
+static int aggregate_run(const char* who, int wkind, bool div, cudaStream_t st, const WorkList& wl, const Exchange& ex,
+                         const float* w, int wh, const float* rowden, const typename P::T* x, int64_t ldx, float* out,
+                         int64_t ldo, int f, int epilogue) {
+  constexpr int KP = P::kPer;
+  GTA_REQUIRE(f % KP == 0, "%s: f=%d must be a multiple of %d (pad the table)", who, f, KP);
+  if (wkind == 2 && (f / wh) % KP != 0) {
+    set_error("%s: per-head width f/wh=%d is not a multiple of %d", who, f / wh, KP);
+    return GTA_ERR_UNSUPPORTED;
+  }
+  // rows wider than one 32-lane pass of single pieces: two pieces per lane (one walk of the work list, not two)
+  if (f > 32 * KP && wkind != 2) {
+    dispatch_aggregate<P, 2, 32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue);
+  } else {
+    switch (lanes_for(f, KP)) {
+      case 4: dispatch_aggregate<P, 1, 4>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+      case 8: dispatch_aggregate<P, 1, 8>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+      case 16: dispatch_aggregate<P, 1, 16>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+      default: dispatch_aggregate<P, 1, 32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
+    }
+  }
+  return GTA_OK;
+}
+
 template <typename T>
 static int aggregate_impl(const char* who, const int32_t* items_, int64_t num_items, const int32_t* row_slots,
                           int64_t num_slots, const int32_t* indices, int32_t wmode, const float* w, int32_t wh,
                           const float* rowden, const T* x, int64_t ldx, float* out, int64_t ldo, int32_t f,
                           int32_t epilogue, float* partials, int32_t* chain_state, const gta_exchange_t* exchange,
                           int32_t phases, void* stream_) {
-  constexpr int KP = Elem<T>::kPer;
+  constexpr int kRow = 16 / int(sizeof(T));          // elements per 16 bytes: the row pitch granule
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(f > 0 && f % KP == 0, "%s: f=%d must be a positive multiple of %d (pad the table)", who, f, KP);
+  GTA_REQUIRE(f > 0 && f % 4 == 0, "%s: f=%d must be a positive multiple of 4 (pad the table)", who, f);
   GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "%s: bad item count", who);
   WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
   int rc = prepare_worklist(who, wl, chain_state, f, phases, st);
   if (rc != GTA_OK) return rc;
   if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && x && out, "%s: null pointer", who);
-  GTA_REQUIRE(ldx % KP == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f && ldx * int64_t(sizeof(T)) < (int64_t(1) << 32),
+  GTA_REQUIRE(ldx % kRow == 0 && ldo % 4 == 0 && ldx >= f && ldo >= f && ldx * int64_t(sizeof(T)) < (int64_t(1) << 32),
               "%s: leading dimensions must be whole 16-byte pieces, >= f, and a row below 4 GiB", who);
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "%s: tables must be 16-byte aligned", who);
   GTA_REQUIRE(wmode >= GTA_W_NONE && wmode <= GTA_W_EDGE_DIV, "%s: bad wmode %d", who, wmode);
@@ -1241,28 +1304,44 @@ static int aggregate_impl(const char* who, const int32_t* items_, int64_t num_it
     GTA_REQUIRE(w && wh >= 1 && f % wh == 0, "%s: weight width %d must divide f=%d", who, wh, f);
     GTA_REQUIRE(!div || rowden, "%s: rowden required for GTA_W_EDGE_DIV", who);
     wkind = wh == 1 ? 1 : 2;
-    if (wkind == 2 && (f / wh) % KP != 0) {
-      set_error("%s: per-head width f/wh=%d is not a multiple of %d", who, f / wh, KP);
-      return GTA_ERR_UNSUPPORTED;
-    }
   }
   Exchange ex;
   rc = make_exchange(who, exchange, wl.work_counter + (f + 127) / 128, ldx * int64_t(sizeof(T)), &ex);
   if (rc != GTA_OK) return rc;
   GTA_REQUIRE(ex.world <= 1 || ex.table == reinterpret_cast<const char*>(x), "%s: x is not the exchange table", who);
-  // rows wider than one 32-lane pass of single pieces: two pieces per lane (one walk of the work list, not two)
-  if (f > 32 * KP && wkind != 2) {
-    dispatch_aggregate<T, 2, 32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue);
+  if constexpr (sizeof(T) == 4) {
+    rc = aggregate_run<F32x4>(who, wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue);
+  } else if (f <= 128) {
+    rc = aggregate_run<Bf16x4>(who, wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue);
   } else {
-    switch (lanes_for(f, KP)) {
-      case 4: dispatch_aggregate<T, 1, 4>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-      case 8: dispatch_aggregate<T, 1, 8>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-      case 16: dispatch_aggregate<T, 1, 16>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-      default: dispatch_aggregate<T, 1, 32>(wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue); break;
-    }
+    rc = aggregate_run<Bf16x8>(who, wkind, div, st, wl, ex, w, wh, rowden, x, ldx, out, ldo, f, epilogue);
   }
+  if (rc != GTA_OK) return rc;
   GTA_CHECK_LAUNCH("aggregate_kernel");
   return GTA_OK;
+}
+
+template <typename P>
+static int gat_run(const char* who, int heads, cudaStream_t st, const WorkList& wl, const Exchange& ex, const float* el,
+                   const float* er, int64_t lder, float slope, const typename P::T* z, int64_t ldz, float* out, int64_t ldo,
+                   int f, int epilogue, float* rowmax, float* rowsum, const uint32_t* er_stats, int stats_pitch,
+                   int64_t col_block) {
+  constexpr int KP = P::kPer;
+  if (f % KP != 0 || (f / heads) % KP != 0) {
+    set_error("%s: per-head width f/heads=%d is not a multiple of %d", who, f / heads, KP);
+    return GTA_ERR_UNSUPPORTED;
+  }
+  const int lanes = lanes_for(f, KP);
+  int rc = GTA_ERR_UNSUPPORTED;
+#define GTA_GAT_H(HH) rc = dispatch_gat<P, HH>(lanes, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
+  switch (heads) {
+    case 1: GTA_GAT_H(1); break;
+    case 2: GTA_GAT_H(2); break;
+    default: GTA_GAT_H(4); break;
+  }
+#undef GTA_GAT_H
+  if (rc != GTA_OK) set_error("%s: no kernel for heads=%d, f=%d", who, heads, f);
+  return rc;
 }
 
 template <typename T>
@@ -1272,16 +1351,16 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
                               int32_t epilogue, float* rowmax, float* rowsum, float* partials, int32_t* chain_state,
                               const uint32_t* er_stats, int64_t col_block, const gta_exchange_t* exchange,
                               int32_t phases, void* stream_) {
-  constexpr int KP = Elem<T>::kPer;
+  constexpr int kRow = 16 / int(sizeof(T));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GTA_REQUIRE(f > 0 && f % KP == 0, "%s: f=%d must be a positive multiple of %d", who, f, KP);
+  GTA_REQUIRE(f > 0 && f % 4 == 0, "%s: f=%d must be a positive multiple of 4", who, f);
   GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "%s: bad item count", who);
   WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
   int rc = prepare_worklist(who, wl, chain_state, f, phases, st);
   if (rc != GTA_OK) return rc;
   if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
   GTA_REQUIRE(items_ && indices && el && er && z && out, "%s: null pointer", who);
-  GTA_REQUIRE(ldz % KP == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f && ldz * int64_t(sizeof(T)) < (int64_t(1) << 32),
+  GTA_REQUIRE(ldz % kRow == 0 && ldo % 4 == 0 && ldz >= f && ldo >= f && ldz * int64_t(sizeof(T)) < (int64_t(1) << 32),
               "%s: leading dimensions must be whole 16-byte pieces, >= f, and a row below 4 GiB", who);
   GTA_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(er) & 15) == 0 && (reinterpret_cast<uintptr_t>(el) & 15) == 0,
@@ -1289,10 +1368,6 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
   GTA_REQUIRE(heads >= 1 && f % heads == 0, "%s: heads=%d must divide f=%d", who, heads, f);
   GTA_REQUIRE(lder >= heads && (heads % 4 != 0 || lder % 4 == 0) && (heads % 2 != 0 || lder % 2 == 0),
               "%s: er row stride %lld breaks the vector alignment of %d heads", who, (long long)lder, heads);
-  if ((f / heads) % KP != 0) {
-    set_error("%s: per-head width f/heads=%d is not a multiple of %d", who, f / heads, KP);
-    return GTA_ERR_UNSUPPORTED;
-  }
   Exchange ex;
   rc = make_exchange(who, exchange, wl.work_counter + (f + 127) / 128, ldz * int64_t(sizeof(T)), &ex);
   if (rc != GTA_OK) return rc;
@@ -1307,24 +1382,27 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
   }
   // the bound path does not track the true row maximum: callers that want it back run the online softmax
   if (rowmax != nullptr) er_stats = nullptr;
-  const int lanes = lanes_for(f, KP);
   // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
   // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint; fp32 tables only)
   const bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
   if (staged) {
-    rc = GTA_ERR_UNSUPPORTED;
-#define GTA_GAT_H(HH) rc = dispatch_gat<T, HH>(lanes, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
-    switch (heads) {
-      case 1: GTA_GAT_H(1); break;
-      case 2: GTA_GAT_H(2); break;
-      default: GTA_GAT_H(4); break;
+    if constexpr (sizeof(T) == 4) {
+      rc = gat_run<F32x4>(who, heads, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum,
+                          er_stats, stats_pitch, col_block);
+    } else if (f <= 128) {
+      rc = gat_run<Bf16x4>(who, heads, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum,
+                           er_stats, stats_pitch, col_block);
+    } else {
+      rc = gat_run<Bf16x8>(who, heads, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum,
+                           er_stats, stats_pitch, col_block);
     }
-#undef GTA_GAT_H
-    if (rc != GTA_OK) {
-      set_error("%s: no kernel for heads=%d, f=%d", who, heads, f);
-      return rc;
-    }
+    if (rc != GTA_OK) return rc;
   } else if constexpr (sizeof(T) == 4) {
+    if ((f / heads) % 4 != 0) {
+      set_error("%s: per-head width f/heads=%d is not a multiple of 4", who, f / heads);
+      return GTA_ERR_UNSUPPORTED;
+    }
+    const int lanes = lanes_for(f, 4);
 #define GTA_LLH(L)                                                                                                  \
   gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f, ex), kAggThreads, 0, \
                                 st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl.num_items, L)), ex, el,   \
