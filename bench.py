@@ -27,6 +27,9 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
+#: second layer of the two-layer workloads: (op graph, ISA program, output width)
+SECOND_LAYER = {"flickr-gcn2": ("opgraph/GCN-flickr-layer2-trans.yaml", "isa/GCN-flickr-layer2-trans__0_1-2-3.yaml", 64)}
+
 WORKLOADS = {
     # name: (shape, network, layer, reorder, opgraph yaml, isa yaml, heads)
     "reddit-gat": ("reddit", "GAT", 1, False, "opgraph/GAT-reddit-restamped-h4.yaml",
@@ -39,6 +42,9 @@ WORKLOADS = {
                    "isa/GCN-flickr-layer1-trans__0_1-2-3.yaml", 0),
     "reddit-gcn": ("reddit", "GCN", 1, True, "opgraph/GCN-reddit-layer1-trans.yaml",
                    "isa/GCN-reddit-layer1-trans__0_1-2-3.yaml", 0),
+    # BASELINE config 3: the 2-layer Flickr GCN (500 -> 128 -> 64), layer 1's (sharded) device output is layer 2's input
+    "flickr-gcn2": ("flickr", "GCN", 1, True, "opgraph/GCN-flickr-layer1-trans.yaml",
+                    "isa/GCN-flickr-layer1-trans__0_1-2-3.yaml", 0),
     # the Reddit shape with the heavier-tailed degree sequence (synthetic.HEAVY_TAIL: max degree 47x the mean)
     "reddit-heavy-gat": ("reddit-heavy", "GAT", 1, False, "opgraph/GAT-reddit-restamped-h4.yaml",
                          "isa/GAT-reddit-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13.yaml", 4),
@@ -257,7 +263,8 @@ def workload_name(args, wl):
         kind = "Chung-Lu P(rank)~(rank+600)^-0.9 (max degree ~47x mean, median ~0.41x)"
     else:
         kind = "Chung-Lu P(rank)~(rank+100)^-0.5 (max degree ~25x mean, median ~0.72x: milder than real Reddit, see DESIGN.md)"
-    return (f"{network} layer{layer} ({'trans' if reorder else 'original'}) on {shape}-shape synthetic graph "
+    two = " + layer2 (128 -> 64) chained on the device" if args.workload in SECOND_LAYER else ""
+    return (f"{network} layer{layer}{two} ({'trans' if reorder else 'original'}) on {shape}-shape synthetic graph "
             f"N={n} E={e} Fin={fin} F={f_out_of(shape)}{h} fp32, {kind}, program {os.path.basename(isa_rel)}")
 
 
@@ -384,6 +391,9 @@ def main():
     big = shape.startswith("rmat") and n > (1 << 21)      # too big for host-side inputs and a whole-output oracle
     op_info = load_yaml(op_rel)
     program = isa.Program.from_records(load_yaml(isa_rel))
+    second = SECOND_LAYER.get(args.workload)
+    if second is not None:
+        op_info2, program2, f_out2 = load_yaml(second[0]), isa.Program.from_records(load_yaml(second[1])), second[2]
 
     # ---- inputs (synthetic, deterministic) ---------------------------------------------------
     t_setup = time.perf_counter()
@@ -453,6 +463,9 @@ def main():
         weights = {0: w_d, 1: al_d, 2: ar_d} if network == "GAT" else {0: w_d}
     final_op = len(op_info) - 1
     edge_inputs = {2: edge_w} if network == "GCN" else None
+    if second is not None:
+        w2_h = synthetic.glorot(np.random.default_rng(11), f_out, f_out2)
+        weights2 = {0: torch.from_numpy(w2_h).to(dev)}
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
@@ -460,10 +473,17 @@ def main():
     sz = 2 if args.dtype == "bf16" else 4
 
     def step(x_dev):
-        return executor.execute(program, op_info, g, {0: x_dev}, weights, edge_inputs, network=network,
+        y1 = executor.execute(program, op_info, g, {0: x_dev}, weights, edge_inputs, network=network,
+                              is_reorder=reorder, fuse_across_blocks=not args.no_fuse, source_table=exchange,
+                              check_shapes=(world == 1 and not shape.startswith("rmat")),
+                              feature_dtype=feature_dtype)[final_op]
+        if second is None:
+            return y1
+        # layer 2 on layer 1's output: the rows this rank owns are the rows it just computed -- no host round trip,
+        # no re-partition; only the layer's own source exchange moves data between the GPUs
+        return executor.execute(program2, op_info2, g, {0: y1}, weights2, edge_inputs, network=network,
                                 is_reorder=reorder, fuse_across_blocks=not args.no_fuse, source_table=exchange,
-                                check_shapes=(world == 1 and not shape.startswith("rmat")),
-                                feature_dtype=feature_dtype)[final_op]
+                                check_shapes=(world == 1), feature_dtype=feature_dtype)[len(op_info2) - 1]
 
     def barrier():
         if world > 1:
@@ -515,7 +535,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    value = e / (ms_per_step * 1e-3) / 1e9
+    layers = 2 if second is not None else 1
+    value = layers * e / (ms_per_step * 1e-3) / 1e9          # GTEPS per layer: every layer walks all E edges
 
     # per-kernel durations: the same K steps issued eagerly with CUDA events around every kernel
     kernels.EVENT_LOG = []
@@ -541,7 +562,8 @@ def main():
             t_pin = pipeline.pinned_table(r1 - r0, fin)
             t_pin.copy_(x_pin)
             xs_pin.append(t_pin)
-        ys_pin = [torch.empty((r1 - r0, f_out), dtype=torch.float32).pin_memory() for _ in range(2)]
+        ys_pin = [torch.empty((r1 - r0, f_out2 if second is not None else f_out), dtype=torch.float32).pin_memory()
+                  for _ in range(2)]
 
         def e2e_run(pipe, steps):
             barrier()
@@ -580,7 +602,7 @@ def main():
         if world > 1:
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
         h2d_ms = float(tc.item())
-        e2e = {"value": e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
+        e2e = {"value": layers * e / (e2e_ms * 1e-3) / 1e9, "unit": "GTEPS", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "serial_ms_per_step": e2e_serial_ms,
                "h2d_alone_ms": h2d_ms, "h2d_alone_gbs_per_rank": h2d / (h2d_ms * 1e-3) / 1e9,
                "note": "per rank and per step: features X (pinned host) -> device, execute(), result -> pinned "
@@ -635,7 +657,18 @@ def main():
             z64, zabs, _, _ = P.host_tables(x_h, w_h)
             deg_l = np.diff(indptr_l)
             pos = np.repeat(indptr_l[rows_sel] - ip_s[:-1], deg_l[rows_sel]) + np.arange(int(ip_s[-1]), dtype=np.int64)
-            parity = P.check_gcn(y_h, ip_s, ix_s, edge_w.cpu().numpy().reshape(-1)[pos], z64, zabs, rtol=tol)
+            ew_rows = edge_w.cpu().numpy().reshape(-1)[pos]
+            if second is not None:
+                # whole chain in fp64: layer 1 over the WHOLE graph (layer 2 gathers from every node), its error scale
+                # carried into layer 2 (3 x: layer 1's output error <= 2e-5 scale, plus layer 2's own product)
+                from oracle import gta_oracle as O
+                coo_h = graph_of(shape)
+                ip_f, ix_f, _ = O.csr_build(coo_h.dst, coo_h.src, n)
+                ew_f = synthetic.gcn_edge_norm(ip_f, ix_f).astype(np.float64)
+                y1 = c_oracle.spmm(ip_f, ix_f, ew_f, z64, dtype=np.float64)
+                s1 = c_oracle.spmm(ip_f, ix_f, ew_f, zabs, dtype=np.float64)
+                z64, zabs = y1 @ w2_h.astype(np.float64), 3.0 * s1 @ np.abs(w2_h).astype(np.float64)
+            parity = P.check_gcn(y_h, ip_s, ix_s, ew_rows, z64, zabs, rtol=tol)
         parity.update(bitwise_rerun=bitwise, rows_of=int(r1 - r0), edges_of=int(indptr_l[-1]),
                       checked="rank 0's destination rows [%d,%d)%s" % (r0, r1, "" if rows_sel.shape[0] == r1 - r0 else
                                                                       " (512 highest-degree rows + every k-th row)"),
@@ -643,9 +676,11 @@ def main():
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     dom = "gta_gat_aggregate_f32" if network == "GAT" else "gta_aggregate_f32"
-    dom_ms = float(np.mean(per_kernel[dom])) if dom in per_kernel else None
+    dom_ms = float(np.mean(per_kernel[dom][0::layers])) if dom in per_kernel else None      # (layer 1's launch)
     _, dom_bytes = algorithmic_bytes(network, r1 - r0, e_local, fin, f_out, max(heads, 1), sz=sz)
     layer_bytes, _ = algorithmic_bytes(network, n, e, fin, f_out, max(heads, 1), sz=sz)
+    if second is not None:
+        layer_bytes += algorithmic_bytes(network, n, e, f_out, f_out2, 1, sz=sz)[0]
     peak, peak_src = measured_peak()
     traffic, traffic_src = measured_traffic(args.workload, dom, world)
     roofline = None

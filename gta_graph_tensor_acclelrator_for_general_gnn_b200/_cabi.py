@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libgta_b200" + ("_" + _TAG if _TAG else "") + ".
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = 0, 1, 2, 3, 4
 EPI_NONE, EPI_ELU, EPI_RELU = 0, 1, 2
 W_NONE, W_EDGE, W_EDGE_DIV = 0, 1, 2
-PHASE_MAIN, PHASE_RESET, PHASE_ALL = 1, 2, 3
+PHASE_MAIN, PHASE_RESET, PHASE_ALL, PHASE_STATIC = 1, 2, 3, 4
 OPND_EDGE, OPND_DST, OPND_SRC = 0, 1, 2
 BIN_ADD, BIN_MUL, BIN_DIV = 0, 1, 2
 UN_EXP_LEAKY_RELU, UN_ELU, UN_RELU, UN_COPY = 0, 1, 2, 3

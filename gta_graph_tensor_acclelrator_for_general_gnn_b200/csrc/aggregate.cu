@@ -1123,22 +1123,24 @@ static int resident_ctas(K kernel) {
   return cached;
 }
 
-// dynamic item fetch, or static striding once every resident warp would get 64 or more group-steps anyway
+// dynamic item fetch (take = 1) unless the caller asked for static striding (GTA_PHASE_STATIC: long lists of
+// tiny items) and the list is long enough for every resident warp to get a few dozen group-steps
 template <typename K>
-static int32_t take_for(K kernel, int64_t num_items, int lanes) {
+static int32_t take_for(K kernel, const WorkList& wl, int lanes) {
   const int groups = 32 / lanes;
   const int64_t warps = int64_t(resident_ctas(kernel)) * (kAggThreads / 32);
-  return num_items / (warps * groups) >= 64 ? 0 : 1;
+  return (wl.take == 0 && wl.num_items / (warps * groups) >= 32) ? 0 : 1;      // wl.take == 0: the caller's hint
 }
 
 template <typename K>
-static dim3 persistent_grid(K kernel, int64_t num_items, int lanes, int f, const Exchange& ex) {
+static dim3 persistent_grid(K kernel, const WorkList& wl, int lanes, int f, const Exchange& ex) {
+  const int64_t num_items = wl.num_items;
   const int64_t need = (num_items * lanes + kAggThreads - 1) / kAggThreads;
   int64_t cap = resident_ctas(kernel);
   // the copy CTAs of an exchange come first in the grid, so they are resident before any CTA can wait on them;
   // with static striding every work CTA must be resident too (a chain may wait on any of them)
   const int64_t copy = ex.world > 1 ? ex.copy_ctas : 0;
-  if (take_for(kernel, num_items, lanes) == 0 && cap > copy + 1) cap -= copy;
+  if (take_for(kernel, wl, lanes) == 0 && cap > copy + 1) cap -= copy;
   return dim3((unsigned)((need < cap ? need : cap) + copy), (unsigned)((f + 127) / 128));
 }
 
@@ -1161,7 +1163,7 @@ static int make_exchange(const char* who, const gta_exchange_t* h, int32_t* arri
               "%s: a slot (%lld rows of %lld bytes) must be a whole number of 128-byte lines", who,
               (long long)h->slot_rows, (long long)h->row_bytes);
   ex->world = h->world;
-  ex->copy_ctas = h->copy_ctas > 0 ? h->copy_ctas : 64;
+  ex->copy_ctas = h->copy_ctas > 0 ? h->copy_ctas : 96;
   ex->step = h->step;
   ex->row_bytes = uint32_t(h->row_bytes);
   ex->slot_rows = h->slot_rows;
@@ -1187,9 +1189,9 @@ static void dispatch_aggregate(int wkind, bool div, cudaStream_t st, const WorkL
 #define GTA_AGG(K, D)                                                                                               \
   do {                                                                                                              \
     auto kern = aggregate_kernel<P, V, LANES, K, D>;                                                                \
-    dim3 grid = persistent_grid(kern, wl.num_items, LANES, 1, ex);                                                  \
+    dim3 grid = persistent_grid(kern, wl, LANES, 1, ex);                                                  \
     grid.y = (unsigned)((f + kWin - 1) / kWin);                                                                     \
-    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl.num_items, LANES)), ex, w, wh, rowden, x,    \
+    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl, LANES)), ex, w, wh, rowden, x,    \
                                        uint32_t(ldx * sizeof(T)), out, ldo, f, epi);                                \
   } while (0)
   if (wkind == 0) GTA_AGG(0, false);
@@ -1210,9 +1212,9 @@ static int dispatch_gat(int lanes, cudaStream_t st, const WorkList& wl, const Ex
 #define GTA_GAT(L)                                                                                                  \
   do {                                                                                                              \
     auto kern = gat_aggregate_kernel<P, L, H>;                                                                      \
-    dim3 grid = persistent_grid(kern, wl.num_items, L, 1, ex);                                                      \
+    dim3 grid = persistent_grid(kern, wl, L, 1, ex);                                                      \
     grid.y = (unsigned)((f + L * P::kPer - 1) / (L * P::kPer));                                                     \
-    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl.num_items, L)), ex, el, er, lder, slope, z,  \
+    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl, L)), ex, el, er, lder, slope, z,  \
                                        uint32_t(ldz * sizeof(typename P::T)), out, ldo, f, epi, rowmax, rowsum,     \
                                        er_stats,                                                                    \
                                        stats_pitch, col_block);                                                     \
@@ -1242,6 +1244,7 @@ static int prepare_worklist(const char* who, WorkList& wl, int32_t* chain_state,
     GTA_CUDA(cudaMemsetAsync(wl.chain_flags, 0, windows * size_t(wl.num_slots) * sizeof(int32_t), st));
     count_launch();
   }
+  wl.take = (phases & GTA_PHASE_STATIC) ? 0 : 1;
   if ((phases & GTA_PHASE_MAIN) && wl.num_items > 0) {
     GTA_CUDA(cudaMemsetAsync(wl.work_counter, 0, (windows + GTA_MAX_RANKS) * sizeof(int32_t), st));
     count_launch();
@@ -1404,8 +1407,8 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
     }
     const int lanes = lanes_for(f, 4);
 #define GTA_LLH(L)                                                                                                  \
-  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl.num_items, L, f, ex), kAggThreads, 0, \
-                                st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl.num_items, L)), ex, el,   \
+  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl, L, f, ex), kAggThreads, 0, \
+                                st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl, L)), ex, el,   \
                                       er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,                     \
                                       epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
     switch (lanes) {

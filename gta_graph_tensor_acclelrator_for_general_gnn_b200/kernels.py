@@ -160,11 +160,16 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
     return z, el, er
 
 
-def _launch_blocks(launch, sched: Schedule, block_events):
+#: below this many edges per work item a long list is walked with static striding (GTA_PHASE_STATIC)
+STATIC_ITEM_EDGES = 48
+
+
+def _launch_blocks(launch, sched: Schedule, block_events, num_edges: int = 0):
     """One launch for everything, or -- when the gathered table arrives chunk by chunk -- the first column
     block as soon as its chunk has landed and the rest after the last event."""
     if block_events is None:
-        launch(0, sched.num_items, _cabi.PHASE_ALL)
+        tiny = sched.num_items >= (1 << 18) and num_edges < STATIC_ITEM_EDGES * sched.num_items
+        launch(0, sched.num_items, _cabi.PHASE_ALL | (_cabi.PHASE_STATIC if tiny else 0))
         return
     if len(block_events) != sched.num_blocks:
         raise ValueError(f"{len(block_events)} chunk events for {sched.num_blocks} column blocks")
@@ -225,7 +230,7 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
                        _cabi.ptr(rowden), _cabi.ptr(x), _ld(x), _cabi.ptr(o), _ld(o), f, epilogue,
                        partials, chain, exchange.byref() if exchange is not None else None,
                        phases, _stream()), fname)
-    _launch_blocks(launch, sched, block_events)
+    _launch_blocks(launch, sched, block_events, g.num_edges)
     return o
 
 
@@ -317,7 +322,7 @@ def gat_aggregate(g: DeviceGraph, el: torch.Tensor, er: torch.Tensor, z: torch.T
                        _ld(o), f, epilogue, _cabi.ptr(rowmax), _cabi.ptr(rowsum),
                        partials, chain, _cabi.ptr(stats), col_block,
                        exchange.byref() if exchange is not None else None, phases, _stream()), fname)
-    _launch_blocks(launch, sched, block_events)
+    _launch_blocks(launch, sched, block_events, g.num_edges)
     if want_stats:
         return o, rowmax, rowsum
     return o
