@@ -3,8 +3,8 @@
 N=$1; TAG=$2; shift; shift
 mkdir -p gpurun_out
 OUT=gpurun_out/scale_${TAG}_n$N
-if [ "$N" = "1" ]; then timeout 600 python bench.py --gpus 1 "$@" > $OUT.json 2> $OUT.err
-else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N "$@" > $OUT.json 2> $OUT.err; fi
+if [ "$N" = "1" ]; then timeout 300 python bench.py --gpus 1 "$@" > $OUT.json 2> $OUT.err
+else timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N "$@" > $OUT.json 2> $OUT.err; fi
 echo "rc=$?"
 tail -1 $OUT.json | python -c "
 import json,sys
