@@ -580,8 +580,8 @@ def main():
         # first steps on fresh streams pay cudaMalloc (device-synchronising) for Z / el / er / out
         pipe2 = pipeline.HostPipeline(step, r1 - r0, fin, dev, depth=2)
         pipe1 = pipeline.HostPipeline(step, r1 - r0, fin, dev, depth=1)
-        e2e_run(pipe2, 3)
-        e2e_run(pipe1, 2)
+        e2e_run(pipe2, 5)
+        e2e_run(pipe1, 3)
         e2e_serial_ms = e2e_run(pipe1, max(args.e2e_steps // 2, 2))
         e2e_ms = e2e_run(pipe2, args.e2e_steps)
         assert torch.equal(ys_pin[0], y.cpu()), "e2e result differs from the resident-input result"

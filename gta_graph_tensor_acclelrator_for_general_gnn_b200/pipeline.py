@@ -43,6 +43,11 @@ class HostPipeline:
         self.ev_first = torch.cuda.Event(enable_timing=True)
         self.ev_last = torch.cuda.Event(enable_timing=True)
         self.count = 0
+        # results whose copy-out is still in flight: (tensor, event after its D2H).  They are kept alive HERE and
+        # dropped only once that event has completed -- not handed to the caching allocator with record_stream(),
+        # whose deferred frees made the steady state allocate now and then (cudaMalloc inside the timed region:
+        # e2e steps of 20 ms instead of 11 in one run out of three)
+        self.inflight = []
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
@@ -69,9 +74,14 @@ class HostPipeline:
             self.ev_run[slot].record(self.s_run)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_run[slot])
-            y.record_stream(self.s_out)
             y_host.copy_(y, non_blocking=True)
             self.ev_last.record(self.s_out)
+            done = torch.cuda.Event()
+            done.record(self.s_out)
+        self.inflight.append((y, done))
+        while len(self.inflight) > self.depth:
+            _, ev = self.inflight.pop(0)
+            ev.synchronize()          # two steps old: complete in the steady state
         self.count += 1
 
     def finish(self) -> float:
@@ -80,6 +90,7 @@ class HostPipeline:
         self.s_out.synchronize()
         self.s_run.synchronize()
         self.s_in.synchronize()
+        self.inflight.clear()
         ms = self.ev_first.elapsed_time(self.ev_last) if self.count else 0.0
         self.count = 0
         return ms

@@ -17,3 +17,7 @@ cuobjdump -sass $SO 2>/dev/null | awk '/Function :/{fn=$3} /UTCHMMA|UTMALDG|LDTM
 echo
 echo "## Resource usage per kernel (cuobjdump -res-usage; CUB kernels omitted): REG, SHARED (static), STACK (spill bytes)"
 cuobjdump -res-usage $SO 2>/dev/null | awk '/Function /{fn=$2; sub(/:$/,"",fn)} /REG:/{print fn" "$0}' | while read f rest; do echo "$(echo $f | c++filt | cut -c1-110) | $rest"; done | grep -v "cub::"
+echo
+echo "## Fused compute + exchange: system-scope peer accesses and release/acquire flags in the AGGREGATION kernels"
+echo "## (ld.relaxed.sys on IPC-mapped peer tables = LDG...STRONG.SYS, st.release.sys / ld.acquire.sys on the signal blocks)"
+cuobjdump -sass $SO 2>/dev/null | awk '/Function :/{fn=$3} /STRONG\.SYS|MEMBAR\.ALL\.SYS|MEMBAR\.SC\.SYS|\.SYS /{c[fn]++} END{for(f in c) print c[f], f}' | sort -rn | head -12 | while read n f; do echo "$n $(echo $f | c++filt | cut -c1-120)"; done
