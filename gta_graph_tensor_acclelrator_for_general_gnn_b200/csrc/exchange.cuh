@@ -44,13 +44,18 @@ struct Exchange {
 // bounded spin on a counter another agent releases; a protocol bug traps instead of hanging the GPU
 template <bool SYSTEM>
 __device__ __forceinline__ void wait_at_least(const int32_t* p, int32_t want) {
+  // relaxed polls, one acquire fence on success (an acquire load per iteration would invalidate L1 every time)
   int32_t v = 0;
 #pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
-    if (SYSTEM) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    else asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    if (v >= want) return;
-    __nanosleep(SYSTEM ? 200 : 64);
+    if (SYSTEM) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= want) {
+      if (SYSTEM) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      return;
+    }
+    __nanosleep(SYSTEM ? 200 : 100);
   }
   __trap();
 }

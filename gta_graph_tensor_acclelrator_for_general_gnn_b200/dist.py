@@ -138,9 +138,11 @@ class SourceExchange:
             self._buf[key] = torch.zeros((p.world, p.stride, kernels.pad4(width)), dtype=torch.float32, device=device)
         return self._buf[key]
 
-    def local_views(self, f: int, h: int, device):
+    def local_views(self, f: int, h: int, device, dtype=torch.float32):
         """``(z [rows, f], er [rows, h])`` views of this rank's slot of the gathered ``[F | H]`` table, for
         producers (the GEMM) that write there directly."""
+        if dtype != torch.float32:
+            raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "SourceExchange", "the NCCL all-gather exchange is fp32 only")
         p = self.part
         slot = self.buffer(f + kernels.pad4(h), device)[p.slot_of(p.rank), :p.rows]
         return slot[:, :f], slot[:, f:f + h]
@@ -279,29 +281,42 @@ class FusedExchange:
         self._emulated = list(peers)
 
     # -- setup: tables (two step parities) + signal block, published to / mapped from the peers ------------
-    def _alloc(self, width: int, device):
+    @staticmethod
+    def _row_bytes(f: int, h: int, dtype) -> int:
+        """Bytes of one table row: ``f`` features of ``dtype`` padded to 16 bytes, then ``h`` fp32 (er) padded to 16."""
+        es = 2 if dtype == torch.bfloat16 else 4
+        return (f * es + 15) // 16 * 16 + kernels.pad4(h) * 4
+
+    def _alloc(self, row_bytes: int, device):
         p = self.part
         lib = _cabi.load()
-        ld = kernels.pad4(width)
-        st = {"ld": ld, "tables": [_IpcBuffer((p.world, p.stride, ld)) for _ in range(2)],
+        st = {"row_bytes": row_bytes, "tables": [_IpcBuffer((p.world, p.stride, row_bytes // 4)) for _ in range(2)],
               "signals": _IpcBuffer(((int(lib.gta_exchange_signal_bytes()) + 3) // 4,))}
-        st["tables_t"] = [t.tensor() for t in st["tables"]]
+        st["tables_t"] = [t.tensor() for t in st["tables"]]          # fp32-typed raw rows [world, stride, row_bytes / 4]
         return st
 
-    def _setup(self, width: int, device):
-        key = (width, torch.device(device))
+    def _views(self, st, parity: int, f: int, h: int, dtype):
+        """``(z [world*stride, f] of dtype, er [world*stride, h] fp32 | None)`` strided views of one table."""
+        raw = st["tables_t"][parity].view(-1, st["row_bytes"] // 4)
+        es = 2 if dtype == torch.bfloat16 else 4
+        z = (raw.view(torch.bfloat16) if dtype == torch.bfloat16 else raw)[:, :f]
+        off = ((f * es + 15) // 16 * 16) // 4
+        return z, (raw[:, off:off + h] if h else None)
+
+    def _setup(self, row_bytes: int, device):
+        key = (row_bytes, torch.device(device))
         if key in self._state:
             return self._state[key]
         p = self.part
         lib = _cabi.load()
         if self._emulated is not None or p.world == 1:
-            st = self._alloc(width, device)
+            st = self._alloc(row_bytes, device)
             st["own"] = True
             self._state[key] = st
             return st
         ok, err, st = 1, "", None
         try:
-            st = self._alloc(width, device)
+            st = self._alloc(row_bytes, device)
             handles = [t.handle() for t in st["tables"]] + [st["signals"].handle()]
         except Exception as exc:          # keep going to the collective below so every rank agrees
             ok, err, handles = 0, str(exc), [b"", b"", b""]
@@ -328,31 +343,32 @@ class FusedExchange:
         self._state[key] = st
         return st
 
-    def _peer_ptrs(self, width: int, device, parity: int):
+    def _peer_ptrs(self, row_bytes: int, device, parity: int):
         """(table pointer of every rank for this parity, signal pointer of every rank)."""
         p = self.part
-        st = self._setup(width, device)
+        st = self._setup(row_bytes, device)
         if self._emulated is not None:
-            others = [pe._setup(width, device) for pe in self._emulated]
+            others = [pe._setup(row_bytes, device) for pe in self._emulated]
             return [o["tables"][parity].ptr for o in others], [o["signals"].ptr for o in others]
         if p.world == 1:
             return [st["tables"][parity].ptr], [st["signals"].ptr]
         return [st["peer"][q][parity] for q in range(p.world)], [st["peer"][q][2] for q in range(p.world)]
 
     # -- per step -----------------------------------------------------------------------------------
-    def local_views(self, f: int, h: int, device):
-        """Views of slot 0 (this rank's rows) of the table the NEXT gather_* call will publish."""
-        st = self._setup(f + kernels.pad4(h), device)
-        slot = st["tables_t"][(self.step + 1) & 1][0, :self.part.rows]
-        return slot[:, :f], slot[:, f:f + h]
+    def local_views(self, f: int, h: int, device, dtype=torch.float32):
+        """Views of slot 0 (this rank's rows) of the table the NEXT gather_* call will publish: ``(z [rows, f] of
+        ``dtype``, er [rows, h] fp32)``.  ``dtype=torch.bfloat16``: the bf16 storage mode travels over NVLink too
+        (half the bytes of the pull; er stays fp32 behind the bf16 features of its row)."""
+        st = self._setup(self._row_bytes(f, h, dtype), device)
+        z, er = self._views(st, (self.step + 1) & 1, f, h, dtype)
+        return z[:self.part.rows], (er[:self.part.rows] if er is not None else None)
 
-    def _publish(self, width: int, device, er: torch.Tensor | None) -> Gate:
+    def _publish(self, st, device, er: torch.Tensor | None) -> Gate:
         p = self.part
         lib = _cabi.load()
-        st = self._setup(width, device)
         self.step += 1
         parity = self.step & 1
-        tables, signals = self._peer_ptrs(width, device, parity)
+        tables, signals = self._peer_ptrs(st["row_bytes"], device, parity)
         sig_arr = (C.c_void_p * p.world)(*signals)
         stats = kernels.er_stats(er, 0) if er is not None and p.rows > 0 else None      # None: no power-of-two head count
         heads = int(er.shape[1]) if stats is not None else 0
@@ -360,7 +376,7 @@ class FusedExchange:
                     "gta_exchange_publish")
         ex = _cabi.Exchange()
         ex.world, ex.rank, ex.step, ex.copy_ctas = p.world, p.rank, self.step, self.copy_ctas
-        ex.slot_rows, ex.row_bytes = p.stride, st["ld"] * 4
+        ex.slot_rows, ex.row_bytes = p.stride, st["row_bytes"]
         ex.table, ex.signals = st["tables"][parity].ptr, st["signals"].ptr
         for k in range(p.world):
             q = p.owner_of(k)
@@ -373,29 +389,30 @@ class FusedExchange:
         """``(z_table, er_table, gate)``: views of this step's gathered table -- only slot 0 is valid until the
         aggregation launch that is handed ``gate`` has pulled the rest."""
         f, h = int(z.shape[1]), int(er.shape[1])
-        width = f + kernels.pad4(h)
-        views = self.local_views(f, h, z.device)
+        st = self._setup(self._row_bytes(f, h, z.dtype), z.device)
+        views = self.local_views(f, h, z.device, z.dtype)
         if not (views[0].data_ptr() == z.data_ptr() and views[1].data_ptr() == er.data_ptr()):
             views[0].copy_(z)          # the producer did not write into the slot: copy
             views[1].copy_(er)
-        st = self._setup(width, z.device)
-        gate = self._publish(width, z.device, views[1])
-        table = st["tables_t"][self.step & 1].view(-1, st["ld"])
-        return table[:, :f], table[:, f:f + h], gate
+        gate = self._publish(st, z.device, views[1])
+        self._last = (st, f, h, z.dtype)
+        zt, ert = self._views(st, self.step & 1, f, h, z.dtype)
+        return zt, ert, gate
 
     @kernels._timed("exchange_publish")
     def gather_one(self, t: torch.Tensor):
-        width = int(t.shape[1])
-        st = self._setup(width, t.device)
-        st["tables_t"][(self.step + 1) & 1][0, :self.part.rows, :width].copy_(t)
-        gate = self._publish(width, t.device, None)
-        return st["tables_t"][self.step & 1].view(-1, st["ld"])[:, :width], gate
+        f = int(t.shape[1])
+        st = self._setup(self._row_bytes(f, 0, t.dtype), t.device)
+        self.local_views(f, 0, t.device, t.dtype)[0].copy_(t)
+        gate = self._publish(st, t.device, None)
+        self._last = (st, f, 0, t.dtype)
+        return self._views(st, self.step & 1, f, 0, t.dtype)[0], gate
 
-    def last_table(self, width: int) -> torch.Tensor:
-        """The gathered ``[world*stride, width]`` table of the last step of that width (complete once the aggregation
-        launch that pulled it has finished)."""
-        st = self._state[next(k for k in self._state if k[0] == width)]
-        return st["tables_t"][self.step & 1].view(-1, st["ld"])[:, :width]
+    def last_table(self, width: int = 0) -> torch.Tensor:
+        """The gathered ``[world*stride, f]`` feature table of the last step (complete once the aggregation launch
+        that pulled it has finished)."""
+        st, f, h, dtype = self._last
+        return self._views(st, self.step & 1, f, h, dtype)[0]
 
     def __call__(self, t: torch.Tensor) -> torch.Tensor:
         """Whole table at once for the generic kernels (any legal plan runs): an NCCL all-gather in rank order,

@@ -379,7 +379,8 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                    (V2/simpletest.yaml: ``isa.LEGACY_SIMPLETEST_COMP_TYPES``)
     feature_dtype : ``torch.bfloat16`` = bf16 STORAGE MODE: the output of a COMP_MM that is
                    gathered over the edges (Z) is stored in bf16 and accumulated in fp32 by the fused aggregate
-                   kernels; tolerance rtol 2e-2, atol 1e-2 rowscale.  Single GPU, fused plans only.
+                   kernels; tolerance rtol 2e-2, atol 1e-2 rowscale.  Fused plans only; across GPUs with the fused
+                   exchange, whose tables then hold (and move) bf16 rows.
     Returns {op position: tensor} (and the kernel log with ``return_log``).
     """
     if isinstance(op_info, (str, os.PathLike)):
@@ -435,8 +436,9 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
 
     if feature_dtype not in (torch.float32, torch.bfloat16):
         raise ExecutionError("feature_dtype is torch.float32 or torch.bfloat16")
-    if feature_dtype == torch.bfloat16 and source_table is not None:
-        raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute", "the bf16 storage mode is single-GPU for now")
+    if feature_dtype == torch.bfloat16 and source_table is not None and not getattr(source_table, "fused", False):
+        raise _cabi.GtaUnsupported(_cabi.ERR_UNSUPPORTED, "execute",
+                                   "the bf16 storage mode needs the fused exchange across GPUs (dist.FusedExchange)")
     # ops whose output is gathered over the edges (consumed by a scatter): the tables the storage mode applies to
     gathered = {q for p in range(n_ops) if op_info[p]["TYPE"] == "scatter" for q in prods[p] if q != -1}
     opts = {"slope": float(slope), "stabilize": bool(stabilize), "max_edge_bytes": int(max_edge_bytes),
@@ -546,10 +548,10 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                 x = kernels.to_table(run.force(v.args[0]))
                 ex = opts["source_table"]
                 views = None
+                zt = opts["feature_dtype"] if p in opts["gathered"] and p not in opts["wanted"] else torch.float32
                 if hasattr(ex, "local_views") and x.shape[0] == ex.part.rows:
                     # partitioned run: Z and er go straight into this rank's slot of the gathered table
-                    views = ex.local_views(int(v.weight.shape[1]), env[kids[1]].width, x.device)
-                zt = opts["feature_dtype"] if p in opts["gathered"] and p not in opts["wanted"] else torch.float32
+                    views = ex.local_views(int(v.weight.shape[1]), env[kids[1]].width, x.device, zt)
                 z, el, er = kernels.gemm(x, v.weight, env[kids[0]].weight, env[kids[1]].weight,
                                          out=views[0] if views else None, er_out=views[1] if views else None, z_dtype=zt)
                 v.tensor, env[kids[0]].tensor, env[kids[1]].tensor = z, el, er

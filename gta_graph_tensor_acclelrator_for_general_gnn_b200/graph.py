@@ -24,6 +24,9 @@ def auto_chunk(num_edges: int, resident_warps: int = 148 * 32) -> int:
     items (the persistent launch hands items out in list order, so the LAST item of a warp is pure tail: on 8 GPUs
     a 1024-edge item is 0.2 ms of a 0.65 ms kernel), a power of two in [128, 1024].  A function of the graph only,
     so the reduction shape stays fixed run to run."""
+    import os
+    if os.environ.get("GTA_CHUNK"):          # experiments only (tools/scale.sh): pin the item size
+        return int(os.environ["GTA_CHUNK"])
     target = max(num_edges // (resident_warps * 48), 1)
     chunk = 128
     while chunk < 1024 and chunk * 3 // 2 < target:

@@ -262,3 +262,42 @@ def test_committed_bench_lines_carry_the_contract_keys(n):
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if n == 1:
         assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+
+
+@pytest.mark.parametrize("name,n,workload_edges", [
+    ("r02_bench_n1", 1, 114615892), ("r02_bench_n2_fused", 2, 114615892), ("r02_bench_n1_reddit_gcn", 1, 114615892),
+    ("r02_bench_n1_bf16", 1, 114615892), ("r02_bench_n1_reddit_heavy_gat", 1, 114615892),
+])
+def test_round2_bench_lines_carry_parity_and_the_measured_ceilings(name, n, workload_edges):
+    """profiles/r02_bench_*.json (what DESIGN.md quotes for round 2): the contract keys, plus the round-2 additions --
+    a parity object over the benchmarked output that is inside the tolerance and bitwise reproducible, the measured
+    L2 gather ceiling next to the HBM roofline, the H2D floor next to the end-to-end number."""
+    import json
+    with open(os.path.join(REPO, "profiles", name + ".json")) as f:
+        line = json.loads([l for l in f.read().splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "parity"):
+        assert key in line, key
+    assert line["n_gpus"] == n and line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["vs_baseline"] is None
+    assert abs(line["value"] - workload_edges / (line["ms_per_step"] * 1e-3) / 1e9) < 1e-6 * line["value"]
+    par = line["parity"]
+    assert par["max_err_over_tol"] <= 1.0 and par["bitwise_rerun"] is True and par["finite"] is True
+    assert par["rows"] > 0 and par["edges"] > 0 and par["rows"] <= par["rows_of"]
+    roof = line["roofline"]
+    assert roof["bound"] == "hbm" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    assert roof["l2_gather_peak_gbs"] > roof["peak"] and 0 < roof["l2_frac"] < 1.2
+    assert (roof["traffic"] is None) == (n > 1 or "no ncu capture" in roof["traffic_source"])
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if line["e2e"] is not None:
+        e2e = line["e2e"]
+        assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < line["value"]
+        assert e2e["h2d_alone_ms"] <= e2e["ms_per_step"] * 1.02          # a step cannot beat its own upload
+
+
+def test_item_size_and_slot_groups_are_functions_of_the_shape_only():
+    """auto_chunk / slot_groups decide the reduction SHAPE: pure functions, so results stay bitwise reproducible."""
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import dist as gdist, graph
+    assert [graph.auto_chunk(e) for e in (10556, 14_300_000, 57_300_000, 114_615_892, 268_435_456)] == [128, 128, 256, 512, 1024]
+    for world in range(1, 17):
+        groups = gdist.slot_groups(world)
+        assert groups[0] == [0] and [k for g in groups for k in g] == list(range(world)) and len(groups) <= 3

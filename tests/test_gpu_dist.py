@@ -208,3 +208,38 @@ def test_schedule_cut_points_equal_uniform_blocks():
             srcs = indices[it[1]:it[1] + it[2]]
             assert srcs.size == 0 or (srcs[0] >= bounds[blk] and srcs[-1] < bounds[blk + 1])
     assert gdist.slot_groups(8) == [[0], [1, 2, 3], [4, 5, 6, 7]] and gdist.slot_groups(2) == [[0], [1]]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_exchange_bf16_tables_emulated(world):
+    """bf16 storage mode across ranks: the IPC tables hold [Z bf16 | er fp32] rows (half the bytes of the pull), the GEMM
+    rounds Z into slot 0, the bf16 gather kernel reads the pulled slots.  Against the fp64 oracle at the mode's tolerance,
+    and against the single-GPU bf16 run at the fp32 tolerance (same stored values, other reduction order)."""
+    import torch
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import dist as gdist, kernels
+    indptr, indices, full, xd, wd, ald, ard, host = _gat_case()
+    x, w, al, ar = host
+    f, heads = int(wd.shape[1]), int(ald.shape[1])
+    ref = O.gat_layer(indptr, indices, x, w, al, ar)
+    zabs = np.abs(x).astype(np.float64) @ np.abs(w).astype(np.float64)
+    scale = O.segment_sum(O.head_broadcast(ref["alpha"], f) * zabs[indices], indptr)
+    z1, el1, er1 = kernels.gemm(xd, wd, ald, ard, z_dtype=torch.bfloat16)
+    single = kernels.gat_aggregate(full, el1, er1, z1).cpu().numpy()
+    parts = [gdist.make_partition(full, r, world) for r in range(world)]
+    exs = [gdist.FusedExchange(p, copy_ctas=8) for p in parts]
+    for ex in exs:
+        ex.emulate_with(exs)
+    for step in range(2):
+        staged = []
+        for p, ex in zip(parts, exs):
+            zv, erv = ex.local_views(f, heads, "cuda", torch.bfloat16)
+            assert zv.dtype == torch.bfloat16 and erv.dtype == torch.float32
+            z, el, er = kernels.gemm(xd[p.row_begin:p.row_end], wd, ald, ard, out=zv, er_out=erv)
+            zt, ert, gate = ex.gather_pair(z, er)
+            assert gate.struct.row_bytes == 2 * f + 16 and zt.dtype == torch.bfloat16
+            staged.append((el, zt, ert, gate))
+        got = torch.cat([kernels.gat_aggregate(p.local, el, ert, zt, exchange=gate)
+                         for p, (el, zt, ert, gate) in zip(parts, staged)]).cpu().numpy()
+        bound = 2e-2 * np.abs(ref["Y"]) + 1e-2 * scale + 1e-30
+        assert np.all(np.isfinite(got)) and np.max(np.abs(got - ref["Y"]) / bound) <= 1.0
+        assert_close_rowscale(got, single.astype(np.float64), scale, what=f"bf16 exchange world={world} step={step}")
