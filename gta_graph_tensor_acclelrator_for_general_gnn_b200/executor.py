@@ -239,6 +239,64 @@ class _Run:
             return ex.gather_one(x)
         return ex(x), None
 
+    def _scatter_sum_leaves(self, v: Value):
+        """The leaves of an ADD tree over edges whose leaves are all virtual scatters of one width (DGN's whole edge
+        phase after the MM has been distributed), or None.  Inner nodes must be lazy, private to the tree and not
+        asked for as outputs -- otherwise they have to exist as edge tensors anyway."""
+        if v.kind != "edge_expr" or v.op != "add" or v.forced:
+            return None
+        leaves, stack = [], list(v.args)
+        while stack:
+            a = stack.pop()
+            if a.kind == "scatter" and not a.forced:
+                leaves.append(a)
+            elif (a.kind == "edge_expr" and a.op == "add" and not a.forced and a.extra.get("consumers", 1) == 1
+                  and a.pos not in self.o["wanted"]):
+                stack.extend(a.args)
+            else:
+                return None
+        if len(leaves) < 2 or len({l.width for l in leaves}) != 1:
+            return None
+        return leaves
+
+    def _gather_scatter_sum(self, leaves, epilogue: int, pos: int) -> torch.Tensor:
+        """gather(sum of scatters): the sources' part is ONE plain segment sum over the added node tables, the
+        destinations' part is the row's own value times its degree -- no edge tensor at all (the generic path makes
+        five passes over E x F for DGN)."""
+        k = kernels
+
+        def total(vals):
+            t = None
+            for val in vals:
+                cur = k.to_table(self.force(val.args[0]))
+                if t is None:
+                    t = cur
+                else:
+                    self.kernel_log.append(("gta_node_binary_f32", pos))
+                    t = k.node_binary(_cabi.BIN_ADD, t, cur)
+            return t
+        by_src = [l for l in leaves if l.side == "C"]
+        by_dst = [l for l in leaves if l.side == "R"]
+        out = None
+        if by_src:
+            x, gate = self._gather_sources(total(by_src))
+            self.kernel_log.append(("gta_aggregate_f32:scatter_sum", pos))
+            out = k.aggregate(self.g, x, None, None, _cabi.EPI_NONE if by_dst else epilogue, exchange=gate)
+            if not by_dst:
+                return out
+        if "degree" not in self.g.schedules:      # graph metadata, once: the row's edge count as an [N, 1] table
+            deg = (self.g.indptr[1:] - self.g.indptr[:-1]).to(torch.float32)[:, None]
+            self.g.schedules["degree"] = k.to_table(deg.contiguous())
+        self.kernel_log.append(("gta_node_binary_f32", pos))
+        own = k.node_binary(_cabi.BIN_MUL, total(by_dst), self.g.schedules["degree"])
+        if out is not None:
+            self.kernel_log.append(("gta_node_binary_f32", pos))
+            own = k.node_binary(_cabi.BIN_ADD, out, own)
+        if epilogue != _cabi.EPI_NONE:
+            self.kernel_log.append(("gta_node_unary_f32", pos))
+            own = k.node_unary(_cabi.UN_ELU if epilogue == _cabi.EPI_ELU else _cabi.UN_RELU, own, self.o["slope"])
+        return own
+
     def _by_source(self) -> DeviceGraph:
         """The CSC walk as a graph over EDGE ids: row j lists the CSR positions of the edges whose
         source is j, ascending (= ascending destination), so an ORDER C gather is the same
@@ -264,6 +322,9 @@ class _Run:
             x, gate = self._gather_sources(k.to_table(self.force(src.args[0])))
             self.kernel_log.append(("gta_aggregate_f32:sum", v.pos))
             return k.aggregate(self.g, x, None, None, epilogue, exchange=gate)
+        leaves = self._scatter_sum_leaves(src)
+        if leaves is not None:
+            return self._gather_scatter_sum(leaves, epilogue, v.pos)
         sp = self._split_mul(src)
         if sp is not None:
             xv, wv = sp
@@ -521,6 +582,16 @@ def execute(program, op_info, graph: DeviceGraph, node_inputs: dict, weights: di
                     # and keep the scatter virtual (what the reference's PNA-trans graph does by hand)
                     inner = Value("mm", args=(a.args[0],), weight=w, width=int(w.shape[1]), pos=pos)
                     return Value("scatter", args=(inner,), side=a.side, width=inner.width, pos=pos)
+                if (a.kind == "edge_expr" and a.op == "add" and not a.forced and consumers.get(a.pos, 1) == 1
+                        and a.pos not in opts["wanted"] and len(a.args) == 2
+                        and all(s_.kind == "scatter" and not s_.forced for s_ in a.args)):
+                    # DGN op 3: MM(ADD(scatter(x), scatter(y)), W) = ADD(scatter(MM(x, W)), scatter(MM(y, W))) -- the
+                    # product is linear, so it runs over the N node rows of each operand and no E x Fin tensor exists
+                    parts = tuple(Value("scatter", side=s_.side, width=int(w.shape[1]), pos=pos,
+                                        args=(Value("mm", args=(s_.args[0],), weight=w, width=int(w.shape[1]), pos=pos),))
+                                  for s_ in a.args)
+                    return Value("edge_expr", op="add", args=parts, width=int(w.shape[1]), pos=pos,
+                                 extra={"consumers": consumers[pos]})
                 return Value("edge_mm", args=(a,), weight=w, width=int(w.shape[1]), pos=pos,
                              extra={"consumers": consumers[pos]})
             return Value("mm", args=(args[0],), weight=w, width=int(w.shape[1]), pos=pos)

@@ -19,19 +19,17 @@ from . import _cabi
 DEFAULT_CHUNK = 1024   # edges per work item (fixed => deterministic reduction shape)
 
 
-def auto_chunk(num_edges: int, resident_warps: int = 148 * 32) -> int:
-    """Edges per work item for a graph of ``num_edges`` edges: small enough that every resident warp gets about 48
-    items (the persistent launch hands items out in list order, so the LAST item of a warp is pure tail: on 8 GPUs
-    a 1024-edge item is 0.2 ms of a 0.65 ms kernel), a power of two in [128, 1024].  A function of the graph only,
-    so the reduction shape stays fixed run to run."""
+def auto_chunk(num_edges: int) -> int:
+    """Edges per work item for a graph of ``num_edges`` edges.  The persistent launch hands items out in list order,
+    so the LAST item a warp takes is pure tail: at 1/8 of the Reddit shape a 1024-edge item is 0.2 ms of a 0.65 ms
+    kernel.  Small items are not free either (about 5 us of exposed latency each: item record, first ids, first er
+    rows, chain state): on the full Reddit shape 256 costs 4 % against 1024 and 128 costs 49 %.  So: 1024 for big
+    graphs, 256 once the graph (or a rank's share of it) is below 80 M edges.  A function of the graph only, so the
+    reduction shape stays fixed run to run."""
     import os
     if os.environ.get("GTA_CHUNK"):          # experiments only (tools/scale.sh): pin the item size
         return int(os.environ["GTA_CHUNK"])
-    target = max(num_edges // (resident_warps * 48), 1)
-    chunk = 128
-    while chunk < 1024 and chunk * 3 // 2 < target:
-        chunk *= 2
-    return chunk
+    return 1024 if num_edges >= 80_000_000 else 256
 
 
 def _stream() -> int:

@@ -139,7 +139,13 @@ def test_dgn_pna_dataflow(host, network, reorder, plan_kind, fuse):
     out, ref, names = _run(host, op_info, records, network, reorder, fuse)
     (p, y), = out.items()
     assert_close_rowscale(y.numpy(), ref[p], ref.scale[p], what=str(names))
-    assert "gta_gemm_f32:edges" in names              # DGN op 3 / PNA op 2: a real E-row GEMM
+    if network == "DGN" and (fuse or plan_kind == "one-block"):
+        # the whole edge phase is linear: MM distributed over the ADD of scatters (two N-row GEMMs), the gather of the
+        # four scatters = one plain segment sum + degree x own rows -- no E-row GEMM, no generic edge kernel
+        assert "gta_gemm_f32:edges" not in names and "gta_aggregate_f32:scatter_sum" in names, names
+        assert not any(k.startswith("gta_edge_") for k in names), names
+    else:
+        assert "gta_gemm_f32:edges" in names          # PNA op 2 (edge features), DGN with every STORE honoured
     if network == "PNA" and not reorder and fuse:
         # ops 3/4 = MM(scatter(x)): commuted to scatter(MM(x)) -> two N-row GEMMs, one E-row GEMM (op 2)
         assert names.count("gta_gemm_f32:edges") == 1 and names.count("gta_gemm_f32") == 3, names
@@ -147,11 +153,17 @@ def test_dgn_pna_dataflow(host, network, reorder, plan_kind, fuse):
 
 def test_edge_mm_respects_the_edge_budget(host):
     g, indptr, indices, dg = host
-    op_info, records = wide_program("DGN", False, "one-block")
+    # PNA op 2 is a GEMM over edge features: an E x F tensor that cannot be rewritten away
+    op_info, records = wide_program("PNA", False, "one-block")
     node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
     with pytest.raises(executor.ExecutionError, match="max_edge_bytes"):
-        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="DGN",
+        executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="PNA",
                          max_edge_bytes=1 << 16, check_shapes=False)
+    # DGN's edge phase is linear and never materialises E x F (even with a tiny budget); a missing input still raises
+    op_info, records = wide_program("DGN", False, "one-block")
+    node_inputs, weights, edge_inputs = shared._inputs(op_info, N, g.num_edges)
+    executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="DGN",
+                     max_edge_bytes=1 << 16, check_shapes=False)
     node_inputs.pop(9)
     with pytest.raises(executor.ExecutionError, match=r"node_inputs\[9\]"):
         executor.execute(records, op_info, dg, _t(node_inputs), _t(weights), _t(edge_inputs), network="DGN", check_shapes=False)
@@ -222,8 +234,12 @@ def test_edge_mm_feeding_a_gather_reduces_first(host, plan, fuse):
     out, ref, names = _run(host, op_info, records, None, False, fuse)
     assert_close_rowscale(out[5].numpy(), ref[5], ref.scale[5], what=str(names))
     stored_between = plan == [[0, 1, 2, 3], [4, 5]] and not fuse
-    assert ("gta_gemm_f32:after_gather" in names) == (not stored_between), names
-    assert ("gta_gemm_f32:edges" in names) == stored_between, names
+    # never an E-row GEMM unless the edge tensor is stored: MM over ADD(scatter, scatter) distributes into two N-row
+    # GEMMs and one segment sum (or, for a non-linear edge value, the gather runs first and the GEMM after it)
+    assert ("gta_aggregate_f32:scatter_sum" in names or "gta_gemm_f32:after_gather" in names) == (not stored_between), names
+    # a stored edge tensor is materialised once, at the output width (the GEMM still runs on N rows)
+    assert "gta_gemm_f32:edges" not in names, names
+    assert ("gta_edge_binary_f32" in names) == (not fuse and len(plan) > 1), names      # some STORE_E is honoured
 
 
 # ---- corrupted inputs are rejected, never crashed on (SURVEY 8b "Errors") ---------------------------

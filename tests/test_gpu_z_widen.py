@@ -34,7 +34,11 @@ def test_dgn_pna_match_oracle(network, reorder, plan_kind, fuse):
     (p, y), = out.items()
     y64 = ref[p]
     assert_close_rowscale(y.cpu().numpy(), y64, ref_scale[p], what=str(log))
-    assert any(k == "gta_gemm_f32:edges" for k, _ in log)
+    if network == "DGN" and (fuse or plan_kind == "one-block"):      # linear edge phase: no E x F tensor at all
+        assert not any(k == "gta_gemm_f32:edges" or k.startswith("gta_edge_") for k, _ in log), log
+        assert any(k == "gta_aggregate_f32:scatter_sum" for k, _ in log), log
+    else:
+        assert any(k == "gta_gemm_f32:edges" for k, _ in log)
 
 
 def test_npz_ingest_matches_scipy(tmp_path):
