@@ -20,16 +20,16 @@ DEFAULT_CHUNK = 1024   # edges per work item (fixed => deterministic reduction s
 
 
 def auto_chunk(num_edges: int) -> int:
-    """Edges per work item for a graph of ``num_edges`` edges.  The persistent launch hands items out in list order,
-    so the LAST item a warp takes is pure tail: at 1/8 of the Reddit shape a 1024-edge item is 0.2 ms of a 0.65 ms
-    kernel.  Small items are not free either (about 5 us of exposed latency each: item record, first ids, first er
-    rows, chain state): on the full Reddit shape 256 costs 4 % against 1024 and 128 costs 49 %.  So: 1024 for big
-    graphs, 256 once the graph (or a rank's share of it) is below 80 M edges.  A function of the graph only, so the
-    reduction shape stays fixed run to run."""
+    """Edges per work item.  Measured, not derived: 1024 is the best item size at every size tried.  One GPU, Reddit
+    shape (114.6 M edges), kernel alone: 1024 3.91 ms, 512 4.00, 256 4.07, 128 5.83 -- an item costs about 5 us of
+    exposed latency (item record, first ids, first er rows, chain state) whatever its length.  8 GPUs (14.3 M edges per
+    rank, exchange inside the launch): 1024 0.946 ms, 512 0.933, 256 1.002, 128 2.54 -- the tail of a 1024-edge item at
+    the end of the list is NOT what limits the small problem.  Kept as a function of the graph so
+    the reduction shape stays fixed run to run; ``GTA_CHUNK`` pins another size for experiments (tools/scale.sh)."""
     import os
-    if os.environ.get("GTA_CHUNK"):          # experiments only (tools/scale.sh): pin the item size
+    if os.environ.get("GTA_CHUNK"):
         return int(os.environ["GTA_CHUNK"])
-    return 1024 if num_edges >= 80_000_000 else 256
+    return 1024
 
 
 def _stream() -> int:

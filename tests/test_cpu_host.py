@@ -297,7 +297,7 @@ def test_round2_bench_lines_carry_parity_and_the_measured_ceilings(name, n, work
 def test_item_size_and_slot_groups_are_functions_of_the_shape_only():
     """auto_chunk / slot_groups decide the reduction SHAPE: pure functions, so results stay bitwise reproducible."""
     from gta_graph_tensor_acclelrator_for_general_gnn_b200 import dist as gdist, graph
-    assert [graph.auto_chunk(e) for e in (10556, 14_300_000, 57_300_000, 114_615_892, 268_435_456)] == [256, 256, 256, 1024, 1024]
+    assert [graph.auto_chunk(e) for e in (10556, 14_300_000, 57_300_000, 114_615_892, 268_435_456)] == [1024] * 5
     for world in range(1, 17):
         groups = gdist.slot_groups(world)
         assert groups[0] == [0] and [k for g in groups for k in g] == list(range(world)) and len(groups) <= 3
