@@ -64,6 +64,12 @@ namespace gta {
 #ifndef GTA_GAT_FORCE_LLH
 #define GTA_GAT_FORCE_LLH 0       // experiment: run the lane-local-head kernel for every head count
 #endif
+#ifndef GTA_ITEM_PREFETCH
+#define GTA_ITEM_PREFETCH 1       // stage the NEXT item's record and first ids / el while the current one is folded
+#endif
+#ifndef GTA_PUBLISH_FENCE
+#define GTA_PUBLISH_FENCE 0       // 1: an extra fence.sc in front of the release store of a chain publish (round-2 form)
+#endif
 constexpr int kAggThreads = GTA_AGG_THREADS;
 constexpr int kAggWarps = kAggThreads / 32;
 
@@ -94,7 +100,12 @@ __device__ __forceinline__ void chain_wait(const int32_t* flag) {
 // idiom of a cooperative grid barrier (block barrier, then one thread fences and signals).  One fence per
 // item instead of one per lane: a membar.gl is the most expensive instruction of a short item.
 __device__ __forceinline__ void chain_publish(int32_t* flag) {
+  // st.release is cumulative over what the barrier ordered before this lane (the idiom of CUTLASS's Semaphore::release:
+  // barrier, then one thread's st.release.gpu); a __threadfence() in front of it is a second, sequentially consistent
+  // fence (membar.gl) per item and buys nothing
+#if GTA_PUBLISH_FENCE
   __threadfence();
+#endif
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
 }
 // predecessor state was written by another SM during this launch: read it at L2, never from L1
@@ -120,6 +131,26 @@ __device__ __forceinline__ void for_groups_in_order(int lane, bool chained, F&& 
     }
   }
 }
+
+// ---- the next item, staged while the current one runs ------------------------------------------
+// An item costs a chain of dependent loads before its first gather can issue: the item record, then its first source
+// ids (streamed from DRAM) and el row, then the er rows of those ids; and two row_slots reads in front of the chain fold.
+// Measured on the Reddit shape (agg_probe, items of 20 edges against items of 164): about 5 us of warp time per item
+// whatever its length, a quarter of the kernel.  The record of the NEXT item and the slot range of the CURRENT row are
+// therefore copied into shared memory asynchronously at the top of an item (no registers held across the gather loop),
+// and the next item's el row and first two id batches are requested right after the gather loop, so that they travel
+// while the chain fold of the current item waits for its predecessor.
+struct NextItem {
+  int4 item;
+  int32_t s0, s1, pad0, pad1;
+};
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int LANES>
 __device__ __forceinline__ float group_max(float v) {
@@ -368,6 +399,9 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
   constexpr int kWindow = LANES * KP * V;          // features one pass of a group covers
   constexpr int kEdges = kAggUnroll;      // edges whose loads (V each) are in flight together
   __shared__ __align__(16) uint2 s_a[kAggWarps][32];        // per warp: {source id, weight} of the staged batch
+#if GTA_ITEM_PREFETCH
+  __shared__ __align__(16) NextItem s_next[kAggWarps][32 / LANES];
+#endif
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
     exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
     return;
@@ -387,19 +421,63 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
   const char* xf = reinterpret_cast<const char*>(x + (on[0] ? fo : 0));
 
   ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
-  while (cur.first < wl.num_items) {
+  int32_t landed = 0;          // exchange_gate: highest peer slot this lane has seen complete
+  const int head = (WKIND == 2 && on[0]) ? fo / (f / wh) : 0;
+  // what an item needs before its first batch (see NextItem): record, first ids (and scalar weights), the row's
+  // denominator, and -- in an exchange -- its last id, which names the highest slot it touches
+  int4 it = make_int4(0, 0, 0, -1);
+  bool have = false;
+  int idx_nxt = 0, last_src = 0;
+  float w_nxt = 0.f, den = 1.f;
+  auto request_inputs = [&](const int4& t, bool hv) {
+    const int cnt = hv ? t.z : 0;
+    const int32_t* ib = wl.indices + t.y;
+    idx_nxt = 0;
+    w_nxt = 0.f;
+    den = 1.f;
+    if (l < cnt) {
+      idx_nxt = ld_stream_i32(ib + l, pol_stream);
+      if (WKIND == 1) w_nxt = ld_stream_f32(w + int64_t(t.y) * wh + l, pol_stream);
+    }
+    if (DIV && hv) den = rowden[int64_t(t.x) * wh + head];
+    last_src = (ex.world > 1 && cnt > 0) ? __ldg(ib + cnt - 1) : 0;
+  };
+#if GTA_ITEM_PREFETCH
+  NextItem* nx = &s_next[threadIdx.x >> 5][lane / LANES];
+  {
     const int64_t group = int64_t(cur.first) + lane / LANES;
-    const bool have = group < wl.num_items;
+    have = group < wl.num_items;
+    if (have) it = __ldg(wl.items + group);
+    request_inputs(it, have);
+  }
+#endif
+  while (cur.first < wl.num_items) {
+#if GTA_ITEM_PREFETCH
+    ItemCursor nxt = cur;
+    cursor_next<LANES>(nxt, wl, counter, lane);
+    const int64_t ngroup = int64_t(nxt.first) + lane / LANES;
+    const bool nhave = nxt.first < wl.num_items && ngroup < wl.num_items;
+    if (l == 0) {
+      if (nhave) cp_async_16(&nx->item, wl.items + ngroup);
+      if (have && it.w >= 0) {
+        cp_async_4(&nx->s0, wl.row_slots + it.x);
+        cp_async_4(&nx->s1, wl.row_slots + it.x + 1);
+      }
+    }
+#else
+    {
+      const int64_t group = int64_t(cur.first) + lane / LANES;
+      have = group < wl.num_items;
+      it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
+      request_inputs(it, have);
+    }
+#endif
     const bool active = have && on[0];
-    const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
     const int count = have ? it.z : 0;
     const int max_count = (LANES == 32) ? count : warp_max_i32(count);
     const int32_t* idx_base = wl.indices + it.y;
     const float* w_base = (WKIND != 0) ? w + int64_t(it.y) * wh : nullptr;
-    int head = 0;
-    float den = 1.f;
-    if (WKIND == 2) head = active ? fo / (f / wh) : 0;
-    if (DIV && have) den = rowden[int64_t(it.x) * wh + head];
+    const float den_cur = den;          // the next item's denominator replaces `den` before this item is folded
 
     float acc[V][KP];
 #pragma unroll
@@ -407,14 +485,8 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
 #pragma unroll
       for (int c = 0; c < KP; ++c) acc[v][c] = 0.f;
     // software pipeline: ids (and scalar weights) of batch b+1 are in flight under the gathers of batch b
-    int idx_nxt = 0;
-    float w_nxt = 0.f;
-    if (l < count) {
-      idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
-      if (WKIND == 1) w_nxt = ld_stream_f32(w_base + l, pol_stream);
-    }
     if (ex.world > 1) {          // the item's slots may still be on their way from the peers
-      if (l == 0 && count > 0) exchange_gate(ex, __ldg(idx_base + count - 1));
+      if (l == 0 && count > 0) exchange_gate(ex, last_src, landed);
       __syncwarp();
     }
     for (int base = 0; base < max_count; base += LANES) {
@@ -423,7 +495,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
       const int my_idx = idx_nxt;
       float my_w = (l < n) ? w_nxt : 0.f;
       // divide only where an edge exists: a neighbouring group's empty row has den = 0 (0/0 = NaN)
-      if (WKIND == 1 && DIV && l < n) my_w = my_w / den;
+      if (WKIND == 1 && DIV && l < n) my_w = my_w / den_cur;
       if (base + LANES + l < count) {
         idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
         if (WKIND == 1) w_nxt = ld_stream_f32(w_base + base + LANES + l, pol_stream);
@@ -457,7 +529,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
                 float ws = __uint_as_float((u & 1) ? ed[u / 2].w : ed[u / 2].y);
                 if (WKIND == 2) {
                   ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
-                  if (DIV) ws = ws / den;
+                  if (DIV) ws = ws / den_cur;
                 }
 #pragma unroll
                 for (int v = 0; v < V; ++v) fma_row<P>(acc[v], ws, raw[u][v]);
@@ -486,7 +558,7 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
                 ws = 0.f;
                 if (ok && active) {
                   ws = __ldg(w_base + int64_t(base + j + u) * wh + head);
-                  if (DIV) ws = ws / den;
+                  if (DIV) ws = ws / den_cur;
                 }
               }
               wv[u] = ws;
@@ -502,10 +574,22 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
       __syncwarp();
     }
     const bool chained = have && it.w >= 0;
+#if GTA_ITEM_PREFETCH
+    cp_async_wait_all();
+    __syncwarp();
+    const int4 itn = nhave ? nx->item : make_int4(0, 0, 0, -1);
+    const int slot0 = chained ? nx->s0 : 0, slot1 = chained ? nx->s1 : 0;
+    __syncwarp();          // everybody has read the staging entry before lane 0 of the group overwrites it
+    request_inputs(itn, nhave);
+#endif
     for_groups_in_order<LANES>(lane, chained, [&]() {
       bool last = true;
       if (chained) {
+#if GTA_ITEM_PREFETCH
+        const int s0 = slot0, s1 = slot1;
+#else
         const int s0 = __ldg(wl.row_slots + it.x), s1 = __ldg(wl.row_slots + it.x + 1);
+#endif
         last = it.w == s1 - 1;
         if (it.w != s0) {
           if (l == 0) chain_wait(flags + it.w - 1);
@@ -534,7 +618,13 @@ aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__
           if (have && on[v]) st_out<KP>(out + int64_t(it.x) * ldo + fo + v * LANES * KP, acc[v], 1.f, epilogue);
       }
     });
+#if GTA_ITEM_PREFETCH
+    cur = nxt;
+    it = itn;
+    have = nhave;
+#else
     cursor_next<LANES>(cur, wl, counter, lane);
+#endif
   }
 }
 
@@ -600,6 +690,48 @@ __device__ __forceinline__ bool block_bound(const uint32_t* er_stats, int64_t cb
   return seen && (hi - lo) < kBoundRange;      // NaN compares false
 }
 
+// ---- the bound, looked up per item -----------------------------------------------------------------
+// Round-2 ncu of the GAT kernel on a low-degree shape (items of 20 edges, profiles/r02_gat_lowdeg_*): computing the
+// bound cost about 230 of an item's 1 180 warp instructions and 12 % of its stall samples -- two emulated 64-bit
+// divisions for the statistics blocks of the first and last source, then, head by head, a loop over those blocks
+// whose two L2 loads are consumed inside the loop: H serialised L2 round trips in front of every item's first batch.
+// Consecutive items of a warp almost always touch the same statistics blocks, so the warp (each lane group of it)
+// keeps the last answer in shared memory, keyed by (first block, last block): the bound stays a pure function of the
+// item, hence bitwise the same whoever computes it, and a hit costs two multiply-high divisions and one LDS.
+template <int MAXH>
+struct __align__(16) BoundCache {
+  int32_t cb0, cb1, ok, pad;
+  float hi[MAXH];
+};
+struct BlockDivider {          // source id -> statistics block, without the 64-bit division
+  uint32_t d, magic;
+  __device__ __forceinline__ explicit BlockDivider(int64_t col_block)
+      : d(col_block > 0 ? uint32_t(col_block) : 0u), magic(d > 1u ? uint32_t((uint64_t(1) << 32) / d) : 0u) {}
+  __device__ __forceinline__ int operator()(int src) const {
+    if (d <= 1u) return d == 0u ? 0 : src;
+    uint32_t q = __umulhi(uint32_t(src), magic);          // floor(2^32 / d): never above the quotient, at most 2 below
+    uint32_t r = uint32_t(src) - q * d;
+    while (r >= d) { ++q; r -= d; }
+    return int(q);
+  }
+};
+template <int LANES, int MAXH>
+__device__ __forceinline__ void bound_lookup(BoundCache<MAXH>* bc, const uint32_t* er_stats, int cb0, int cb1, int pitch,
+                                             int heads, int l, uint32_t gmask) {
+  if (bc->cb0 != cb0 || bc->cb1 != cb1) {          // the same answer in every lane of the group
+    __syncwarp(gmask);          // everybody has read the old key
+    bool ok = true;
+    for (int h = l; h < heads; h += LANES) {
+      float hi;
+      ok = block_bound(er_stats, cb0, cb1, pitch, heads, h, &hi) && ok;
+      bc->hi[h] = hi;
+    }
+    ok = __all_sync(gmask, ok);
+    if (l == 0) { bc->cb0 = cb0; bc->cb1 = cb1; bc->ok = ok ? 1 : 0; }
+    __syncwarp(gmask);
+  }
+}
+
 template <typename P, int LANES, int H>
 __global__ void __launch_bounds__(kAggThreads, (H <= 4) ? GTA_GAT_MINBLOCKS : (GTA_GAT_MINBLOCKS + 1) / 2)
 gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ el, const float* __restrict__ er,
@@ -616,6 +748,10 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   constexpr int KP = P::kPer;
   constexpr int kWindow = LANES * KP;
   __shared__ __align__(16) uint2 s_e[kAggWarps][H * kS];
+  __shared__ BoundCache<H> s_bound[kAggWarps][32 / LANES];
+#if GTA_ITEM_PREFETCH
+  __shared__ __align__(16) NextItem s_next[kAggWarps][32 / LANES];
+#endif
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
     exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
     return;
@@ -623,6 +759,10 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
   const int gbase = lane & ~(LANES - 1);          // first lane of my group inside the warp
+  BoundCache<H>* bc = &s_bound[threadIdx.x >> 5][lane / LANES];
+  if (l == 0) { bc->cb0 = -1; bc->cb1 = -1; bc->ok = 0; }
+  __syncwarp();
+  const BlockDivider block_of(col_block);
   const int fo = blockIdx.y * kWindow + KP * l;
   const int head = (fo < f) ? fo / (f / H) : 0;
   uint2* se = s_e[threadIdx.x >> 5];
@@ -636,35 +776,76 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
   const char* zf = reinterpret_cast<const char*>(z + (fo < f ? fo : 0));
 
   ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
-  while (cur.first < wl.num_items) {
+  int32_t landed = 0;          // exchange_gate: highest peer slot this lane has seen complete
+  // what an item needs before its first batch: the record, the row's el, the ids of its first two batches and its
+  // last id (sources ascend: the last id names the highest slot / statistics block the item touches)
+  int4 it = make_int4(0, 0, 0, -1);
+  bool have = false;
+  float elr[H];
+  int idx_cur = 0, idx_nxt = 0, last_src = 0;
+  const bool want_last = ex.world > 1 || er_stats != nullptr;
+  auto request_inputs = [&](const int4& t, bool hv) {
+    const int cnt = hv ? t.z : 0;
+    const int32_t* ib = wl.indices + t.y;
+#pragma unroll
+    for (int h = 0; h < H; ++h) elr[h] = 0.f;
+    if (hv) load_heads<H>(el + int64_t(t.x) * H, elr);
+    idx_cur = 0;
+    idx_nxt = 0;
+    if (l < cnt) idx_cur = ld_stream_i32(ib + l, pol_stream);
+    if (LANES + l < cnt) idx_nxt = ld_stream_i32(ib + LANES + l, pol_stream);
+    last_src = (cnt > 0 && want_last) ? __ldg(ib + cnt - 1) : 0;
+  };
+#if GTA_ITEM_PREFETCH
+  NextItem* nx = &s_next[threadIdx.x >> 5][lane / LANES];
+  {
     const int64_t group = int64_t(cur.first) + lane / LANES;
-    const bool have = group < wl.num_items;
+    have = group < wl.num_items;
+    if (have) it = __ldg(wl.items + group);
+    request_inputs(it, have);
+  }
+#endif
+  while (cur.first < wl.num_items) {
+#if GTA_ITEM_PREFETCH
+    // claim the next item now and let its record (and this row's slot range) travel into shared memory under the gathers
+    ItemCursor nxt = cur;
+    cursor_next<LANES>(nxt, wl, counter, lane);
+    const int64_t ngroup = int64_t(nxt.first) + lane / LANES;
+    const bool nhave = nxt.first < wl.num_items && ngroup < wl.num_items;
+    if (l == 0) {
+      if (nhave) cp_async_16(&nx->item, wl.items + ngroup);
+      if (have && it.w >= 0) {
+        cp_async_4(&nx->s0, wl.row_slots + it.x);
+        cp_async_4(&nx->s1, wl.row_slots + it.x + 1);
+      }
+    }
+#else
+    {
+      const int64_t group = int64_t(cur.first) + lane / LANES;
+      have = group < wl.num_items;
+      it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
+      request_inputs(it, have);
+    }
+#endif
     const bool active = have && fo < f;
-    const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
     const int count = have ? it.z : 0;
     const int max_count = (LANES == 32) ? count : warp_max_i32(count);
     const int32_t* idx_base = wl.indices + it.y;
 
-    float elr[H], m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
-    if (have) load_heads<H>(el + int64_t(it.x) * H, elr);
+    float m[H], s[H];      // s: this lane's share of the running sum (reduced at the end)
 #pragma unroll
-    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; if (!have) elr[h] = 0.f; }
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
     float acc[KP];
 #pragma unroll
     for (int c = 0; c < KP; ++c) acc[c] = 0.f;
 
     // software pipeline: source ids are loaded two batches ahead and the er rows one batch ahead, so
     // the id -> er -> softmax dependency chain of batch b+1 hides under the row gathers of batch b
-    int idx_cur = 0, idx_nxt = 0;
     float er_cur[H];
 #pragma unroll
     for (int h = 0; h < H; ++h) er_cur[h] = 0.f;
-    if (l < count) idx_cur = ld_stream_i32(idx_base + l, pol_stream);
-    if (LANES + l < count) idx_nxt = ld_stream_i32(idx_base + LANES + l, pol_stream);
-    // an item's sources are ascending: its last id names the highest slot (statistics block) it touches
-    const int last_src = (count > 0 && (ex.world > 1 || er_stats != nullptr)) ? __ldg(idx_base + count - 1) : 0;
     if (ex.world > 1) {          // the item's slots (z, er and their er range) may still be on their way from the peers
-      if (l == 0 && count > 0) exchange_gate(ex, last_src);
+      if (l == 0 && count > 0) exchange_gate(ex, last_src, landed);
       __syncwarp();
     }
     if (l < count) load_heads<H>(er + int64_t(idx_cur) * lder, er_cur);
@@ -675,14 +856,10 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
       bool ok = true;
       const int first_src = __shfl_sync(0xffffffffu, idx_cur, gbase);
       if (count > 0) {
-        const int64_t cb0 = col_block > 0 ? int64_t(first_src) / col_block : 0;
-        const int64_t cb1 = col_block > 0 ? int64_t(last_src) / col_block : 0;
+        bound_lookup<LANES, H>(bc, er_stats, block_of(first_src), block_of(last_src), stats_pitch, H, l, group_mask<LANES>(lane));
+        ok = bc->ok != 0;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          float hi;
-          ok = block_bound(er_stats, cb0, cb1, stats_pitch, H, h, &hi) && ok;
-          if (ok) m[h] = leaky(elr[h] + hi, slope);
-        }
+        for (int h = 0; h < H; ++h) m[h] = leaky(elr[h] + bc->hi[h], slope);
       }
       bounded = __all_sync(0xffffffffu, ok);
       if (!bounded) {
@@ -776,10 +953,24 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
 #pragma unroll
     for (int h = 0; h < H; ++h) s[h] = group_sum<LANES>(s[h]);
     const bool chained = have && it.w >= 0;
+#if GTA_ITEM_PREFETCH
+    // the gather loop is over: elr / idx_* are free, the staged record has long arrived.  Request the next item's
+    // inputs now; they travel while this item's chain fold waits for its predecessor and writes its state.
+    cp_async_wait_all();
+    __syncwarp();
+    const int4 itn = nhave ? nx->item : make_int4(0, 0, 0, -1);
+    const int slot0 = chained ? nx->s0 : 0, slot1 = chained ? nx->s1 : 0;
+    __syncwarp();          // everybody has read the staging entry before lane 0 of the group overwrites it
+    request_inputs(itn, nhave);
+#endif
     for_groups_in_order<LANES>(lane, chained, [&]() {
       bool last = true;
       if (chained) {
+#if GTA_ITEM_PREFETCH
+        const int s0 = slot0, s1 = slot1;
+#else
         const int s0 = __ldg(wl.row_slots + it.x), s1 = __ldg(wl.row_slots + it.x + 1);
+#endif
         last = it.w == s1 - 1;
         if (it.w != s0) {
           // fold the state of slots [s0, it.w) in: (max, sum, acc) triples merge like the online softmax itself
@@ -791,8 +982,10 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
           for (int h = 0; h < H; ++h) {
             const float pm = ld_state_f32(prev + stats + h), ps = ld_state_f32(prev + stats + H + h);
             const float mn = fmaxf(pm, m[h]);
-            const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
-            const float b = (m[h] == -INFINITY) ? 0.f : expf(m[h] - mn);
+            // one of the two factors is exp(0) = 1: a single exp per head (bit-identical to computing both)
+            const float t = (mn == -INFINITY) ? 0.f : expf(fminf(pm, m[h]) - mn);
+            const float a = (pm == -INFINITY) ? 0.f : (pm == mn ? 1.f : t);
+            const float b = (m[h] == -INFINITY) ? 0.f : (m[h] == mn ? 1.f : t);
             s[h] = fmaf(ps, a, s[h] * b);
             m[h] = mn;
             a_mine = (h == head) ? a : a_mine;
@@ -828,7 +1021,13 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
         }
       }
     });
+#if GTA_ITEM_PREFETCH
+    cur = nxt;
+    it = itn;
+    have = nhave;
+#else
     cursor_next<LANES>(cur, wl, counter, lane);
+#endif
   }
 }
 
@@ -850,12 +1049,17 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
                          int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
                          const uint32_t* er_stats, int stats_pitch, int64_t col_block) {
   __shared__ uint32_t s_id[kAggWarps][32];
+  __shared__ BoundCache<32> s_bound[kAggWarps][32 / LANES];          // er_stats are only passed for heads <= 32
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
     exchange_pull(ex, blockIdx.x);          // these CTAs move the peers' slots; everybody else reduces
     return;
   }
   const int lane = threadIdx.x & 31;
   const int l = lane & (LANES - 1);
+  BoundCache<32>* bc = &s_bound[threadIdx.x >> 5][lane / LANES];
+  if (l == 0) { bc->cb0 = -1; bc->cb1 = -1; bc->ok = 0; }
+  __syncwarp();
+  const BlockDivider block_of(col_block);
   const int fo = blockIdx.y * 128 + 4 * l;
   const int d = f / heads;
   const int head = (fo < f) ? fo / d : 0;
@@ -870,6 +1074,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
   const int stats = f + int(blockIdx.y) * gat_stats_stride(heads);
 
   ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
+  int32_t landed = 0;          // exchange_gate: highest peer slot this lane has seen complete
   while (cur.first < wl.num_items) {
     const int64_t group = int64_t(cur.first) + lane / LANES;
     const bool have = group < wl.num_items;
@@ -887,7 +1092,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
     if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
     const int last_src = (count > 0 && (ex.world > 1 || er_stats != nullptr)) ? __ldg(idx_base + count - 1) : 0;
     if (ex.world > 1) {
-      if (l == 0 && count > 0) exchange_gate(ex, last_src);
+      if (l == 0 && count > 0) exchange_gate(ex, last_src, landed);
       __syncwarp();
     }
     // bound path (see gat_aggregate_kernel): a lane only needs the bound of its own head; the choice is
@@ -895,17 +1100,10 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
     bool bounded = false;
     int first_src = 0;
     if (er_stats != nullptr) first_src = __shfl_sync(0xffffffffu, idx_nxt, lane & ~(LANES - 1));
-    if (er_stats != nullptr && count > 0) {
-      const int64_t cb0 = col_block > 0 ? int64_t(first_src) / col_block : 0;
-      const int64_t cb1 = col_block > 0 ? int64_t(last_src) / col_block : 0;
-      bool ok = true;
-      for (int h = 0; h < heads; ++h) {          // every head of the block must pass: lanes of one item agree
-        float hi;
-        ok = block_bound(er_stats, cb0, cb1, stats_pitch, heads, h, &hi) && ok;
-        if (h == head) m = leaky(elh + hi, slope);
-      }
-      bounded = ok;
-      if (!bounded) m = -INFINITY;
+    if (er_stats != nullptr && count > 0) {          // every head of the block must pass: lanes of one item agree
+      bound_lookup<LANES, 32>(bc, er_stats, block_of(first_src), block_of(last_src), stats_pitch, heads, l, group_mask<LANES>(lane));
+      bounded = bc->ok != 0;
+      m = bounded ? leaky(elh + bc->hi[head], slope) : -INFINITY;
     }
     for (int base = 0; base < max_count; base += LANES) {
       int n = count - base;
@@ -975,8 +1173,9 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
             const float* prev = wl.partials + int64_t(it.w - 1) * pstride;
             const float pm = ld_state_f32(prev + stats + head), ps = ld_state_f32(prev + stats + heads + head);
             const float mn = fmaxf(pm, m);
-            const float a = (pm == -INFINITY) ? 0.f : expf(pm - mn);
-            const float b = (m == -INFINITY) ? 0.f : expf(m - mn);
+            const float t = (mn == -INFINITY) ? 0.f : expf(fminf(pm, m) - mn);      // the other factor is exp(0) = 1
+            const float a = (pm == -INFINITY) ? 0.f : (pm == mn ? 1.f : t);
+            const float b = (m == -INFINITY) ? 0.f : (m == mn ? 1.f : t);
             const float4 p = ld_state_f32x4(prev + fo);
             s = fmaf(ps, a, s * b);
             m = mn;

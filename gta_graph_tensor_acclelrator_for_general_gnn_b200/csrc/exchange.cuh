@@ -99,9 +99,14 @@ __device__ __forceinline__ void exchange_pull(const Exchange& ex, int cta) {
 // slots in ring order, so once the slot of the last source has landed every earlier slot the item touches
 // has too.  Slot 0 is the rank's own rows.  Called by ONE lane of the group, followed by a group-wide
 // __syncwarp by the caller.
-__device__ __forceinline__ void exchange_gate(const Exchange& ex, int32_t last_src) {
+// `landed` (per calling lane, 0 at kernel start) is the highest slot this lane has already seen complete: slots land in
+// order and the work list walks them in order, so all but P-1 of a warp's items return on the first compare -- no
+// division, no L2 poll, no fence.
+__device__ __forceinline__ void exchange_gate(const Exchange& ex, int32_t last_src, int32_t& landed) {
+  if (int64_t(last_src) < int64_t(landed + 1) * ex.slot_rows) return;
   const int64_t k = int64_t(last_src) / ex.slot_rows;
-  if (k > 0) wait_at_least<false>(ex.arrived + k, ex.copy_ctas);
+  wait_at_least<false>(ex.arrived + k, ex.copy_ctas);
+  landed = int32_t(k);
 }
 
 }  // namespace gta
