@@ -1032,22 +1032,40 @@ gat_aggregate_kernel(const WorkList wl, const Exchange ex, const float* __restri
 }
 
 // ----------------------------------------------------------------------------------------
-// GAT edge phase, lane-local-head variant (any H with (F/H) % 4 == 0; used for H >= 8)
+// GAT edge phase, lane-local-head variant (any H whose per-head width F/H is a multiple of 4, or 2, or 1;
+// used for H >= 8 and for the narrow heads of the reference's third GAT layer, F = H = 16)
 //
 // The staged kernel above keeps el/max/sum/er for ALL heads in every lane (5H registers: H = 16
-// spills and runs at a quarter of the H = 4 speed).  Here a lane tracks only the head its own 4
-// features belong to: one scalar er gather per edge (the 32 lanes of a row read the H
-// consecutive floats of er[j]: one wavefront), softmax over groups of kLlhUnroll edges, no
-// per-head arrays, no shuffles.  Lanes of one head see the same edges in the same order, so their
-// (max, sum) are bit-identical.
+// spills and runs at a quarter of the H = 4 speed).  Here a lane tracks only the heads its own 4
+// features belong to -- HPL = 1 head when the per-head width is a multiple of 4, 2 heads of width 2, 4 heads
+// of width 1: one er gather of HPL floats per edge (the lanes of a row read the H consecutive floats of
+// er[j]: one wavefront), softmax over groups of a few edges, no arrays over all heads, no shuffles.  Lanes
+// of one head see the same edges in the same order, so their (max, sum) are bit-identical.
 // ----------------------------------------------------------------------------------------
-template <int LANES>
+template <int N>
+__device__ __forceinline__ void ldg_vec(const float* p, float (&v)[N]) {
+  if constexpr (N == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (N == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+// which of a lane's HPL heads its feature c (0..3) belongs to
+template <int HPL>
+__device__ __forceinline__ constexpr int head_of(int c) { return HPL == 1 ? 0 : (HPL == 2 ? c / 2 : c); }
+
+template <int LANES, int HPL>
 __global__ void __launch_bounds__(kAggThreads, GTA_LLH_MINBLOCKS)
 gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ el,
                          const float* __restrict__ er, int64_t lder, int heads, float slope,
                          const float* __restrict__ z, const uint32_t row_bytes, float* __restrict__ out, int64_t ldo,
                          int f, int epilogue, float* __restrict__ rowmax, float* __restrict__ rowsum,
                          const uint32_t* er_stats, int stats_pitch, int64_t col_block) {
+  constexpr int kU = kLlhUnroll / HPL > 2 ? kLlhUnroll / HPL : 2;      // edges per softmax group: e / p are HPL wide
   __shared__ uint32_t s_id[kAggWarps][32];
   __shared__ BoundCache<32> s_bound[kAggWarps][32 / LANES];          // er_stats are only passed for heads <= 32
   if (ex.world > 1 && blockIdx.y == 0 && blockIdx.x < ex.copy_ctas) {
@@ -1061,8 +1079,8 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
   __syncwarp();
   const BlockDivider block_of(col_block);
   const int fo = blockIdx.y * 128 + 4 * l;
-  const int d = f / heads;
-  const int head = (fo < f) ? fo / d : 0;
+  const int d = f / heads;          // HPL == 1: a multiple of 4;  HPL == 2: 2;  HPL == 4: 1
+  const int head = (fo < f) ? fo / d : 0;          // the lane's first head (a multiple of HPL)
   const float* erh = er + head;
   const uint32_t er_bytes = uint32_t(lder) * 4u;
   uint32_t* sid = s_id[threadIdx.x >> 5];
@@ -1084,9 +1102,11 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
     const int max_count = (LANES == 32) ? count : warp_max_i32(count);
     const int32_t* idx_base = wl.indices + it.y;
     const float* zf = z + (active ? fo : 0);
-    const float elh = have ? __ldg(el + int64_t(it.x) * heads + head) : 0.f;
+    float elh[HPL], m[HPL], s[HPL];
+#pragma unroll
+    for (int k = 0; k < HPL; ++k) { elh[k] = 0.f; m[k] = -INFINITY; s[k] = 0.f; }
+    if (active) ldg_vec<HPL>(el + int64_t(it.x) * heads + head, elh);
 
-    float m = -INFINITY, s = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int idx_nxt = 0;
     if (l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
@@ -1095,7 +1115,7 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
       if (l == 0 && count > 0) exchange_gate(ex, last_src, landed);
       __syncwarp();
     }
-    // bound path (see gat_aggregate_kernel): a lane only needs the bound of its own head; the choice is
+    // bound path (see gat_aggregate_kernel): a lane only needs the bound of its own heads; the choice is
     // per lane group here, nothing below synchronises across groups on it
     bool bounded = false;
     int first_src = 0;
@@ -1103,7 +1123,8 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
     if (er_stats != nullptr && count > 0) {          // every head of the block must pass: lanes of one item agree
       bound_lookup<LANES, 32>(bc, er_stats, block_of(first_src), block_of(last_src), stats_pitch, heads, l, group_mask<LANES>(lane));
       bounded = bc->ok != 0;
-      m = bounded ? leaky(elh + bc->hi[head], slope) : -INFINITY;
+#pragma unroll
+      for (int k = 0; k < HPL; ++k) m[k] = bounded ? leaky(elh[k] + bc->hi[head + k], slope) : -INFINITY;
     }
     for (int base = 0; base < max_count; base += LANES) {
       int n = count - base;
@@ -1113,53 +1134,62 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
       __syncwarp();
       const int nmax = (LANES == 32) ? n : LANES;
 #pragma unroll 1
-      for (int j = 0; j < nmax; j += kLlhUnroll) {
-        float e[kLlhUnroll];
-        float4 v[kLlhUnroll];
-        uint32_t id[kLlhUnroll];
+      for (int j = 0; j < nmax; j += kU) {
+        float e[kU][HPL];
+        float4 v[kU];
+        uint32_t id[kU];
 #pragma unroll
-        for (int u = 0; u < kLlhUnroll; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
+        for (int u = 0; u < kU; ++u) id[u] = (j + u < LANES) ? mine[(j + u) & (LANES - 1)] : 0u;
 #pragma unroll
-        for (int u = 0; u < kLlhUnroll; ++u) {
+        for (int u = 0; u < kU; ++u) {
           const bool ok = (j + u) < n;
-          e[u] = ok ? leaky(elh + __ldg(row_ptr(erh, id[u], er_bytes)), slope) : -INFINITY;
+          float erv[HPL];
+#pragma unroll
+          for (int k = 0; k < HPL; ++k) erv[k] = 0.f;
+          if (ok) ldg_vec<HPL>(row_ptr(erh, id[u], er_bytes), erv);
+#pragma unroll
+          for (int k = 0; k < HPL; ++k) e[u][k] = ok ? leaky(elh[k] + erv[k], slope) : -INFINITY;
         }
 #pragma unroll
-        for (int u = 0; u < kLlhUnroll; ++u) {
+        for (int u = 0; u < kU; ++u) {
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (active && (j + u) < n) v[u] = ld_row_f32x4(row_ptr(zf, id[u], row_bytes), pol_keep);
         }
-        if (bounded) {
+        if (!bounded) {
+          // online softmax: new running maximum per head, rescale what has been accumulated.  A head that has
+          // seen no edge yet (mn = -inf) keeps its zeros.
+          float sc[HPL];
 #pragma unroll
-          for (int u = 0; u < kLlhUnroll; ++u) {
-            const float p = __expf(e[u] - m);          // e = -inf for the padding: p = 0
-            s += p;
-            fma4(acc, p, v[u]);
+          for (int k = 0; k < HPL; ++k) {
+            float bm = e[0][k];
+#pragma unroll
+            for (int u = 1; u < kU; ++u) bm = fmaxf(bm, e[u][k]);
+            const float mn = fmaxf(m[k], bm);
+            sc[k] = (mn == -INFINITY) ? 1.f : expf(m[k] - mn);          // m = -inf on the first group: sc = 0, acc and s are 0 anyway
+            s[k] *= sc[k];
+            m[k] = mn;
           }
-        } else {
-          float bm = e[0];
+          acc.x *= sc[head_of<HPL>(0)]; acc.y *= sc[head_of<HPL>(1)];
+          acc.z *= sc[head_of<HPL>(2)]; acc.w *= sc[head_of<HPL>(3)];
+        }
 #pragma unroll
-          for (int u = 1; u < kLlhUnroll; ++u) bm = fmaxf(bm, e[u]);
-          const float mn = fmaxf(m, bm);
-          if (mn != -INFINITY) {          // at least one edge seen so far
-            const float sc = expf(m - mn);          // m = -inf on the first group: sc = 0, acc and s are 0 anyway
-            acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
-            s *= sc;
-            m = mn;
+        for (int u = 0; u < kU; ++u) {
+          // e = -inf for the padding of the last group: p = 0.  ex2.approx path: the argument is <= 0 and terms
+          // that matter have small |e - m|; relative error < 2e-6, inside the 1e-5 tolerance
+          float p[HPL];
 #pragma unroll
-            for (int u = 0; u < kLlhUnroll; ++u) {
-              // e = -inf for the padding of the last group: p = 0.  ex2.approx path: the argument is <= 0 and
-              // terms that matter have small |e - mn|; relative error < 2e-6, inside the 1e-5 tolerance
-              const float p = __expf(e[u] - mn);
-              s += p;
-              fma4(acc, p, v[u]);
-            }
+          for (int k = 0; k < HPL; ++k) {
+            p[k] = (m[k] == -INFINITY) ? 0.f : __expf(e[u][k] - m[k]);
+            s[k] += p[k];
           }
+          acc.x = fmaf(p[head_of<HPL>(0)], v[u].x, acc.x); acc.y = fmaf(p[head_of<HPL>(1)], v[u].y, acc.y);
+          acc.z = fmaf(p[head_of<HPL>(2)], v[u].z, acc.z); acc.w = fmaf(p[head_of<HPL>(3)], v[u].w, acc.w);
         }
       }
       __syncwarp();
     }
-    const bool head_leader = active && (fo % d) == 0;       // one lane per head publishes the statistics
+    // who publishes a head's statistics: the first lane of the head (width >= 4), or the one lane that owns it
+    const bool head_leader = active && (HPL > 1 || (fo % d) == 0);
     const bool chained = have && it.w >= 0;
     for_groups_in_order<LANES>(lane, chained, [&]() {
       bool last = true;
@@ -1171,34 +1201,51 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
           __syncwarp(group_mask<LANES>(lane));
           if (active) {
             const float* prev = wl.partials + int64_t(it.w - 1) * pstride;
-            const float pm = ld_state_f32(prev + stats + head), ps = ld_state_f32(prev + stats + heads + head);
-            const float mn = fmaxf(pm, m);
-            const float t = (mn == -INFINITY) ? 0.f : expf(fminf(pm, m) - mn);      // the other factor is exp(0) = 1
-            const float a = (pm == -INFINITY) ? 0.f : (pm == mn ? 1.f : t);
-            const float b = (m == -INFINITY) ? 0.f : (m == mn ? 1.f : t);
+            float a[HPL], b[HPL];
+#pragma unroll
+            for (int k = 0; k < HPL; ++k) {
+              const float pm = ld_state_f32(prev + stats + head + k), ps = ld_state_f32(prev + stats + heads + head + k);
+              const float mn = fmaxf(pm, m[k]);
+              const float t = (mn == -INFINITY) ? 0.f : expf(fminf(pm, m[k]) - mn);      // the other factor is exp(0) = 1
+              a[k] = (pm == -INFINITY) ? 0.f : (pm == mn ? 1.f : t);
+              b[k] = (m[k] == -INFINITY) ? 0.f : (m[k] == mn ? 1.f : t);
+              s[k] = fmaf(ps, a[k], s[k] * b[k]);
+              m[k] = mn;
+            }
             const float4 p = ld_state_f32x4(prev + fo);
-            s = fmaf(ps, a, s * b);
-            m = mn;
-            acc.x = fmaf(p.x, a, acc.x * b); acc.y = fmaf(p.y, a, acc.y * b);
-            acc.z = fmaf(p.z, a, acc.z * b); acc.w = fmaf(p.w, a, acc.w * b);
+            acc.x = fmaf(p.x, a[head_of<HPL>(0)], acc.x * b[head_of<HPL>(0)]);
+            acc.y = fmaf(p.y, a[head_of<HPL>(1)], acc.y * b[head_of<HPL>(1)]);
+            acc.z = fmaf(p.z, a[head_of<HPL>(2)], acc.z * b[head_of<HPL>(2)]);
+            acc.w = fmaf(p.w, a[head_of<HPL>(3)], acc.w * b[head_of<HPL>(3)]);
           }
         }
         if (!last) {
           float* part = wl.partials + int64_t(it.w) * pstride;
           if (active) *reinterpret_cast<float4*>(part + fo) = acc;
           if (head_leader) {
-            part[stats + head] = m;
-            part[stats + heads + head] = s;
+#pragma unroll
+            for (int k = 0; k < HPL; ++k) {
+              part[stats + head + k] = m[k];
+              part[stats + heads + head + k] = s[k];
+            }
           }
           __syncwarp(group_mask<LANES>(lane));          // the group's stores happen-before lane 0's release
           if (l == 0) chain_publish(flags + it.w);
         }
       }
       if (last && active) {
-        st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, s > 0.f ? 1.f / s : 0.f, epilogue));
+        float inv[HPL];
+#pragma unroll
+        for (int k = 0; k < HPL; ++k) inv[k] = s[k] > 0.f ? 1.f / s[k] : 0.f;
+        st_stream_f32x4(out + int64_t(it.x) * ldo + fo,
+                        make_float4(apply_epilogue(acc.x * inv[head_of<HPL>(0)], epilogue), apply_epilogue(acc.y * inv[head_of<HPL>(1)], epilogue),
+                                    apply_epilogue(acc.z * inv[head_of<HPL>(2)], epilogue), apply_epilogue(acc.w * inv[head_of<HPL>(3)], epilogue)));
         if (head_leader) {
-          if (rowmax) rowmax[int64_t(it.x) * heads + head] = (count > 0 || it.w >= 0) && m != -INFINITY ? m : 0.f;
-          if (rowsum) rowsum[int64_t(it.x) * heads + head] = s;
+#pragma unroll
+          for (int k = 0; k < HPL; ++k) {
+            if (rowmax) rowmax[int64_t(it.x) * heads + head + k] = (count > 0 || it.w >= 0) && m[k] != -INFINITY ? m[k] : 0.f;
+            if (rowsum) rowsum[int64_t(it.x) * heads + head + k] = s[k];
+          }
         }
       }
     });
@@ -1590,9 +1637,11 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
   }
   // the bound path does not track the true row maximum: callers that want it back run the online softmax
   if (rowmax != nullptr) er_stats = nullptr;
-  // H <= 4: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8 or an unusual H:
-  // lane-local-head kernel (any H with (f/H) % 4 == 0, constant register footprint; fp32 tables only)
-  const bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
+  // H <= 4 with whole pieces per head: staged kernel (all heads per lane, softmax once per 32-edge batch);  H >= 8, an
+  // unusual H or heads narrower than a piece: lane-local-head kernel (per-head width a multiple of 4, or 2, or 1;
+  // constant register footprint; fp32 tables only)
+  bool staged = !GTA_GAT_FORCE_LLH && (heads == 1 || heads == 2 || heads == 4);
+  if constexpr (sizeof(T) == 4) staged = staged && (f / heads) % 4 == 0;
   if (staged) {
     if constexpr (sizeof(T) == 4) {
       rc = gat_run<F32x4>(who, heads, st, wl, ex, el, er, lder, slope, z, ldz, out, ldo, f, epilogue, rowmax, rowsum,
@@ -1606,16 +1655,24 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
     }
     if (rc != GTA_OK) return rc;
   } else if constexpr (sizeof(T) == 4) {
-    if ((f / heads) % 4 != 0) {
-      set_error("%s: per-head width f/heads=%d is not a multiple of 4", who, f / heads);
+    const int width = f / heads;
+    const int hpl = width % 4 == 0 ? 1 : (width == 2 ? 2 : (width == 1 ? 4 : 0));      // heads per 4-feature lane
+    if (hpl == 0) {
+      set_error("%s: per-head width f/heads=%d is neither a multiple of 4 nor 2 nor 1", who, width);
       return GTA_ERR_UNSUPPORTED;
     }
     const int lanes = lanes_for(f, 4);
-#define GTA_LLH(L)                                                                                                  \
-  gat_aggregate_llh_kernel<L><<<persistent_grid(gat_aggregate_llh_kernel<L>, wl, L, f, ex), kAggThreads, 0, \
-                                st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L>, wl, L)), ex, el,   \
-                                      er, lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f,                     \
-                                      epilogue, rowmax, rowsum, er_stats, stats_pitch, col_block)
+#define GTA_LLH2(L, HP)                                                                                                 \
+  gat_aggregate_llh_kernel<L, HP><<<persistent_grid(gat_aggregate_llh_kernel<L, HP>, wl, L, f, ex), kAggThreads, 0,      \
+                                    st>>>(with_take(wl, take_for(gat_aggregate_llh_kernel<L, HP>, wl, L)), ex, el, er,   \
+                                          lder, heads, slope, z, uint32_t(ldz) * 4u, out, ldo, f, epilogue, rowmax,      \
+                                          rowsum, er_stats, stats_pitch, col_block)
+#define GTA_LLH(L)                                                                                                      \
+  do {                                                                                                                  \
+    if (hpl == 1) GTA_LLH2(L, 1);                                                                                       \
+    else if (hpl == 2) GTA_LLH2(L, 2);                                                                                  \
+    else GTA_LLH2(L, 4);                                                                                                \
+  } while (0)
     switch (lanes) {
       case 4: GTA_LLH(4); break;
       case 8: GTA_LLH(8); break;
@@ -1623,6 +1680,7 @@ static int gat_aggregate_impl(const char* who, const int32_t* items_, int64_t nu
       default: GTA_LLH(32); break;
     }
 #undef GTA_LLH
+#undef GTA_LLH2
   } else {
     set_error("%s: %d heads on a bf16 table has no kernel yet (fp32 tables: any head count)", who, heads);
     return GTA_ERR_UNSUPPORTED;

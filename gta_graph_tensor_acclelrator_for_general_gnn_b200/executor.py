@@ -218,6 +218,13 @@ class _Run:
         self.kernel_log.append(("gta_edge_binary_f32", v.pos))
         return k.edge_binary(self.g, code, ta, ka, tb, kb)
 
+    def _single_pass_head_width(self, f: int, heads: int) -> bool:
+        """Shapes the single-pass GAT kernels take: per-head width of whole 4-feature pieces, or -- fp32 tables of
+        whole pieces only -- heads of 1 or 2 features (layer 3 of the reference's GAT, F = H = 16:
+        ``genGraphOP.py:31-32,50``).  Anything else runs on the generic kernels."""
+        width = f // heads
+        return width % 4 == 0 or (width in (1, 2) and f % 4 == 0 and self.o["feature_dtype"] == torch.float32)
+
     def _gat_single_pass(self, numer: Value, z_value: Value, epilogue: int, pos: int):
         sm = self._is_softmax_numerator(numer)
         el = self.force(sm[0])
@@ -334,7 +341,7 @@ class _Run:
                 if (den.kind == "scatter" and den.side == "R" and den.args[0].kind == "gather"
                         and den.args[0].side == "R" and den.args[0].args[0] is p and not p.forced and not den.args[0].forced
                         and self._is_softmax_numerator(p) is not None and xv.width % p.width == 0
-                        and (xv.width // p.width) % 4 == 0):
+                        and self._single_pass_head_width(xv.width, p.width)):
                     return self._gat_single_pass(p, xv, epilogue, v.pos)
                 if den.kind == "scatter" and den.side == "R" and p.width == den.width:
                     x = self.o["source_table"](k.to_table(self.force(xv)))
@@ -411,7 +418,7 @@ class _Run:
         xv, wv = sp
         if wv is not den.args[0] or wv.forced or self._is_softmax_numerator(wv) is None:
             return None
-        if xv.width % wv.width or (xv.width // wv.width) % 4:
+        if xv.width % wv.width or not self._single_pass_head_width(xv.width, wv.width):
             return None
         return self._gat_single_pass(wv, xv, epilogue, v.pos)
 

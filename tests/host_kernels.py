@@ -107,6 +107,11 @@ def gat_logits(g, el, er, slope=LEAKY_SLOPE, stabilize=True):
 
 def gat_aggregate(g, el, er, z, slope=LEAKY_SLOPE, epilogue=_cabi.EPI_ELU, sched=None, out=None,
                   want_stats=False, block_events=None, bounded=True, exchange=None):
+    # the shapes gta_gat_aggregate_f32 takes (csrc/aggregate.cu): the double must refuse what the library refuses, or
+    # the CPU fuzz cannot see an executor that routes an unsupported shape to the fused kernel
+    f, heads = int(z.shape[1]), int(el.shape[1])
+    if f % 4 or f % heads or not ((f // heads) % 4 == 0 or f // heads in (1, 2)):
+        raise _cabi.GtaError(f"gta_gat_aggregate_f32 (test double): f={f} heads={heads} has no kernel")
     p, rowmax, rowsum = gat_logits(g, el, er, slope, True)
     alpha = p / rowsum[_rows(g)]
     res = _epilogue(_segment_sum(z[g.indices.long()] * _spread(alpha, z.shape[1]), g), epilogue)

@@ -74,10 +74,9 @@ def test_golden_program_dataflow(host, prog, fuse):
         assert_close_rowscale(out[p].numpy(), y64, ref.scale[p], what=str(names))
     if prog["network"] == "GAT" and fuse:
         f_out, heads = op_info[0]["OUTPUT"]["size_per_feature"] // 4, op_info[1]["OUTPUT"]["size_per_feature"] // 4
-        if (f_out // heads) % 4 == 0:
-            assert "gta_gat_aggregate_f32" in names and not any(k.startswith("gta_edge_") for k in names), names
-        else:
-            assert "gta_gat_logits_f32" in names, names
+        # one pass whatever the layer: whole pieces per head, or the narrow heads of layer 3 (F = H = 16)
+        assert (f_out // heads) % 4 == 0 or f_out // heads in (1, 2)
+        assert "gta_gat_aggregate_f32" in names and not any(k.startswith("gta_edge_") for k in names), names
     if prog["network"] in ("GCN", "SGC", "GraphSAGE", "GIN"):
         assert any(k.startswith("gta_aggregate_f32") for k in names), names
         if fuse:

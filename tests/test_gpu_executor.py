@@ -90,11 +90,10 @@ def test_program_matches_oracle(rt, prog, fuse):
     names = [k for k, _ in log]
     if prog["network"] == "GAT" and fuse:
         f_out, heads = op_info[0]["OUTPUT"]["size_per_feature"] // 4, op_info[1]["OUTPUT"]["size_per_feature"] // 4
-        if (f_out // heads) % 4 == 0:
-            assert "gta_gat_aggregate_f32" in names, names     # the edge phase collapsed to one pass
-            assert not any(k.startswith("gta_edge_") for k in names), names
-        else:       # layer 3 of the reference's GAT (F = H = 16): one feature per head, generic kernels
-            assert "gta_gat_logits_f32" in names, names
+        # the edge phase collapsed to one pass -- layer 3 of the reference's GAT (F = H = 16, one feature per head) too
+        assert (f_out // heads) % 4 == 0 or f_out // heads in (1, 2)
+        assert "gta_gat_aggregate_f32" in names, names
+        assert not any(k.startswith("gta_edge_") for k in names), names
     if prog["network"] in ("GCN", "SGC", "GraphSAGE", "GIN"):
         assert any(k.startswith("gta_aggregate_f32") for k in names), names
         if fuse:        # E x Fin scatters stay virtual: no materialising copy, no generic edge kernel

@@ -216,7 +216,9 @@ def test_aggregate_scalar_weight(T, name, n, e, seed, i0, f, chunk, col_block):
 
 
 @pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
-@pytest.mark.parametrize("f,heads", [(128, 4), (128, 8), (128, 16), (128, 1), (64, 4), (64, 16), (16, 4), (16, 2), (256, 8)])
+@pytest.mark.parametrize("f,heads", [(128, 4), (128, 8), (128, 16), (128, 1), (64, 4), (64, 16), (16, 4), (16, 2), (256, 8),
+                                     # heads narrower than a 4-feature piece (layer 3 of the reference's GAT: F = H = 16)
+                                     (16, 16), (16, 8), (8, 4), (8, 8), (32, 16), (4, 4), (4, 2), (64, 32)])
 @pytest.mark.parametrize("chunk,col_block", [(32, 0), (1024, 0), (64, 500), (1024, 60)])
 def test_gat_single_pass(T, name, n, e, seed, i0, f, heads, chunk, col_block):
     g = _graph(name, n, e, seed, i0)
@@ -261,7 +263,7 @@ def test_er_stats_codes(T):
     assert T.k.er_stats(_dev(T, np.zeros((8, 3), np.float32))) is None          # 3 heads: no power of two
 
 
-@pytest.mark.parametrize("heads,f", [(4, 128), (8, 128), (2, 16)])
+@pytest.mark.parametrize("heads,f", [(4, 128), (8, 128), (2, 16), (16, 16), (8, 16)])
 @pytest.mark.parametrize("col_block", [0, 700])
 def test_gat_bound_falls_back_when_the_er_range_is_wide(T, heads, f, col_block):
     """Source logits spanning far more than the bound path's exponent budget (60): those column blocks must take the
@@ -348,9 +350,12 @@ def test_errors_are_loud(T):
     x = T.torch.zeros((64, 6), device="cuda")           # width not a multiple of 4
     with pytest.raises(T.cabi.GtaError):
         T.k.aggregate(dg, x)
-    with pytest.raises(T.cabi.GtaUnsupported):            # per-head width 2 has no kernel yet
+    with pytest.raises(T.cabi.GtaUnsupported):            # per-head width 3: neither whole pieces nor 2 nor 1
+        T.k.gat_aggregate(dg, T.torch.zeros((64, 4), device="cuda"), T.torch.zeros((64, 4), device="cuda"),
+                          T.torch.zeros((64, 12), device="cuda"))
+    with pytest.raises(T.cabi.GtaUnsupported):            # narrow heads on a bf16 table have no kernel
         T.k.gat_aggregate(dg, T.torch.zeros((64, 8), device="cuda"), T.torch.zeros((64, 8), device="cuda"),
-                          T.torch.zeros((64, 16), device="cuda"))
+                          T.k.to_table(T.torch.zeros((64, 16), device="cuda", dtype=T.torch.bfloat16)))
     with pytest.raises(RuntimeError):
         T.k.aggregate(dg, T.torch.zeros((64, 8)))          # CPU tensor: no CPU fallback
 
