@@ -78,6 +78,8 @@ SIGNATURES = {
     "gta_gemm_get_mode": (C.c_int, []),
     "gta_aggregate_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _i32, _p, _i32, _p, _p, _i64, _p, _i64, _i32, _i32,
                                     _p, _p, _p, _i32, _p]),
+    "gta_aggregate_edge_sum_f32": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _i32, _f32, _p, _i64,
+                                             _i32, _i32, _p, _p, _i32, _p]),
     "gta_gat_partial_stride": (_i32, [_i32, _i32]),
     "gta_gather_peak_probe": (C.c_int, [_p, _i64, _i64, _i32, _i64, _p, _p]),
     "gta_er_stats": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _p]),

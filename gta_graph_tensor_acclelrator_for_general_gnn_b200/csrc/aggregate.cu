@@ -1254,6 +1254,111 @@ gat_aggregate_llh_kernel(const WorkList wl, const Exchange ex, const float* __re
 }
 
 // ----------------------------------------------------------------------------------------
+// Edge phase "sum of three, then a unary, then the row sum" in one pass (PNA ops 5-8,
+// genGraphOP.py:110-147:  gather_R( SF( edge + scatterC(a) + scatterR(b) ) )):
+//     out[i, :] = epilogue( sum_{k in row i} unary( edge[k, :] + x[src_k, :] + rowterm[i, :] ) )
+// Any of the three terms may be absent.  The generic path materialises three E x F tensors (two adds and the
+// unary) before the segment sum; here the E x F operand is read once, streaming, and nothing E x F is written.
+// Same work list, dynamic item fetch and slot chain as aggregate_kernel; the reduction is the plain ascending
+// edge order per lane.  A lane moves one 16-byte piece of every row it touches.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float edge_unary_value(float v, int unary, float slope) {
+  if (unary == GTA_UN_RELU) return fmaxf(v, 0.f);
+  if (unary == GTA_UN_ELU) return elu1(v);
+  if (unary == GTA_UN_EXP_LEAKY_RELU) return expf(leaky(v, slope));
+  return v;
+}
+template <int LANES, bool HAS_X, bool HAS_E>
+__global__ void __launch_bounds__(kAggThreads, 8)
+edge_sum_kernel(const WorkList wl, const Exchange ex, const float* __restrict__ edge, int64_t lde,
+                const float* __restrict__ x, const uint32_t row_bytes, const float* __restrict__ rowterm, int64_t ldr,
+                int unary, float slope, float* __restrict__ out, int64_t ldo, int f, int epilogue) {
+  constexpr int kU = 4;
+  __shared__ uint32_t s_id[kAggWarps][32];
+  const int lane = threadIdx.x & 31;
+  const int l = lane & (LANES - 1);
+  const int fo = blockIdx.y * (LANES * 4) + 4 * l;
+  uint32_t* sid = s_id[threadIdx.x >> 5];
+  const uint32_t* mine = sid + (lane & ~(LANES - 1));
+  int32_t* counter = wl.work_counter + blockIdx.y;
+  int32_t* flags = wl.chain_flags + int64_t(blockIdx.y) * wl.num_slots;
+  const uint64_t pol_stream = wl.pol_stream, pol_keep = wl.pol_keep;
+
+  ItemCursor cur = cursor_begin<LANES>(wl, ex, counter, lane);
+  while (cur.first < wl.num_items) {
+    const int64_t group = int64_t(cur.first) + lane / LANES;
+    const bool have = group < wl.num_items;
+    const bool active = have && fo < f;
+    const int4 it = have ? __ldg(wl.items + group) : make_int4(0, 0, 0, -1);
+    const int count = have ? it.z : 0;
+    const int max_count = (LANES == 32) ? count : warp_max_i32(count);
+    const int32_t* idx_base = wl.indices + it.y;
+    const float* xf = HAS_X ? x + (active ? fo : 0) : nullptr;
+    const float* ef = HAS_E ? edge + int64_t(it.y) * lde + (active ? fo : 0) : nullptr;
+    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && rowterm != nullptr) r4 = __ldg(reinterpret_cast<const float4*>(rowterm + int64_t(it.x) * ldr + fo));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int idx_nxt = 0;
+    if (HAS_X && l < count) idx_nxt = ld_stream_i32(idx_base + l, pol_stream);
+    for (int base = 0; base < max_count; base += LANES) {
+      int n = count - base;
+      n = n < 0 ? 0 : (n > LANES ? LANES : n);
+      if (HAS_X) {
+        sid[lane] = uint32_t(idx_nxt);
+        if (base + LANES + l < count) idx_nxt = ld_stream_i32(idx_base + base + LANES + l, pol_stream);
+        __syncwarp();
+      }
+      const int nmax = (LANES == 32) ? n : LANES;
+#pragma unroll 1
+      for (int j = 0; j < nmax; j += kU) {
+        float4 xv[kU], ev[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const bool ok = active && (j + u) < n;
+          xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (HAS_X && ok) xv[u] = ld_row_f32x4(row_ptr(xf, mine[(j + u) & (LANES - 1)], row_bytes), pol_keep);
+          if (HAS_E && ok) ev[u] = ld_gather_f32x4(ef + int64_t(base + j + u) * lde, pol_stream);          // streamed: read once, evict first
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          if ((j + u) < n) {          // a padded slot would contribute unary(rowterm), not 0
+            acc.x += edge_unary_value(ev[u].x + xv[u].x + r4.x, unary, slope);
+            acc.y += edge_unary_value(ev[u].y + xv[u].y + r4.y, unary, slope);
+            acc.z += edge_unary_value(ev[u].z + xv[u].z + r4.z, unary, slope);
+            acc.w += edge_unary_value(ev[u].w + xv[u].w + r4.w, unary, slope);
+          }
+        }
+      }
+      if (HAS_X) __syncwarp();
+    }
+    const bool chained = have && it.w >= 0;
+    for_groups_in_order<LANES>(lane, chained, [&]() {
+      bool last = true;
+      if (chained) {
+        const int s0 = __ldg(wl.row_slots + it.x), s1 = __ldg(wl.row_slots + it.x + 1);
+        last = it.w == s1 - 1;
+        if (it.w != s0) {
+          if (l == 0) chain_wait(flags + it.w - 1);
+          __syncwarp(group_mask<LANES>(lane));
+          if (active) {
+            const float4 p = ld_state_f32x4(wl.partials + int64_t(it.w - 1) * f + fo);
+            acc.x = p.x + acc.x; acc.y = p.y + acc.y; acc.z = p.z + acc.z; acc.w = p.w + acc.w;
+          }
+        }
+        if (!last) {
+          if (active) *reinterpret_cast<float4*>(wl.partials + int64_t(it.w) * f + fo) = acc;
+          __syncwarp(group_mask<LANES>(lane));          // the group's stores happen-before lane 0's release
+          if (l == 0) chain_publish(flags + it.w);
+        }
+      }
+      if (last && active) st_stream_f32x4(out + int64_t(it.x) * ldo + fo, epilogue4(acc, 1.f, epilogue));
+    });
+    cursor_next<LANES>(cur, wl, counter, lane);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // Roofline denominator of the gather kernels: random whole-row gathers from a table that fits L2, with the
 // kernels' own load instruction (one 128-bit load per lane, L1 no-allocate, L2 evict_last), 8 in flight per
 // lane, ids from a hash so nothing else touches memory.  bench.py reports gather bytes / time of the real
@@ -1714,6 +1819,58 @@ int gta_aggregate_bf16(const int32_t* items, int64_t num_items, const int32_t* r
   return aggregate_impl<__nv_bfloat16>("gta_aggregate_bf16", items, num_items, row_slots, num_slots, indices, wmode, w, wh,
                                        rowden, static_cast<const __nv_bfloat16*>(x), ldx, out, ldo, f, epilogue, partials,
                                        chain_state, exchange, phases, stream);
+}
+
+int gta_aggregate_edge_sum_f32(const int32_t* items_, int64_t num_items, const int32_t* row_slots, int64_t num_slots,
+                               const int32_t* indices, const float* edge, int64_t lde, const float* x, int64_t ldx,
+                               const float* rowterm, int64_t ldr, int32_t unary, float slope, float* out, int64_t ldo,
+                               int32_t f, int32_t epilogue, float* partials, int32_t* chain_state, int32_t phases,
+                               void* stream_) {
+  const char* who = "gta_aggregate_edge_sum_f32";
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  GTA_REQUIRE(f > 0 && f % 4 == 0, "%s: f=%d must be a positive multiple of 4 (pad the table)", who, f);
+  GTA_REQUIRE(num_items >= 0 && num_items < (int64_t(1) << 31) - 64, "%s: bad item count", who);
+  WorkList wl{reinterpret_cast<const int4*>(items_), num_items, row_slots, num_slots, indices, partials, nullptr, nullptr, 1, 0, 0};
+  int rc = prepare_worklist(who, wl, chain_state, f, phases, st);
+  if (rc != GTA_OK) return rc;
+  if (num_items == 0 || !(phases & GTA_PHASE_MAIN)) return GTA_OK;
+  GTA_REQUIRE(items_ && out && (edge || x || rowterm), "%s: null pointer (at least one of edge / x / rowterm is needed)", who);
+  GTA_REQUIRE(!x || indices, "%s: indices are required to gather x", who);
+  GTA_REQUIRE(unary >= GTA_UN_EXP_LEAKY_RELU && unary <= GTA_UN_COPY, "%s: bad unary %d", who, unary);
+  GTA_REQUIRE(ldo % 4 == 0 && ldo >= f && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "%s: out must be 16-byte aligned rows >= f", who);
+  GTA_REQUIRE(!edge || (lde % 4 == 0 && lde >= f && (reinterpret_cast<uintptr_t>(edge) & 15) == 0),
+              "%s: edge must be 16-byte aligned rows >= f", who);
+  GTA_REQUIRE(!x || (ldx % 4 == 0 && ldx >= f && ldx * 4 < (int64_t(1) << 32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0),
+              "%s: x must be 16-byte aligned rows >= f, a row below 4 GiB", who);
+  GTA_REQUIRE(!rowterm || (ldr % 4 == 0 && ldr >= f && (reinterpret_cast<uintptr_t>(rowterm) & 15) == 0),
+              "%s: rowterm must be 16-byte aligned rows >= f", who);
+  Exchange ex;
+  memset(&ex, 0, sizeof(ex));
+#define GTA_ES2(L, HX, HE)                                                                                          \
+  do {                                                                                                              \
+    auto kern = edge_sum_kernel<L, HX, HE>;                                                                         \
+    dim3 grid = persistent_grid(kern, wl, L, 1, ex);                                                                \
+    grid.y = (unsigned)((f + 127) / 128);                                                                           \
+    kern<<<grid, kAggThreads, 0, st>>>(with_take(wl, take_for(kern, wl, L)), ex, edge, lde, x, uint32_t(ldx * 4),   \
+                                       rowterm, ldr, unary, slope, out, ldo, f, epilogue);                          \
+  } while (0)
+#define GTA_ES(L)                                                                                                   \
+  do {                                                                                                              \
+    if (x && edge) GTA_ES2(L, true, true);                                                                          \
+    else if (x) GTA_ES2(L, true, false);                                                                            \
+    else if (edge) GTA_ES2(L, false, true);                                                                         \
+    else GTA_ES2(L, false, false);                                                                                  \
+  } while (0)
+  switch (lanes_for(f, 4)) {
+    case 4: GTA_ES(4); break;
+    case 8: GTA_ES(8); break;
+    case 16: GTA_ES(16); break;
+    default: GTA_ES(32); break;
+  }
+#undef GTA_ES
+#undef GTA_ES2
+  GTA_CHECK_LAUNCH("edge_sum_kernel");
+  return GTA_OK;
 }
 
 int gta_gather_peak_probe(const float* table, int64_t rows, int64_t ld, int32_t f, int64_t gathers_per_group,

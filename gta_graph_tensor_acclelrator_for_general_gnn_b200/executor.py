@@ -271,17 +271,7 @@ class _Run:
         destinations' part is the row's own value times its degree -- no edge tensor at all (the generic path makes
         five passes over E x F for DGN)."""
         k = kernels
-
-        def total(vals):
-            t = None
-            for val in vals:
-                cur = k.to_table(self.force(val.args[0]))
-                if t is None:
-                    t = cur
-                else:
-                    self.kernel_log.append(("gta_node_binary_f32", pos))
-                    t = k.node_binary(_cabi.BIN_ADD, t, cur)
-            return t
+        total = lambda vals: self._sum_node_tables(vals, pos)
         by_src = [l for l in leaves if l.side == "C"]
         by_dst = [l for l in leaves if l.side == "R"]
         out = None
@@ -303,6 +293,60 @@ class _Run:
             self.kernel_log.append(("gta_node_unary_f32", pos))
             own = k.node_unary(_cabi.UN_ELU if epilogue == _cabi.EPI_ELU else _cabi.UN_RELU, own, self.o["slope"])
         return own
+
+    def _sum_node_tables(self, scatters, pos: int):
+        """The node tables behind a list of scatters, added up (None for an empty list)."""
+        t = None
+        for val in scatters:
+            cur = kernels.to_table(self.force(val.args[0]))
+            if t is None:
+                t = cur
+            else:
+                self.kernel_log.append(("gta_node_binary_f32", pos))
+                t = kernels.node_binary(_cabi.BIN_ADD, t, cur)
+        return t
+
+    _EDGE_SUM_UNARY = {"relu": _cabi.UN_RELU, "elu": _cabi.UN_ELU}
+
+    def _edge_sum_terms(self, v: Value):
+        """The operand of a gather_R as ``unary(edge + sum of scatters)`` (PNA ops 5-7, ``genGraphOP.py:110-147``):
+        ``(unary code, C-side scatters, R-side scatters, edge value or None)``, or None when it is not of that form.
+        Every inner node must be lazy, private and not asked for as an output; a pure sum of scatters without a unary
+        is ``_scatter_sum_leaves`` (cheaper: the destinations' part needs no pass over the edges at all)."""
+        def private(a):
+            return not a.forced and a.extra.get("consumers", 1) == 1 and a.pos not in self.o["wanted"]
+        unary = _cabi.UN_COPY
+        if v.kind == "edge_expr" and v.op in self._EDGE_SUM_UNARY and private(v):
+            unary, v = self._EDGE_SUM_UNARY[v.op], v.args[0]
+        if v.kind != "edge_expr" or v.op != "add" or not private(v):
+            return None
+        by_src, by_dst, edges, stack = [], [], [], list(v.args)
+        while stack:
+            a = stack.pop()
+            if a.kind == "scatter" and not a.forced:
+                (by_src if a.side == "C" else by_dst).append(a)
+            elif a.kind == "edge_expr" and a.op == "add" and private(a):
+                stack.extend(a.args)
+            else:
+                edges.append(a)
+        if len(edges) > 1 or not (by_src or by_dst) or (unary == _cabi.UN_COPY and not edges):
+            return None
+        if len({t.width for t in by_src + by_dst + edges}) != 1:
+            return None
+        return unary, by_src, by_dst, (edges[0] if edges else None)
+
+    def _gather_edge_sum(self, terms, epilogue: int, pos: int) -> torch.Tensor:
+        """gather_R(unary(edge + scatterC(a) + scatterR(b))) in ONE pass over the edges: the E x F operand (if any) is
+        read once, the three E x F intermediates of the generic path (two adds, the unary) never exist."""
+        unary, by_src, by_dst, edge = terms
+        k = kernels
+        et = k.to_table(self.force(edge)) if edge is not None else None
+        x = self._sum_node_tables(by_src, pos)
+        if x is not None:
+            x = self.o["source_table"](x)
+        r = self._sum_node_tables(by_dst, pos)
+        self.kernel_log.append(("gta_aggregate_edge_sum_f32", pos))
+        return k.aggregate_edge_sum(self.g, et, x, r, unary, self.o["slope"], epilogue)
 
     def _by_source(self) -> DeviceGraph:
         """The CSC walk as a graph over EDGE ids: row j lists the CSR positions of the edges whose
@@ -332,6 +376,9 @@ class _Run:
         leaves = self._scatter_sum_leaves(src)
         if leaves is not None:
             return self._gather_scatter_sum(leaves, epilogue, v.pos)
+        terms = self._edge_sum_terms(src)
+        if terms is not None:
+            return self._gather_edge_sum(terms, epilogue, v.pos)
         sp = self._split_mul(src)
         if sp is not None:
             xv, wv = sp

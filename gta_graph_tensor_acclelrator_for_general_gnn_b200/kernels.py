@@ -234,6 +234,38 @@ def aggregate(g: DeviceGraph, x: torch.Tensor, w: torch.Tensor | None = None, ro
     return o
 
 
+@_timed("gta_aggregate_edge_sum_f32")
+def aggregate_edge_sum(g: DeviceGraph, edge: torch.Tensor | None = None, x: torch.Tensor | None = None,
+                       rowterm: torch.Tensor | None = None, unary: int = _cabi.UN_COPY, slope: float = LEAKY_SLOPE,
+                       epilogue: int = _cabi.EPI_NONE, sched: Schedule | None = None):
+    """``out[i] = epi(sum_k unary(edge[k] + x[src k] + rowterm[i]))`` in one pass (PNA ops 5-8): ``edge`` [E, F] in
+    CSR edge order, ``x`` [sources, F] gathered by source, ``rowterm`` [N, F]; any may be None (not all).  fp32
+    tables (``to_table``); nothing E x F is written."""
+    lib = _cabi.load()
+    given = [t for t in (edge, x, rowterm) if t is not None]
+    if not given:
+        raise ValueError("aggregate_edge_sum: at least one of edge / x / rowterm")
+    _require_cuda(*given)
+    f = int(given[0].shape[1])
+    if any(int(t.shape[1]) != f or t.dtype != torch.float32 for t in given):
+        raise ValueError("aggregate_edge_sum: fp32 operands of one width")
+    sched = sched or (g.schedule_for(_ld(x) * 4) if x is not None else g.schedule())
+    rows = sched.row_end - sched.row_begin
+    o = alloc_table(rows, f, given[0].device)
+    if f % 4 and all(_ld(t) >= pad_row(f, torch.float32) for t in given + [o]):
+        f = pad_row(f, torch.float32)      # run over the pad columns too (independent columns, never read back)
+    partials, chain = _chain_state(_agg_ws, sched.num_slots, f, f, o.device)
+
+    def launch(first, count, phases):
+        _cabi.check(lib.gta_aggregate_edge_sum_f32(
+            sched.items.data_ptr() + 16 * first, count, _cabi.ptr(sched.row_slots), sched.num_slots, _cabi.ptr(g.indices),
+            _cabi.ptr(edge), _ld(edge) if edge is not None else 0, _cabi.ptr(x), _ld(x) if x is not None else 0,
+            _cabi.ptr(rowterm), _ld(rowterm) if rowterm is not None else 0, unary, slope, _cabi.ptr(o), _ld(o), f,
+            epilogue, partials, chain, phases, _stream()), "gta_aggregate_edge_sum_f32")
+    _launch_blocks(launch, sched, None, g.num_edges)
+    return o
+
+
 _gat_ws = _Workspace()      # chain state of the single-pass GAT kernel
 
 

@@ -263,6 +263,20 @@ int gta_aggregate_f32(const int32_t* items, int64_t num_items, const int32_t* ro
                       int32_t epilogue, float* partials, int32_t* chain_state,
                       const gta_exchange_t* exchange, int32_t phases, void* stream);
 
+/* Edge phase "sum of up to three terms, a unary, the row sum" in one pass -- PNA ops 5-8
+ * (vTCAD/GraphOP/genGraphOP.py:110-147: gather_R(SF(edge + scatterC(a) + scatterR(b)))):
+ *     out[i, :] = epilogue( sum_{k in row i} unary( edge[k, :] + x[src_k, :] + rowterm[i, :] ) )
+ * edge [E, lde] in CSR edge order, x [num_sources, ldx] gathered by source, rowterm [N, ldr]; any of the three
+ * may be NULL (not all).  unary: GTA_UN_* (GTA_UN_COPY = identity; slope for GTA_UN_EXP_LEAKY_RELU).  fp32,
+ * f % 4 == 0, 16-byte aligned rows.  Same work list, chain state and phases as gta_aggregate_f32 (partials:
+ * num_slots * f floats); ascending-edge reduction, bitwise reproducible.  Nothing E x F is written. */
+int gta_aggregate_edge_sum_f32(const int32_t* items, int64_t num_items, const int32_t* row_slots,
+                               int64_t num_slots, const int32_t* indices,
+                               const float* edge, int64_t lde, const float* x, int64_t ldx,
+                               const float* rowterm, int64_t ldr, int32_t unary, float slope,
+                               float* out, int64_t ldo, int32_t f, int32_t epilogue,
+                               float* partials, int32_t* chain_state, int32_t phases, void* stream);
+
 /* Measured ceiling of the gather kernels (roofline denominator, not part of the path): every resident
  * lane group gathers `gathers_per_group` pseudo-random rows of `table` ([rows, ld] fp32, f <= 128 features
  * read per row) with the aggregation kernels' own load instruction and nothing else.  Returns the number of

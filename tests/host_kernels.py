@@ -105,6 +105,22 @@ def gat_logits(g, el, er, slope=LEAKY_SLOPE, stabilize=True):
     return p, rowmax, _segment_sum(p, g)
 
 
+def aggregate_edge_sum(g, edge=None, x=None, rowterm=None, unary=_cabi.UN_COPY, slope=LEAKY_SLOPE,
+                       epilogue=_cabi.EPI_NONE, sched=None):
+    given = [t for t in (edge, x, rowterm) if t is not None]
+    f = int(given[0].shape[1])
+    if any(int(t.shape[1]) != f or t.dtype != torch.float32 for t in given):
+        raise ValueError("aggregate_edge_sum: fp32 operands of one width")
+    v = torch.zeros((g.num_edges, f), dtype=torch.float32)
+    if edge is not None:
+        v = v + edge
+    if x is not None:
+        v = v + x[g.indices.long()]
+    if rowterm is not None:
+        v = v + rowterm[_rows(g)]
+    return _epilogue(_segment_sum(_unary(unary, v, slope), g), epilogue)
+
+
 def gat_aggregate(g, el, er, z, slope=LEAKY_SLOPE, epilogue=_cabi.EPI_ELU, sched=None, out=None,
                   want_stats=False, block_events=None, bounded=True, exchange=None):
     # the shapes gta_gat_aggregate_f32 takes (csrc/aggregate.cu): the double must refuse what the library refuses, or

@@ -148,6 +148,9 @@ def test_dgn_pna_dataflow(host, network, reorder, plan_kind, fuse):
     if network == "PNA" and not reorder and fuse:
         # ops 3/4 = MM(scatter(x)): commuted to scatter(MM(x)) -> two N-row GEMMs, one E-row GEMM (op 2)
         assert names.count("gta_gemm_f32:edges") == 1 and names.count("gta_gemm_f32") == 3, names
+    if network == "PNA" and (fuse or plan_kind == "one-block"):
+        # ops 5-8 = gather(SF(edge + scatterC + scatterR)): one pass over the edges, no E x F intermediate written
+        assert "gta_aggregate_edge_sum_f32" in names and not any(k.startswith("gta_edge_") for k in names), names
 
 
 def test_edge_mm_respects_the_edge_budget(host):

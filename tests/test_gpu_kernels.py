@@ -319,6 +319,41 @@ def test_gat_two_block_path(T, heads, f):
     assert_close_rowscale(out.cpu().numpy(), r["Y"], scale, rtol=2e-5, what="two-block GAT")
 
 
+@pytest.mark.parametrize("name,n,e,seed,i0", GRAPHS)
+@pytest.mark.parametrize("f", [16, 6, 128, 256])
+@pytest.mark.parametrize("terms,unary", [("exr", "relu"), ("exr", "elu"), ("exr", "copy"), ("xr", "relu"), ("e", "relu"),
+                                         ("x", "copy"), ("er", "relu"), ("ex", "elu")])
+@pytest.mark.parametrize("chunk,col_block", [(32, 0), (1024, 60)])
+def test_edge_sum_single_pass(T, name, n, e, seed, i0, f, terms, unary, chunk, col_block):
+    """gta_aggregate_edge_sum_f32 (PNA ops 5-8): out[i] = sum_k unary(edge[k] + x[src k] + rowterm[i]) against fp64."""
+    g = _graph(name, n, e, seed, i0)
+    indptr, indices, _ = O.csr_build(g.dst, g.src, n)
+    rows = O.row_ids(indptr)
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    rng = np.random.default_rng(seed + f)
+    edge = rng.standard_normal((len(indices), f), dtype=np.float32) if "e" in terms else None
+    x = rng.standard_normal((n, f), dtype=np.float32) if "x" in terms else None
+    r = rng.standard_normal((n, f), dtype=np.float32) if "r" in terms else None
+    v = np.zeros((len(indices), f))
+    sc = np.zeros((len(indices), f))
+    for t, sel in ((edge, slice(None)), (x, indices), (r, rows)):
+        if t is not None:
+            v = v + t[sel].astype(np.float64)
+            sc = sc + np.abs(t[sel]).astype(np.float64)
+    y64 = O.segment_sum({"relu": lambda a: np.maximum(a, 0), "elu": O.elu, "copy": lambda a: a}[unary](v), indptr)
+    scale = O.segment_sum(sc, indptr)
+    code = {"relu": T.cabi.UN_RELU, "elu": T.cabi.UN_ELU, "copy": T.cabi.UN_COPY}[unary]
+    tab = lambda a: None if a is None else T.k.to_table(_dev(T, a))
+    sched = dg.schedule(chunk, col_block)
+    out = T.k.aggregate_edge_sum(dg, tab(edge), tab(x), tab(r), code, sched=sched)
+    assert out.shape == (n, f)
+    assert T.torch.equal(out, T.k.aggregate_edge_sum(dg, tab(edge), tab(x), tab(r), code, sched=sched)), "not reproducible"
+    assert_close_rowscale(out.cpu().numpy(), y64, scale, what=f"edge sum {terms} {unary} f={f} chunk={chunk}")
+    # with an applynode epilogue on top
+    out_e = T.k.aggregate_edge_sum(dg, tab(edge), tab(x), tab(r), code, epilogue=T.cabi.EPI_RELU, sched=sched)
+    assert_close_rowscale(out_e.cpu().numpy(), np.maximum(y64, 0), scale, what="edge sum + ReLU epilogue")
+
+
 def test_generic_edge_and_node_ops(T):
     g = _graph("tiny", 64, 300, 1, 5.0)
     n = g.num_nodes

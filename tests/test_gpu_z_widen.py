@@ -39,6 +39,9 @@ def test_dgn_pna_match_oracle(network, reorder, plan_kind, fuse):
         assert any(k == "gta_aggregate_f32:scatter_sum" for k, _ in log), log
     else:
         assert any(k == "gta_gemm_f32:edges" for k, _ in log)
+    if network == "PNA" and (fuse or plan_kind == "one-block"):      # ops 5-8 in one pass, nothing E x F written after op 2
+        assert any(k == "gta_aggregate_edge_sum_f32" for k, _ in log), log
+        assert not any(k.startswith("gta_edge_") for k, _ in log), log
 
 
 def test_npz_ingest_matches_scipy(tmp_path):
