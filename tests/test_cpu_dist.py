@@ -209,6 +209,10 @@ def _worker_execute(rank, world, port, prog_file, op_file, network, reorder, rot
 @pytest.mark.parametrize("name,network,reorder", [
     ("GAT-cora-layer1-original__0-1-2_4-5-6-7-8_3-9-10-11-12-13", "GAT", False),
     ("GCN-cora-layer1-trans__0_1-2-3", "GCN", True),
+    # the linear DGN edge phase (degree x own rows uses the LOCAL degrees) and PNA's one-pass edge sum (gathered rows
+    # through the exchange, row term and edge features local) in a partitioned run
+    ("DGN-cora-layer2-original__0-1-2-3-4-5-6-7-8-9-10", "DGN", False),
+    ("PNA-cora-layer2-original__0-1-2-3-4-5-6-7-8-9-10", "PNA", False),
 ])
 def test_partitioned_execute_world2_gloo(tmp_path, name, network, reorder, rotate):
     """Destination-range partition, one replication of the source-side table per layer: the rows two ranks
@@ -218,7 +222,7 @@ def test_partitioned_execute_world2_gloo(tmp_path, name, network, reorder, rotat
     mode = "trans" if reorder else "original"
     port = _free_port()
     mp.spawn(_worker_execute, args=(2, port, os.path.join(golden, "isa", name + ".yaml"),
-                                    os.path.join(golden, "opgraph", f"{network}-cora-layer1-{mode}.yaml"), network, reorder,
+                                    os.path.join(golden, "opgraph", f"{'-'.join(name.split('-')[:3])}-{mode}.yaml"), network, reorder,
                                     rotate, str(tmp_path)), nprocs=2, join=True)
     bounds = np.load(tmp_path / "bounds.npy")
     whole, ref = np.load(tmp_path / "y_whole.npy"), np.load(tmp_path / "y_ref.npy")
