@@ -301,3 +301,33 @@ def test_item_size_and_slot_groups_are_functions_of_the_shape_only():
     for world in range(1, 17):
         groups = gdist.slot_groups(world)
         assert groups[0] == [0] and [k for g in groups for k in g] == list(range(world)) and len(groups) <= 3
+
+
+def test_built_library_holds_the_blackwell_instructions_the_design_claims():
+    """Static check of the in-tree libgta_b200.so (no GPU): the GEMM is tcgen05 + TMA + TMEM, the aggregation kernels
+    carry the in-launch exchange (system-scope peer loads and signal stores) and the cp.async item staging -- what
+    DESIGN.md sections 4-5 state and tools/static_evidence.sh prints in full.  A build that silently lost one of
+    these (a fallback path, a dropped -gencode) fails here, before any GPU time is spent."""
+    import shutil
+    import subprocess
+    from gta_graph_tensor_acclelrator_for_general_gnn_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True, check=True).stdout
+    per_fn, fn = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            per_fn[fn] = []
+        elif fn is not None:
+            per_fn[fn].append(line)
+    assert "EF_CUDA_SM100" in sass or "sm_100" in sass
+    has = lambda fn_part, mnemonic: any(fn_part in f and any(mnemonic in ln for ln in body) for f, body in per_fn.items())
+    assert has("gemm_tc_kernel", "UTCHMMA"), "tcgen05.mma missing from gemm_tc_kernel"
+    assert has("gemm_tc_kernel", "UTMALDG"), "TMA loads missing from gemm_tc_kernel"
+    assert has("gemm_tc_kernel", "LDTM"), "tcgen05.ld (TMEM read-back) missing from gemm_tc_kernel"
+    # mangled names (length-prefixed): "16aggregate_kernel" is the weighted aggregate only, not the GAT kernels
+    for kernel in ("3gta20gat_aggregate_kernel", "3gta16aggregate_kernel", "3gta24gat_aggregate_llh_kernel"):
+        assert has(kernel, "STRONG.SYS"), f"{kernel}: no system-scope access -- the exchange is not inside the launch"
+    for kernel in ("3gta20gat_aggregate_kernel", "3gta16aggregate_kernel"):
+        assert has(kernel, "LDGSTS"), f"{kernel}: cp.async staging of the next item is gone"
