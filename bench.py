@@ -538,7 +538,10 @@ def main():
     layers = 2 if second is not None else 1
     value = layers * e / (ms_per_step * 1e-3) / 1e9          # GTEPS per layer: every layer walks all E edges
 
-    # per-kernel durations: the same K steps issued eagerly with CUDA events around every kernel
+    # per-kernel durations: the same K steps issued eagerly with CUDA events around every kernel.  One untimed eager
+    # step first: the timed region above replayed a CUDA graph, so this is the first eager launch on this stream and
+    # it allocates that stream's chain-state workspace (1 GB on RMAT-20) inside what would be the first interval
+    y = step(x_d)
     kernels.EVENT_LOG = []
     lib.gta_launch_count_reset()
     barrier()

@@ -162,13 +162,14 @@ def gemm(x: torch.Tensor, w: torch.Tensor, al: torch.Tensor | None = None, ar: t
 
 #: below this many edges per work item a long list is walked with static striding (GTA_PHASE_STATIC)
 STATIC_ITEM_EDGES = 48
+STATIC_MIN_ITEMS = 1 << 18
 
 
 def _launch_blocks(launch, sched: Schedule, block_events, num_edges: int = 0):
     """One launch for everything, or -- when the gathered table arrives chunk by chunk -- the first column
     block as soon as its chunk has landed and the rest after the last event."""
     if block_events is None:
-        tiny = sched.num_items >= (1 << 18) and num_edges < STATIC_ITEM_EDGES * sched.num_items
+        tiny = sched.num_items >= STATIC_MIN_ITEMS and num_edges < STATIC_ITEM_EDGES * sched.num_items
         launch(0, sched.num_items, _cabi.PHASE_ALL | (_cabi.PHASE_STATIC if tiny else 0))
         return
     if len(block_events) != sched.num_blocks:

@@ -354,6 +354,43 @@ def test_edge_sum_single_pass(T, name, n, e, seed, i0, f, terms, unary, chunk, c
     assert_close_rowscale(out_e.cpu().numpy(), np.maximum(y64, 0), scale, what="edge sum + ReLU epilogue")
 
 
+@pytest.mark.parametrize("chunk,col_block", [(32, 0), (64, 150_000)])
+def test_static_striding_is_the_same_reduction(T, monkeypatch, chunk, col_block):
+    """GTA_PHASE_STATIC (long lists of tiny items, the RMAT shapes: warps stride through the work list instead of
+    taking items from the counter) only changes WHO runs an item, never the reduction: every kernel must return the
+    bits of the dynamic launch.  Forced here on a small graph by lowering the thresholds of kernels._launch_blocks."""
+    # the library strides statically only when a warp gets at least 32 steps (aggregate.cu take_for): with up to 5 920
+    # resident warps that takes 190 k items -- 400 k rows of about 6 edges give one or more items per row
+    g = synthetic.powerlaw_graph(400_000, 2_400_000, seed=3, i0=50.0, name="wide-low-degree")
+    n = g.num_nodes
+    dg = T.graph.csr_from_coo(g.dst, g.src, n)
+    sched = dg.schedule(chunk, col_block)
+    assert sched.num_items >= 32 * 5920
+    rng = np.random.default_rng(11)
+    z = T.k.to_table(_dev(T, rng.standard_normal((n, 128), dtype=np.float32)))
+    z256 = T.k.to_table(_dev(T, rng.standard_normal((n, 256), dtype=np.float32)))
+    zb = T.k.to_table(z.to(T.torch.bfloat16))
+    el, er = _dev(T, rng.standard_normal((n, 4), dtype=np.float32)), _dev(T, rng.standard_normal((n, 4), dtype=np.float32))
+    el16, er16 = _dev(T, rng.standard_normal((n, 16), dtype=np.float32)), _dev(T, rng.standard_normal((n, 16), dtype=np.float32))
+    w = _dev(T, rng.random((g.num_edges, 1), dtype=np.float32))
+    et = T.k.to_table(_dev(T, rng.standard_normal((g.num_edges, 128), dtype=np.float32)))
+    runs = {
+        "aggregate": lambda: T.k.aggregate(dg, z, w, sched=sched),
+        "aggregate 256 wide": lambda: T.k.aggregate(dg, z256, w, sched=sched),
+        "aggregate bf16": lambda: T.k.aggregate(dg, zb, w, sched=sched),
+        "gat": lambda: T.k.gat_aggregate(dg, el, er, z, sched=sched),
+        "gat online": lambda: T.k.gat_aggregate(dg, el, er, z, sched=sched, bounded=False),
+        "gat bf16": lambda: T.k.gat_aggregate(dg, el, er, zb, sched=sched),
+        "gat 16 heads": lambda: T.k.gat_aggregate(dg, el16, er16, z, sched=sched),
+        "edge sum": lambda: T.k.aggregate_edge_sum(dg, et, z, z, T.cabi.UN_RELU, sched=sched),
+    }
+    dynamic = {k: f().clone() for k, f in runs.items()}
+    monkeypatch.setattr(T.k, "STATIC_MIN_ITEMS", 0)
+    monkeypatch.setattr(T.k, "STATIC_ITEM_EDGES", 1 << 30)
+    for k, f in runs.items():
+        assert T.torch.equal(f(), dynamic[k]), f"{k}: static striding changed the result"
+
+
 def test_generic_edge_and_node_ops(T):
     g = _graph("tiny", 64, 300, 1, 5.0)
     n = g.num_nodes
