@@ -19,7 +19,7 @@ OBJ = os.path.join(CSRC, "_build")
 TAG = os.environ.get("GTA_LIB_TAG", "")
 OBJ = os.path.join(CSRC, "_build" + ("_" + TAG if TAG else ""))
 LIB = os.path.join(HERE, "libgta_b200" + ("_" + TAG if TAG else "") + ".so")
-SOURCES = ["api.cu", "preprocess.cu", "schedule.cu", "aggregate.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "ipc.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "schedule.cu", "aggregate.cu", "gat_aggregate.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "ipc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("GTA_NVCC_DEFS", "").split()
 

@@ -111,7 +111,7 @@ int gta_remap_sources(const int32_t* indices, int64_t num_edges, const int64_t* 
                       int32_t parts, int64_t stride, int32_t rotate, int32_t* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * Exchange of the source-side tables INSIDE the aggregation launch (ipc.cu, aggregate.cu); replaces the
+ * Exchange of the source-side tables INSIDE the aggregation launch (ipc.cu, exchange.cuh, aggregate.cu, gat_aggregate.cu); replaces the
  * per-layer NCCL all-gather of a destination-partitioned run.
  *
  * Every rank owns, per step parity, one gathered table [parts, stride, ld] (gta_ipc_alloc, published to

@@ -123,7 +123,7 @@ def aggregate_edge_sum(g, edge=None, x=None, rowterm=None, unary=_cabi.UN_COPY, 
 
 def gat_aggregate(g, el, er, z, slope=LEAKY_SLOPE, epilogue=_cabi.EPI_ELU, sched=None, out=None,
                   want_stats=False, block_events=None, bounded=True, exchange=None):
-    # the shapes gta_gat_aggregate_f32 takes (csrc/aggregate.cu): the double must refuse what the library refuses, or
+    # the shapes gta_gat_aggregate_f32 takes (csrc/gat_aggregate.cu): the double must refuse what the library refuses, or
     # the CPU fuzz cannot see an executor that routes an unsupported shape to the fused kernel
     f, heads = int(z.shape[1]), int(el.shape[1])
     if f % 4 or f % heads or not ((f // heads) % 4 == 0 or f // heads in (1, 2)):

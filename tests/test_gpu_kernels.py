@@ -359,7 +359,7 @@ def test_static_striding_is_the_same_reduction(T, monkeypatch, chunk, col_block)
     """GTA_PHASE_STATIC (long lists of tiny items, the RMAT shapes: warps stride through the work list instead of
     taking items from the counter) only changes WHO runs an item, never the reduction: every kernel must return the
     bits of the dynamic launch.  Forced here on a small graph by lowering the thresholds of kernels._launch_blocks."""
-    # the library strides statically only when a warp gets at least 32 steps (aggregate.cu take_for): with up to 5 920
+    # the library strides statically only when a warp gets at least 32 steps (aggregate_common.cuh take_for): with up to 5 920
     # resident warps that takes 190 k items -- 400 k rows of about 6 edges give one or more items per row
     g = synthetic.powerlaw_graph(400_000, 2_400_000, seed=3, i0=50.0, name="wide-low-degree")
     n = g.num_nodes
